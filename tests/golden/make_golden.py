@@ -1,0 +1,266 @@
+"""Generate the golden vectors under tests/golden/ from the REFERENCE's own torch CPU path.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is imported unmodified from /root/reference with three stub
+modules for third-party imports that are not on the arithmetic path (mmh3,
+pyevtk, h5py).  Every case stores the exact input
+populations and the reference's output after N steps, so the oracle
+(oracle/lbm_oracle.py) and the CUDA path can both be pinned against it without
+the reference being present.
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    m = types.ModuleType("mmh3")
+    m.hash_bytes = lambda v: hashlib.md5(v.encode() if isinstance(v, str) else v).digest()
+    sys.modules["mmh3"] = m
+    hl = types.ModuleType("pyevtk.hl"); hl.gridToVTK = lambda *a, **k: None
+    pe = types.ModuleType("pyevtk"); pe.hl = hl
+    sys.modules["pyevtk"] = pe; sys.modules["pyevtk.hl"] = hl
+    h5 = types.ModuleType("h5py"); h5.File = None
+    sys.modules["h5py"] = h5
+    sys.path.insert(0, "/root/reference")
+    import lettuce as lt
+    return lt
+
+
+lt = import_reference()
+torch.set_num_threads(1)
+STRATS = {s.name: s for s in lt.StreamingStrategy}
+STENCILS = {"D2Q9": lt.D2Q9, "D3Q19": lt.D3Q19, "D3Q27": lt.D3Q27}
+
+
+def npy(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def make_collision(kind, flow, tau_minus=1.0):
+    tau = flow.units.relaxation_parameter_lu
+    return {"bgk": lambda: lt.BGKCollision(tau), "trt": lambda: lt.TRTCollision(tau, tau_minus),
+            "kbc": lambda: lt.KBCCollision(), "none": lambda: lt.NoCollision()}[kind]()
+
+
+# ---------------------------------------------------------------- TGV cases
+def tgv_case(name, stencil, res, re, ma, coll, steps, strategies, dtype=torch.float64, observables=False,
+             perturb=0.0):
+    """`perturb` > 0 multiplies the initial populations by (1 + perturb * uniform(-.5,.5)) with a fixed seed.
+    Needed for D2Q9 KBC: the analytic f_neq initialisation has no higher-order part, so KBC's
+    sum_h is pure rounding noise on the first step and gamma (kbc_collision.py:152) is ill-conditioned."""
+    out = {}
+    out["perturbed"] = np.array(perturb > 0)
+    for sname in strategies:
+        ctx = lt.Context(device="cpu", dtype=dtype, use_native=False)
+        flow = lt.TaylorGreenVortex(ctx, list(res), re, ma, stencil=STENCILS[stencil]())
+        if perturb > 0:
+            rng = np.random.default_rng(7)
+            flow.f = flow.f * ctx.convert_to_tensor(1.0 + perturb * (rng.random(tuple(flow.f.shape)) - 0.5))
+        out["f0"] = npy(flow.f)
+        out["tau"] = np.float64(flow.units.relaxation_parameter_lu)
+        sim = lt.Simulation(flow, make_collision(coll, flow), [], STRATS[sname])
+        sim(steps)
+        out["f_" + sname] = npy(flow.f)
+        if observables:
+            out["energy_" + sname] = npy(lt.IncompressibleKineticEnergy(flow)(flow.f))
+            out["enstrophy_" + sname] = npy(lt.Enstrophy(flow)(flow.f))
+            out["maxvel_" + sname] = npy(lt.MaximumVelocity(flow)(flow.f))
+            out["mass_" + sname] = npy(lt.Mass(flow)(flow.f))
+            out["rho_" + sname] = npy(flow.rho())
+            out["u_" + sname] = npy(flow.u())
+    out["meta"] = np.array([stencil, coll, str(steps), str(re), str(ma)])
+    out["res"] = np.array(res)
+    save(name, **out)
+
+
+# ---------------------------------------------------------------- obstacle cases (BASELINE.md section 5 helper)
+class ObstacleEqOut(lt.Obstacle):
+    @property
+    def post_boundaries(self):
+        x = self.grid[0]
+        return [lt.EquilibriumBoundaryPU(flow=self, context=self.context, mask=torch.abs(x) < 1e-6,
+                                         velocity=self.units.characteristic_velocity_pu * self._unit_vector()),
+                lt.EquilibriumOutletP(direction=self._unit_vector().tolist(), flow=self, rho_outlet=1.0),
+                lt.BounceBackBoundary(self.mask)]
+
+
+def make_obstacle(cls, ctx, res, stencil):
+    D = res[1] / 8
+    flow = cls(ctx, list(res), reynolds_number=100, mach_number=0.05,
+               domain_length_x=res[0] / D, stencil=stencil)
+    g = flow.grid
+    c = [0.25 * g[0].max()] + [0.5 * gi.max() for gi in g[1:]]
+    flow.mask = sum((gi - ci) ** 2 for gi, ci in zip(g, c)) < 0.5 ** 2
+    return flow
+
+
+def obstacle_case(name, cls, stencil, res, coll, steps, strategies, dtype=torch.float64):
+    out = {}
+    for sname in strategies:
+        ctx = lt.Context(device="cpu", dtype=dtype, use_native=False)
+        flow = make_obstacle(cls, ctx, res, STENCILS[stencil]())
+        flow.initialize()                      # mask was set after __init__; re-initialise like a user would
+        out["f0"] = npy(flow.f)
+        out["solid"] = npy(flow.mask)
+        out["tau"] = np.float64(flow.units.relaxation_parameter_lu)
+        sim = lt.Simulation(flow, make_collision(coll, flow), [], STRATS[sname])
+        out["ncm"] = npy(sim.no_collision_mask)
+        out["nsm"] = npy(sim.no_streaming_mask)
+        sim(steps)
+        out["f_" + sname] = npy(flow.f)
+        out["mass_" + sname] = npy(lt.Mass(flow, no_mass_mask=flow.mask)(flow.f))
+    out["meta"] = np.array([stencil, coll, str(steps), "100", "0.05"])
+    out["res"] = np.array(res)
+    save(name, **out)
+
+
+# ---------------------------------------------------------------- single-operator known answers on random f
+class RandomFlow(lt.ExtFlow):
+    """Uniform-resolution flow whose populations are overwritten by the caller."""
+
+    def make_resolution(self, resolution, stencil=None):
+        return resolution
+
+    def make_units(self, reynolds_number, mach_number, resolution):
+        return lt.UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                                 characteristic_length_lu=resolution[0])
+
+    def initial_pu(self):
+        d = len(self.resolution)
+        return np.zeros((1, *self.resolution)), np.zeros((d, *self.resolution))
+
+    @property
+    def post_boundaries(self):
+        return []
+
+
+def random_collision_case():
+    out = {}
+    rng = np.random.default_rng(20261017)
+    for stencil, res in (("D2Q9", [6, 5]), ("D3Q19", [4, 5, 6]), ("D3Q27", [4, 5, 6])):
+        ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+        flow = RandomFlow(ctx, res, 50.0, 0.1, stencil=STENCILS[stencil]())
+        w = np.asarray(flow.stencil.w).reshape((-1,) + (1,) * len(res))
+        f0 = w * (1.0 + 0.2 * (rng.random((flow.stencil.q, *res)) - 0.5))
+        out[f"{stencil}_f0"] = f0
+        out[f"{stencil}_tau"] = np.float64(flow.units.relaxation_parameter_lu)
+        for coll in ("bgk", "trt", "kbc"):
+            if coll == "kbc" and stencil == "D3Q19":
+                continue
+            flow.f = ctx.convert_to_tensor(f0)
+            c = make_collision(coll, flow, tau_minus=0.8)
+            out[f"{stencil}_{coll}"] = npy(c(flow))
+        flow.f = ctx.convert_to_tensor(f0)
+        out[f"{stencil}_rho"] = npy(flow.rho())
+        out[f"{stencil}_u"] = npy(flow.u())
+        out[f"{stencil}_feq"] = npy(flow.equilibrium(flow))
+    save("random_collisions", **out)
+
+
+# ---------------------------------------------------------------- the reference's own native known-answer cases
+class Dummy16(RandomFlow):
+    pass
+
+
+def native_known_answers():
+    """Torch-path side of tests/native/*.py (16x16 D2Q9)."""
+    out = {}
+    ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+
+    def fresh():
+        return Dummy16(ctx, [16, 16], 1.0, 0.05, stencil=lt.D2Q9())
+
+    # tests/native/test_native_streaming.py:9-51 : nine tagged populations move by e_q
+    flow = fresh(); flow.f[:] = 0.0
+    for q in range(9):
+        flow.f[q, 1, 1] = q + 1.0
+    out["streaming_f0"] = npy(flow.f)
+    lt.Simulation(flow, lt.NoCollision(), [])(1)
+    out["streaming_f1"] = npy(flow.f)
+
+    # tests/native/test_native_bgk_collision.py:26-71 and test_native_streaming_strategy.py:9-59
+    for sname in STRATS:
+        flow = fresh(); flow.f[:] = 1.0; flow.f[:, 2, 2] = 2.0
+        out["bgk_f0"] = npy(flow.f)
+        lt.Simulation(flow, lt.BGKCollision(2.0), [], STRATS[sname])(1)
+        out["bgk_f1_" + sname] = npy(flow.f)
+
+    # tests/native/test_native_bounce_back.py:11-74 : bounce-back everywhere but node (1,1), two steps
+    class BB(lt.BounceBackBoundary):
+        def make_no_collision_mask(self, shape, context):
+            m = context.zero_tensor(shape, dtype=bool)
+            m[0, :] = True; m[:, 0] = True; m[2:, :] = True; m[:, 2:] = True
+            return m
+
+    class BBFlow(Dummy16):
+        @property
+        def post_boundaries(self):
+            return [BB(torch.ones(self.resolution))]
+
+    flow = BBFlow(ctx, [16, 16], 1.0, 0.05, stencil=lt.D2Q9()); flow.f[:] = 0.0; flow.f[:, 1, 1] = 1.0
+    out["bb_f0"] = npy(flow.f)
+    sim = lt.Simulation(flow, lt.NoCollision(), [])
+    sim(1); out["bb_f1"] = npy(flow.f)
+    sim(1); out["bb_f2"] = npy(flow.f)
+
+    # tests/native/test_native_equilibrium_pu.py:12-71 : equilibrium boundary + all-ones no-stream mask
+    class EQ(lt.EquilibriumBoundaryPU):
+        def make_no_streaming_mask(self, shape, context):
+            return context.one_tensor(shape, dtype=bool)
+
+    class EQFlow(Dummy16):
+        @property
+        def post_boundaries(self):
+            m = torch.zeros(self.resolution, dtype=torch.bool); m[:, 3:5] = True
+            return [EQ(self.context, self, m, velocity=[0.1, 0.05], pressure=0.02)]
+
+    flow = EQFlow(ctx, [16, 16], 1.0, 0.05, stencil=lt.D2Q9())
+    flow.f[:] = torch.rand(flow.f.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64) + 0.5
+    out["eq_f0"] = npy(flow.f)
+    lt.Simulation(flow, lt.NoCollision(), [])(1)
+    out["eq_f1"] = npy(flow.f)
+    save("native_known_answers", **out)
+
+
+def stock_obstacle_case():
+    """Stock lt.Obstacle (AntiBounceBackOutlet default, lettuce/ext/_flows/obstacle.py:107-122)."""
+    obstacle_case("obstacle2d_abb_bgk", lt.Obstacle, "D2Q9", [48, 16], "bgk", 20, ["POST_STREAMING"])
+    obstacle_case("obstacle3d_abb_bgk", lt.Obstacle, "D3Q19", [24, 12, 12], "bgk", 8, ["POST_STREAMING"])
+
+
+if __name__ == "__main__":
+    all4 = list(STRATS)
+    tgv_case("tgv2d_d2q9_bgk", "D2Q9", [24, 24], 1.0, 0.05, "bgk", 10, all4, observables=True)
+    tgv_case("tgv3d_d3q19_bgk", "D3Q19", [12, 12, 12], 1600.0, 0.05, "bgk", 10, all4, observables=True)
+    tgv_case("tgv3d_d3q27_kbc", "D3Q27", [12, 10, 8], 1600.0, 0.05, "kbc", 10, ["POST_STREAMING", "PRE_STREAMING"],
+             observables=True)
+    tgv_case("tgv2d_d2q9_kbc", "D2Q9", [20, 16], 800.0, 0.1, "kbc", 10, ["POST_STREAMING"], perturb=1e-3)
+    tgv_case("tgv3d_d3q27_trt", "D3Q27", [10, 12, 8], 400.0, 0.05, "trt", 6, ["POST_STREAMING", "PRE_STREAMING"])
+    tgv_case("tgv3d_d3q19_trt", "D3Q19", [8, 8, 12], 400.0, 0.05, "trt", 6, ["POST_STREAMING"])
+    tgv_case("tgv3d_d3q19_bgk_fp32", "D3Q19", [12, 12, 12], 1600.0, 0.05, "bgk", 10, ["POST_STREAMING"],
+             dtype=torch.float32)
+    obstacle_case("cylinder_d2q9_bgk", ObstacleEqOut, "D2Q9", [64, 16], "bgk", 30, all4)
+    obstacle_case("sphere_d3q27_trt", ObstacleEqOut, "D3Q27", [32, 16, 16], "trt", 10,
+                  ["POST_STREAMING", "PRE_STREAMING"])
+    obstacle_case("sphere_d3q19_bgk", ObstacleEqOut, "D3Q19", [32, 16, 16], "bgk", 10, ["POST_STREAMING"])
+    obstacle_case("cylinder_d2q9_kbc", ObstacleEqOut, "D2Q9", [64, 16], "kbc", 20, ["POST_STREAMING"])
+    stock_obstacle_case()
+    random_collision_case()
+    native_known_answers()
