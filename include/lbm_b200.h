@@ -1,0 +1,202 @@
+/* lbm_b200.h -- C ABI of the B200-native lattice-Boltzmann stream+collide engine.
+ *
+ * This is the drop-in boundary for lettuce's hot path.  It replaces the run-time
+ * generated torch extension of the reference:
+ *
+ *   reference interface                                           replaced by
+ *   -----------------------------------------------------------   ------------------------
+ *   cuda_native.lettuce(f, [ncm,] tau_inv..., [nsm,] f_next)      lbm_step()
+ *     (lettuce/cuda_native/_template.py:42-53,72-81; generated
+ *      kernel body lettuce/cuda_native/_default_code_gen.py:285-316)
+ *   invoke(simulation) python shim (_template.py:35-39)           lettuce_b200.native.invoke()
+ *   Simulation.__init__ mask build (_simulation.py:100-146)       lbm_pack_masks()
+ *   Flow.rho / Flow.j / Flow.u (lettuce/_flow.py:157-193)         lbm_moments()
+ *   reporter reductions (ext/_reporter/observable_reporter.py     lbm_reduce()
+ *     :27-68,140-158; util/utility.py:37-99 order=6)
+ *   Simulation.__call__ with host-resident populations            lbm_run_host()
+ *     (_simulation.py:311-323)
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All pointers named
+ * `d_*` or documented as "device" are CUDA device pointers of the current
+ * device; `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream).  Functions never synchronise the device unless stated, never throw,
+ * and return LBM_OK (0) or a negative lbm_status.  Buffers are borrowed for
+ * the duration of the call only (ownership stays with the caller, as in the
+ * reference where Python owns every tensor, _default_code_gen.py:117-145).
+ *
+ * Memory layout: populations are `real f[q][nx][ny][nz]`, q slowest, z fastest,
+ * exactly lettuce's `flow.f` (lettuce/_flow.py:92); 2-D lattices use nz = 1 and
+ * `f[q][nx][ny]`.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_ABI_VERSION 1
+#define LBM_MAX_OPS 8 /* transformer list length: pre_boundaries + collision + post_boundaries */
+
+typedef enum lbm_status {
+    LBM_OK = 0,
+    LBM_ERR_BAD_ARGUMENT = -1, /* NULL pointer, non-positive extent, bad enum value */
+    LBM_ERR_UNSUPPORTED = -2,  /* valid request the engine has no kernel for (e.g. KBC on D3Q19) */
+    LBM_ERR_CUDA = -3,         /* a CUDA runtime call failed; see lbm_last_cuda_error() */
+    LBM_ERR_ALIASING = -4,     /* f_in and f_out overlap */
+    LBM_ERR_TOO_LARGE = -5     /* nx*ny*nz does not fit 31 bits */
+} lbm_status;
+
+/* lettuce/ext/_stencil/{d2q9,d3q19,d3q27}.py; velocity order, weights and opposite
+ * tables are lettuce's. */
+typedef enum lbm_stencil { LBM_D2Q9 = 0, LBM_D3Q19 = 1, LBM_D3Q27 = 2 } lbm_stencil;
+
+typedef enum lbm_dtype { LBM_F32 = 0, LBM_F64 = 1 } lbm_dtype;
+
+/* Same bit values as lettuce's StreamingStrategy (cuda_native/_default_code_gen.py:13-25):
+ * bit 1 = stream before the collide phase, bit 0 = stream after it. */
+typedef enum lbm_streaming {
+    LBM_NO_STREAMING = 0,
+    LBM_POST_STREAMING = 1,
+    LBM_PRE_STREAMING = 2,
+    LBM_DOUBLE_STREAMING = 3
+} lbm_streaming;
+
+typedef enum lbm_op_kind {
+    LBM_OP_NO_COLLISION = 0, /* ext/_collision/no_collision.py:9-11 */
+    LBM_OP_BGK = 1,          /* ext/_collision/bgk_collision.py:17-22 (force = None); p0 = tau */
+    LBM_OP_TRT = 2,          /* ext/_collision/trt_collision.py:16-27; p0 = tau_plus, p1 = tau_minus */
+    LBM_OP_KBC = 3,          /* ext/_collision/kbc_collision.py:96-160; p0 = tau (units.relaxation_parameter_lu) */
+    LBM_OP_BOUNCE_BACK = 16, /* ext/_boundary/bounce_back_boundary.py:10-32 */
+    LBM_OP_EQUILIBRIUM = 17, /* ext/_boundary/equilibrium_boundary_pu.py:79-84, values already in lattice units */
+    LBM_OP_OUTLET_P = 18,    /* ext/_boundary/equilibrium_outlet_p.py:63-73; p0 = rho_outlet */
+    LBM_OP_ANTI_BOUNCE_BACK = 19 /* ext/_boundary/anti_bounce_back_outlet.py:71-91 */
+} lbm_op_kind;
+
+/* One entry of the transformer list (lettuce/_simulation.py:70).  Entry i acts on
+ * the nodes whose label equals i; outlet kinds additionally act on their whole
+ * boundary plane irrespective of the label. */
+typedef struct lbm_op {
+    int32_t kind;  /* lbm_op_kind */
+    int32_t axis;  /* outlets: 0 = x, 1 = y, 2 = z */
+    int32_t side;  /* outlets: +1 = plane n-1 (neighbour n-2), -1 = plane 0 (neighbour 1) */
+    int32_t _pad;
+    double p0, p1; /* see lbm_op_kind */
+    /* LBM_OP_EQUILIBRIUM: density and velocity in lattice units, dtype of the lattice.
+     * Element strides per spatial axis x,y,z (0 broadcasts that axis); u has an
+     * additional component stride.  This mirrors checked_tensor's broadcast rules
+     * (equilibrium_boundary_pu.py:23-69). */
+    const void *rho;
+    const void *u;
+    int64_t rho_stride[3];
+    int64_t u_stride[4]; /* component, x, y, z */
+} lbm_op;
+
+/* Geometry of the slab of lattice this call works on. */
+typedef struct lbm_lattice {
+    int32_t stencil; /* lbm_stencil */
+    int32_t dtype;   /* lbm_dtype */
+    int32_t nx, ny, nz; /* nz = 1 for D2Q9 */
+    int32_t _pad;
+} lbm_lattice;
+
+/* Planes adjacent to the slab in x.  Single GPU / periodic: leave all NULL and the
+ * engine wraps around inside the buffer.  Multi-GPU x-slabs: `lo` is the plane at
+ * local x = -1 (last plane of the left neighbour), `hi` the plane at x = nx (first
+ * plane of the right neighbour); they may be peer-mapped device pointers, the
+ * kernel then loads / stores them directly over NVLink.  Each pointer addresses
+ * population 0 of that plane; population q is `q_stride` elements further. */
+typedef struct lbm_halo {
+    const void *in_lo;
+    const void *in_hi;
+    void *out_lo;
+    void *out_hi;
+    int64_t in_lo_qstride, in_hi_qstride, out_lo_qstride, out_hi_qstride;
+    /* labels / frozen-slot words of the neighbour planes (masked runs only) */
+    const uint8_t *label_lo;
+    const uint8_t *label_hi;
+    const uint32_t *frozen_lo;
+    const uint32_t *frozen_hi;
+} lbm_halo;
+
+typedef struct lbm_step_desc {
+    lbm_lattice lat;
+    int32_t streaming; /* lbm_streaming */
+    int32_t n_ops;     /* 1 <= n_ops <= LBM_MAX_OPS */
+    int32_t collision_index; /* index of the collision entry in ops (= number of pre-boundaries) */
+    int32_t variant;   /* kernel variant hint: 0 = auto */
+    lbm_op ops[LBM_MAX_OPS];
+    /* Masked runs (any boundary present): per-node label byte produced by
+     * lbm_pack_masks() and one frozen-slot word per node (bit q set = slot (q,node) is
+     * not overwritten by streaming).  Both NULL for unmasked runs. */
+    const uint8_t *labels;
+    const uint32_t *frozen;
+    lbm_halo halo;
+} lbm_step_desc;
+
+/* One time step: f_out = Step(f_in) for desc->streaming, reading f_in once and writing
+ * f_out once.  f_in and f_out must not overlap.  Launches on `stream`, does not sync. */
+int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream);
+
+/* `n` consecutive steps ping-ponging between two buffers (a -> b -> a ...), without returning
+ * to the caller in between: the loop `for _ in range(num_steps)` of Simulation.__call__
+ * (lettuce/_simulation.py:317-318) when no reporter is due.  The newest populations end up in
+ * d_f_b if n is odd and in d_f_a if n is even. */
+int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream);
+
+/* Builds the per-node label byte and frozen-slot word from lettuce's masks
+ * (`no_collision_mask` uint8 [nx,ny,nz] and `no_streaming_mask` uint8 [q,nx,ny,nz],
+ * lettuce/_simulation.py:100-146).  label = ncm value, with bit 7 set on every node
+ * that needs the general path: a frozen slot of its own, a neighbour slot it would
+ * stream into that is frozen, or membership in an outlet plane of `desc`. */
+int lbm_pack_masks(const lbm_step_desc *desc, const uint8_t *d_ncm, const uint8_t *d_nsm,
+                   uint8_t *d_labels, uint32_t *d_frozen, void *stream);
+
+/* Density [nx,ny,nz] and velocity [d,nx,ny,nz] fields (either may be NULL). */
+int lbm_moments(const lbm_lattice *lat, const void *d_f, void *d_rho, void *d_u, void *stream);
+
+typedef enum lbm_reduction {
+    LBM_SUM_HALF_U2 = 0, /* sum over nodes of 0.5*|u|^2 in lattice units (_flow.py:200-204) */
+    LBM_MAX_U = 1,       /* max over nodes of |u| in lattice units (observable_reporter.py:27-31) */
+    LBM_SUM_F = 2,       /* sum of all populations */
+    LBM_SUM_F_INNER = 3, /* sum of f[..., 1:-1, 1:-1] (observable_reporter.py:155) */
+    LBM_SUM_F_MASKED = 4,/* sum over q and nodes of f*mask, mask uint8 [nx,ny,nz] (observable_reporter.py:157) */
+    LBM_ENSTROPHY = 5    /* sum of |curl u|^2 with 6th-order periodic differences, lattice units,
+                            dx = 1 (observable_reporter.py:45-68, util/utility.py:56-58,88-98);
+                            needs d_u from lbm_moments */
+} lbm_reduction;
+
+/* Bytes of scratch lbm_reduce needs for this lattice. */
+size_t lbm_reduce_scratch_bytes(const lbm_lattice *lat);
+
+/* Deterministic two-stage reduction.  `d_in` is f for the SUM_F*, SUM_HALF_U2 and MAX_U
+ * kinds and the velocity field [d,nx,ny,nz] for LBM_ENSTROPHY.  The result is written as
+ * ONE double to d_out (device). */
+int lbm_reduce(const lbm_lattice *lat, int what, const void *d_in, const uint8_t *d_mask,
+               void *d_scratch, double *d_out, void *stream);
+
+/* End-to-end entry with HOST buffers: uploads h_f (q*nx*ny*nz reals) to the device,
+ * runs `nsteps` time steps of `desc` (desc->labels/frozen and op field pointers are
+ * device pointers as for lbm_step; halo must be all NULL), downloads the final
+ * populations into h_f_out and synchronises.  If h_energy is non-NULL it must hold
+ * nsteps doubles and receives sum 0.5|u|^2 after every step (a reporter with
+ * interval 1).  Device scratch is allocated and freed inside the call. */
+int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int64_t nsteps,
+                 double *h_energy);
+
+/* Introspection. */
+int lbm_abi_version(void);
+const char *lbm_status_string(int status);
+const char *lbm_last_cuda_error(void);
+/* Number of kernel launches this library has issued since load (all streams). */
+int64_t lbm_launch_count(void);
+/* Name of the kernel variant lbm_step would launch for desc (static string). */
+const char *lbm_step_variant_name(const lbm_step_desc *desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,173 @@
+"""Simulation driver (API of lettuce/_simulation.py:17-344).
+
+The step itself is `native.invoke` -- one fused CUDA kernel launch per time step -- installed
+on `Simulation._collide_and_stream`, the attribute through which the reference plugs in its
+generated extension (lettuce/_simulation.py:229).  User subclasses that re-assign that
+attribute keep working.  There is no torch implementation of collide/stream here.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from enum import Enum
+from timeit import default_timer as timer
+from typing import List, Optional
+
+import torch
+
+from . import native
+
+__all__ = ["Collision", "Reporter", "Simulation", "BreakableSimulation", "StreamingStrategy"]
+
+
+class StreamingStrategy(Enum):
+    """bit 1: stream before the collide phase, bit 0: after it
+    (lettuce/cuda_native/_default_code_gen.py:13-25)"""
+    NO_STREAMING = 0b00
+    PRE_STREAMING = 0b10
+    POST_STREAMING = 0b01
+    DOUBLE_STREAMING = 0b11
+
+    def pre_streaming(self) -> bool:
+        return bool(self.value & 0b10)
+
+    def post_streaming(self) -> bool:
+        return bool(self.value & 0b01)
+
+
+class Collision(ABC):
+    """Collision operators are parameter holders for the fused kernel; `native_available`
+    keeps the reference's query (lettuce/_simulation.py:17-28)."""
+
+    def native_available(self) -> bool:
+        try:
+            native.op_kind(self)
+            return True
+        except NotImplementedError:
+            return False
+
+
+class Reporter(ABC):
+    interval: int
+    # True when the reporter only acts on steps with flow.i % interval == 0, so the driver may run
+    # the steps in between without calling it
+    batchable = False
+
+    def __init__(self, interval: int):
+        self.interval = interval
+
+    @abstractmethod
+    def __call__(self, simulation: "Simulation"):
+        ...
+
+
+class Simulation:
+    def __init__(self, flow, collision, reporter: List[Reporter],
+                 streaming_strategy: StreamingStrategy = StreamingStrategy.POST_STREAMING):
+        self.flow = flow
+        self.flow.collision = collision
+        self.context = flow.context
+        self.collision = collision
+        self.reporter = reporter
+        self.streaming_strategy = streaming_strategy
+        # boundaries are read once each; flows build fresh objects per access (obstacle.py:107-122)
+        self.pre_boundaries = list(flow.pre_boundaries or [])
+        self.post_boundaries = list(flow.post_boundaries or [])
+        self.collision_index = len(self.pre_boundaries)
+        self.transformer = self.pre_boundaries + [collision] + self.post_boundaries
+        self.no_collision_mask: Optional[torch.Tensor] = None
+        self.no_streaming_mask: Optional[torch.Tensor] = None
+        self._build_masks()
+        self._collide_and_stream = native.invoke
+
+    def _build_masks(self):
+        """Label field and no-stream mask (lettuce/_simulation.py:100-146): `no_collision_mask`
+        holds, per node, the index of the transformer entry acting there (later boundaries win);
+        `no_streaming_mask` is the OR of the boundaries' masks.  As in the reference both start
+        out filled with `collision_index`."""
+        boundaries = self.pre_boundaries + self.post_boundaries
+        if not boundaries:
+            return
+        flow, ctx = self.flow, self.context
+        shape = [int(s) for s in flow.f.shape]
+        self.no_collision_mask = ctx.full_tensor(shape[1:], self.collision_index, dtype=torch.uint8)
+        self.no_streaming_mask = ctx.full_tensor(shape, self.collision_index, dtype=torch.uint8)
+        labels = list(range(len(self.pre_boundaries))) + \
+            list(range(self.collision_index + 1, self.collision_index + 1 + len(self.post_boundaries)))
+        for label, boundary in zip(labels, boundaries):
+            ncm = boundary.make_no_collision_mask(shape[1:], context=ctx)
+            if ncm is not None:
+                self.no_collision_mask[ncm.to(device=ctx.device, dtype=torch.bool)] = label
+            nsm = boundary.make_no_streaming_mask(shape, context=ctx)
+            if nsm is not None:
+                self.no_streaming_mask |= nsm.to(device=ctx.device, dtype=torch.uint8)
+
+    @property
+    def units(self):
+        return self.flow.units
+
+    def step(self, num_steps: int):
+        return self(num_steps)
+
+    def _report(self):
+        for reporter in self.reporter:
+            reporter(self)
+
+    def _batch_length(self, remaining: int) -> int:
+        """Number of steps that can run before any reporter has to see the state."""
+        if self._collide_and_stream is not native.invoke:
+            return 1
+        k = remaining
+        for r in self.reporter:
+            if not getattr(r, "batchable", False):
+                return 1
+            interval = max(int(r.interval), 1)
+            k = min(k, interval - self.flow.i % interval)
+        return max(k, 1)
+
+    def __call__(self, num_steps: int) -> float:
+        """Run `num_steps` time steps; returns MLUPS (lettuce/_simulation.py:311-323).  The
+        device is synchronised before the clock is read."""
+        self.context.synchronize()
+        beg = timer()
+        if self.flow.i == 0:
+            self._report()
+        remaining = int(num_steps)
+        while remaining > 0:
+            k = self._batch_length(remaining)
+            if k == 1:
+                self._collide_and_stream(self)
+            else:
+                native.invoke_n(self, k)
+            self.flow.i += k
+            self._report()
+            remaining -= k
+        self.context.synchronize()
+        end = timer()
+        nodes = 1
+        for n in self.flow.resolution:
+            nodes *= int(n)
+        return num_steps * nodes / 1e6 / (end - beg)
+
+
+class BreakableSimulation(Simulation):
+    """Runs until `flow.i` reaches `num_steps`; reporters may push `flow.i` past it to abort
+    (lettuce/_simulation.py:325-344)."""
+
+    def __init__(self, flow, collision, reporter: List[Reporter]):
+        super().__init__(flow, collision, reporter)
+
+    def __call__(self, num_steps: int) -> float:
+        self.context.synchronize()
+        beg = timer()
+        if self.flow.i == 0:
+            self._report()
+        while self.flow.i < num_steps:
+            self._collide_and_stream(self)
+            self.flow.i += 1
+            self._report()
+        self.context.synchronize()
+        end = timer()
+        nodes = 1
+        for n in self.flow.resolution:
+            nodes *= int(n)
+        return num_steps * nodes / 1e6 / (end - beg)

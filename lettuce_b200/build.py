@@ -1,0 +1,105 @@
+"""Ahead-of-time build of liblbm_b200.so (sm_100a) with plain nvcc.
+
+No per-configuration JIT (the reference generates and compiles one extension per
+(stencil, strategy, operator list), lettuce/cuda_native/_generator.py:99-127):
+every (stencil, dtype, collision, streaming, masked) variant is template-instantiated
+once and selected at run time from the descriptor.  The six (stencil, dtype) pairs
+are separate translation units and compile in parallel.
+
+    python -m lettuce_b200.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+ROOT = os.path.dirname(PKG)
+OBJ = os.path.join(PKG, "build")
+LIB = os.path.join(PKG, "liblbm_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
+
+STENCILS = ("D2Q9", "D3Q19", "D3Q27")
+REALS = ("float", "double")
+
+
+def _units():
+    units = [("lbm_api", os.path.join(CSRC, "lbm_api.cu"), []),
+             ("lbm_moments", os.path.join(CSRC, "lbm_moments.cu"), [])]
+    for s in STENCILS:
+        for r in REALS:
+            units.append((f"lbm_step_{s}_{r}", os.path.join(CSRC, "lbm_step_inst.cu"),
+                          [f"-DLBM_INST_STENCIL={s}", f"-DLBM_INST_REAL={r}"]))
+    return units
+
+
+def _headers_hash() -> "hashlib._Hash":
+    h = hashlib.sha256()
+    for d in (CSRC, os.path.join(ROOT, "include")):
+        for name in sorted(os.listdir(d)):
+            if name.endswith((".cuh", ".h")):
+                with open(os.path.join(d, name), "rb") as fh:
+                    h.update(name.encode() + b"\0" + fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h
+
+
+def _unit_hash(unit) -> str:
+    name, src, defs = unit
+    h = _headers_hash()
+    with open(src, "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(defs).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if sources changed) and return the path of the shared library."""
+    os.makedirs(OBJ, exist_ok=True)
+    units = _units()
+    digests = {u[0]: _unit_hash(u) for u in units}
+    stamp = os.path.join(OBJ, "source.sha256")
+    digest = hashlib.sha256("".join(sorted(digests.values())).encode()).hexdigest()
+    if (not force and os.path.exists(LIB) and os.path.exists(stamp)
+            and open(stamp).read().strip() == digest):
+        return LIB
+
+    def compile_one(unit):
+        name, src, defs = unit
+        obj = os.path.join(OBJ, name + ".o")
+        ustamp = obj + ".sha256"
+        if (not force and os.path.exists(obj) and os.path.exists(ustamp)
+                and open(ustamp).read().strip() == digests[name]):
+            return obj
+        cmd = [NVCC, *FLAGS, *defs, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {name}:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        with open(ustamp, "w") as fh:
+            fh.write(digests[name])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, units))
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as fh:
+        fh.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,360 @@
+// lbm_api.cu -- the C ABI declared in include/lbm_b200.h: argument validation,
+// descriptor -> kernel-parameter translation, dispatch, mask packing, host-buffer
+// end-to-end entry.
+#include <cstdio>
+#include <cstring>
+
+#include "lbm_launch.cuh"
+
+namespace lbm {
+
+int64_t g_launch_count = 0;
+static thread_local char g_cuda_error[256] = "";
+
+template <class S, class R>
+int launch_moments(const R *f, R *rho, R *u, int64_t N, cudaStream_t st);
+template <class S, class R>
+int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, int n2, double *partials, double *out,
+                  cudaStream_t st);
+size_t reduce_scratch_bytes();
+
+static int cuda_fail(int e) {
+    if (e <= 0) return e;  // already an lbm_status
+    snprintf(g_cuda_error, sizeof g_cuda_error, "%s: %s", cudaGetErrorName((cudaError_t)e),
+             cudaGetErrorString((cudaError_t)e));
+    return LBM_ERR_CUDA;
+}
+
+struct Dims {
+    int n0, n1, n2, d, q;
+};
+
+static int lattice_dims(const lbm_lattice *lat, Dims &dm) {
+    if (!lat) return LBM_ERR_BAD_ARGUMENT;
+    if (lat->dtype != LBM_F32 && lat->dtype != LBM_F64) return LBM_ERR_BAD_ARGUMENT;
+    if (lat->nx < 1 || lat->ny < 1 || lat->nz < 1) return LBM_ERR_BAD_ARGUMENT;
+    switch (lat->stencil) {
+        case LBM_D2Q9:
+            if (lat->nz != 1) return LBM_ERR_BAD_ARGUMENT;
+            dm = {lat->nx, 1, lat->ny, 2, 9};  // (x, -, y): contiguous axis last
+            break;
+        case LBM_D3Q19: dm = {lat->nx, lat->ny, lat->nz, 3, 19}; break;
+        case LBM_D3Q27: dm = {lat->nx, lat->ny, lat->nz, 3, 27}; break;
+        default: return LBM_ERR_BAD_ARGUMENT;
+    }
+    if ((int64_t)dm.n0 * dm.n1 * dm.n2 >= (int64_t)1 << 31) return LBM_ERR_TOO_LARGE;
+    return LBM_OK;
+}
+
+static bool is_collision(int kind) { return kind >= LBM_OP_NO_COLLISION && kind <= LBM_OP_KBC; }
+static bool is_outlet(int kind) { return kind == LBM_OP_OUTLET_P || kind == LBM_OP_ANTI_BOUNCE_BACK; }
+
+static int validate_desc(const lbm_step_desc *d, Dims &dm) {
+    if (!d) return LBM_ERR_BAD_ARGUMENT;
+    int rc = lattice_dims(&d->lat, dm);
+    if (rc) return rc;
+    if (d->streaming < 0 || d->streaming > 3) return LBM_ERR_BAD_ARGUMENT;
+    if (d->n_ops < 1 || d->n_ops > LBM_MAX_OPS) return LBM_ERR_BAD_ARGUMENT;
+    if (d->collision_index < 0 || d->collision_index >= d->n_ops) return LBM_ERR_BAD_ARGUMENT;
+    if (!is_collision(d->ops[d->collision_index].kind)) return LBM_ERR_BAD_ARGUMENT;
+    for (int i = 0; i < d->n_ops; ++i) {
+        const lbm_op &op = d->ops[i];
+        if (i != d->collision_index && is_collision(op.kind)) return LBM_ERR_BAD_ARGUMENT;
+        if (i != d->collision_index && op.kind != LBM_OP_BOUNCE_BACK && op.kind != LBM_OP_EQUILIBRIUM &&
+            !is_outlet(op.kind))
+            return LBM_ERR_BAD_ARGUMENT;
+        if (op.kind == LBM_OP_EQUILIBRIUM && (!op.rho || !op.u)) return LBM_ERR_BAD_ARGUMENT;
+        if (is_outlet(op.kind)) {
+            if (op.axis < 0 || op.axis >= dm.d || (op.side != 1 && op.side != -1 && op.side != 0))
+                return LBM_ERR_BAD_ARGUMENT;
+            const int n = op.axis == 0 ? d->lat.nx : (op.axis == 1 ? d->lat.ny : d->lat.nz);
+            if (n < 2) return LBM_ERR_BAD_ARGUMENT;
+            // The neighbour of an outlet node is evaluated with node-local operators only; an earlier
+            // outlet acting on that neighbour (two outlets on different axes, or on both ends of a
+            // 3-plane axis) would need a second level of look-up.
+            for (int k = 0; k < i; ++k) {
+                if (!is_outlet(d->ops[k].kind) || d->ops[k].side == 0 || op.side == 0) continue;
+                if (d->ops[k].axis != op.axis) return LBM_ERR_UNSUPPORTED;
+                const int here_k = d->ops[k].side > 0 ? n - 1 : 0;
+                const int nb_i = op.side > 0 ? n - 2 : 1;
+                if (here_k == nb_i) return LBM_ERR_UNSUPPORTED;
+            }
+        }
+    }
+    if (d->n_ops > 1 && (!d->labels || !d->frozen)) return LBM_ERR_BAD_ARGUMENT;
+    if (d->ops[d->collision_index].kind == LBM_OP_KBC && d->lat.stencil == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
+    return LBM_OK;
+}
+
+template <class S, class R>
+static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, StepParams<R> &p) {
+    memset(&p, 0, sizeof p);
+    p.in = (const R *)f_in;
+    p.out = (R *)f_out;
+    p.n0 = dm.n0; p.n1 = dm.n1; p.n2 = dm.n2;
+    p.N = (int64_t)dm.n0 * dm.n1 * dm.n2;
+    const int64_t plane = (int64_t)dm.n1 * dm.n2;
+    const lbm_halo &h = d->halo;
+    // periodic wrap inside the buffer unless the caller supplied neighbour planes
+    p.in_lo = h.in_lo ? (const R *)h.in_lo : p.in + (dm.n0 - 1) * plane;
+    p.in_lo_qs = h.in_lo ? h.in_lo_qstride : p.N;
+    p.in_hi = h.in_hi ? (const R *)h.in_hi : p.in;
+    p.in_hi_qs = h.in_hi ? h.in_hi_qstride : p.N;
+    p.out_lo = h.out_lo ? (R *)h.out_lo : p.out + (dm.n0 - 1) * plane;
+    p.out_lo_qs = h.out_lo ? h.out_lo_qstride : p.N;
+    p.out_hi = h.out_hi ? (R *)h.out_hi : p.out;
+    p.out_hi_qs = h.out_hi ? h.out_hi_qstride : p.N;
+    p.labels = d->labels;
+    p.frozen = d->frozen;
+    p.labels_lo = h.label_lo ? h.label_lo : (d->labels ? d->labels + (dm.n0 - 1) * plane : nullptr);
+    p.labels_hi = h.label_hi ? h.label_hi : d->labels;
+    p.frozen_lo = h.frozen_lo ? h.frozen_lo : (d->frozen ? d->frozen + (dm.n0 - 1) * plane : nullptr);
+    p.frozen_hi = h.frozen_hi ? h.frozen_hi : d->frozen;
+    p.n_ops = d->n_ops;
+    p.collision_index = d->collision_index;
+    const lbm_op &c = d->ops[d->collision_index];
+    collision_scalars<R>(c.kind, c.p0, c.p1, p.ca, p.cb);
+    for (int i = 0; i < d->n_ops; ++i) {
+        const lbm_op &o = d->ops[i];
+        OpDev<R> &t = p.ops[i];
+        t.kind = o.kind;
+        t.axis = (o.axis >= 0 && o.axis < S::D) ? S::axis_of(o.axis) : 0;
+        t.side = o.side;
+        collision_scalars<R>(o.kind, o.p0, o.p1, t.a, t.b);
+        if (o.kind == LBM_OP_OUTLET_P) t.a = (R)o.p0;
+        t.rho = (const R *)o.rho;
+        t.u = (const R *)o.u;
+        for (int a = 0; a < 3; ++a) t.rho_stride[a] = 0;
+        for (int a = 0; a < 4; ++a) t.u_stride[a] = 0;
+        t.u_stride[0] = o.u_stride[0];
+        for (int c2 = 0; c2 < S::D; ++c2) {
+            t.rho_stride[S::axis_of(c2)] = o.rho_stride[c2];
+            t.u_stride[1 + S::axis_of(c2)] = o.u_stride[1 + c2];
+        }
+    }
+}
+
+template <class S, class R>
+static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, cudaStream_t st) {
+    StepParams<R> p;
+    fill_params<S, R>(d, dm, f_in, f_out, p);
+    const bool masked = d->n_ops > 1;
+    return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, d->variant, st));
+}
+
+#define LBM_DISPATCH(stencil, dtype, ...)                                   \
+    do {                                                                      \
+        if ((dtype) == LBM_F32) {                                             \
+            using R = float;                                                  \
+            if ((stencil) == LBM_D2Q9) { using S = D2Q9; __VA_ARGS__; }              \
+            else if ((stencil) == LBM_D3Q19) { using S = D3Q19; __VA_ARGS__; }       \
+            else { using S = D3Q27; __VA_ARGS__; }                                   \
+        } else {                                                              \
+            using R = double;                                                 \
+            if ((stencil) == LBM_D2Q9) { using S = D2Q9; __VA_ARGS__; }              \
+            else if ((stencil) == LBM_D3Q19) { using S = D3Q19; __VA_ARGS__; }       \
+            else { using S = D3Q27; __VA_ARGS__; }                                   \
+        }                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// mask packing (lettuce/_simulation.py:100-146 -> label byte + frozen-slot word)
+// ---------------------------------------------------------------------------
+template <class S>
+__global__ void pack_masks_kernel(const uint8_t *__restrict__ ncm, const uint8_t *__restrict__ nsm, int n0, int n1,
+                                  int n2, int n_ops, const int *__restrict__ op_kind, const int *__restrict__ op_axis,
+                                  const int *__restrict__ op_side, uint8_t *labels, uint32_t *frozen) {
+    const int64_t N = (int64_t)n0 * n1 * n2;
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(n % n2);
+        const int y = (int)((n / n2) % n1);
+        const int x = (int)(n / ((int64_t)n1 * n2));
+        uint32_t own = 0;
+        bool general = false;
+        ForQ<S::Q>::run([&]<int q>() {
+            if (nsm[q * N + n] == 1) own |= 1u << q;  // torch.eq(no_streaming_mask[i], 1), _simulation.py:254
+            const int xd = wrap(x + S::e(q, 0), n0), yd = wrap(y + S::e(q, 1), n1), zd = wrap(z + S::e(q, 2), n2);
+            if (nsm[q * N + ((int64_t)xd * n1 + yd) * n2 + zd] == 1) general = true;
+        });
+        if (own) general = true;
+        for (int i = 0; i < n_ops; ++i) {
+            if (op_kind[i] != LBM_OP_OUTLET_P && op_kind[i] != LBM_OP_ANTI_BOUNCE_BACK) continue;
+            if (op_side[i] != 0 && in_plane_of(op_axis[i], op_side[i], x, y, z, n0, n1, n2)) general = true;
+        }
+        frozen[n] = own;
+        labels[n] = (uint8_t)((ncm[n] & 0x7f) | (general ? kLabelGeneral : 0));
+    }
+}
+
+template <class S>
+static int pack_typed(const lbm_step_desc *d, const Dims &dm, const uint8_t *ncm, const uint8_t *nsm, uint8_t *labels,
+                      uint32_t *frozen, cudaStream_t st) {
+    int host[3][LBM_MAX_OPS];
+    for (int i = 0; i < LBM_MAX_OPS; ++i) {
+        host[0][i] = i < d->n_ops ? d->ops[i].kind : 0;
+        const int ax = i < d->n_ops ? d->ops[i].axis : 0;
+        host[1][i] = (ax >= 0 && ax < S::D) ? S::axis_of(ax) : 0;
+        host[2][i] = i < d->n_ops ? d->ops[i].side : 0;
+    }
+    int *dev = nullptr;
+    int e = (int)cudaMallocAsync(&dev, sizeof host, st);
+    if (e) return e;
+    e = (int)cudaMemcpyAsync(dev, host, sizeof host, cudaMemcpyHostToDevice, st);
+    if (e) return e;
+    const int64_t N = (int64_t)dm.n0 * dm.n1 * dm.n2;
+    int64_t b = (N + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    pack_masks_kernel<S><<<(int)b, 256, 0, st>>>(ncm, nsm, dm.n0, dm.n1, dm.n2, d->n_ops, dev, dev + LBM_MAX_OPS,
+                                                  dev + 2 * LBM_MAX_OPS, labels, frozen);
+    ++g_launch_count;
+    e = (int)cudaGetLastError();
+    cudaFreeAsync(dev, st);
+    // the staging copy reads `host` from this stack frame
+    cudaStreamSynchronize(st);
+    return e;
+}
+
+}  // namespace lbm
+
+using namespace lbm;
+
+extern "C" {
+
+int lbm_abi_version(void) { return LBM_ABI_VERSION; }
+
+const char *lbm_status_string(int s) {
+    switch (s) {
+        case LBM_OK: return "ok";
+        case LBM_ERR_BAD_ARGUMENT: return "bad argument (null pointer, bad extent or enum)";
+        case LBM_ERR_UNSUPPORTED: return "unsupported combination (no kernel for this request)";
+        case LBM_ERR_CUDA: return "CUDA runtime error (see lbm_last_cuda_error)";
+        case LBM_ERR_ALIASING: return "f_in and f_out overlap";
+        case LBM_ERR_TOO_LARGE: return "lattice has 2^31 nodes or more";
+    }
+    return "unknown status";
+}
+
+const char *lbm_last_cuda_error(void) { return g_cuda_error; }
+
+int64_t lbm_launch_count(void) { return g_launch_count; }
+
+int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream) {
+    Dims dm;
+    int rc = validate_desc(desc, dm);
+    if (rc) return rc;
+    if (!d_f_in || !d_f_out) return LBM_ERR_BAD_ARGUMENT;
+    const size_t bytes = (size_t)dm.q * dm.n0 * dm.n1 * dm.n2 * (desc->lat.dtype == LBM_F32 ? 4 : 8);
+    const char *a = (const char *)d_f_in, *b = (const char *)d_f_out;
+    if (a < b + bytes && b < a + bytes) return LBM_ERR_ALIASING;
+    LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype,
+                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, (cudaStream_t)stream)));
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream) {
+    if (n < 0) return LBM_ERR_BAD_ARGUMENT;
+    void *a = d_f_a, *b = d_f_b;
+    for (int64_t k = 0; k < n; ++k) {
+        const int rc = lbm_step(desc, a, b, stream);
+        if (rc) return rc;
+        void *t = a; a = b; b = t;
+    }
+    return LBM_OK;
+}
+
+const char *lbm_step_variant_name(const lbm_step_desc *desc) {
+    Dims dm;
+    if (validate_desc(desc, dm)) return "invalid";
+    const bool masked = desc->n_ops > 1;
+    LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype, {
+        StepParams<R> p;
+        fill_params<S, R>(desc, dm, nullptr, nullptr, p);
+        return (step_variant_name<S, R>(p, desc->ops[desc->collision_index].kind, desc->streaming, masked,
+                                        desc->variant));
+    });
+    return "invalid";
+}
+
+int lbm_pack_masks(const lbm_step_desc *desc, const uint8_t *d_ncm, const uint8_t *d_nsm, uint8_t *d_labels,
+                   uint32_t *d_frozen, void *stream) {
+    if (!desc || !d_ncm || !d_nsm || !d_labels || !d_frozen) return LBM_ERR_BAD_ARGUMENT;
+    Dims dm;
+    int rc = lattice_dims(&desc->lat, dm);
+    if (rc) return rc;
+    if (desc->n_ops < 1 || desc->n_ops > LBM_MAX_OPS) return LBM_ERR_BAD_ARGUMENT;
+    switch (desc->lat.stencil) {
+        case LBM_D2Q9: return cuda_fail(pack_typed<D2Q9>(desc, dm, d_ncm, d_nsm, d_labels, d_frozen, (cudaStream_t)stream));
+        case LBM_D3Q19: return cuda_fail(pack_typed<D3Q19>(desc, dm, d_ncm, d_nsm, d_labels, d_frozen, (cudaStream_t)stream));
+        default: return cuda_fail(pack_typed<D3Q27>(desc, dm, d_ncm, d_nsm, d_labels, d_frozen, (cudaStream_t)stream));
+    }
+}
+
+int lbm_moments(const lbm_lattice *lat, const void *d_f, void *d_rho, void *d_u, void *stream) {
+    Dims dm;
+    int rc = lattice_dims(lat, dm);
+    if (rc) return rc;
+    if (!d_f || (!d_rho && !d_u)) return LBM_ERR_BAD_ARGUMENT;
+    const int64_t N = (int64_t)dm.n0 * dm.n1 * dm.n2;
+    LBM_DISPATCH(lat->stencil, lat->dtype,
+                 return cuda_fail((launch_moments<S, R>((const R *)d_f, (R *)d_rho, (R *)d_u, N, (cudaStream_t)stream))));
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+size_t lbm_reduce_scratch_bytes(const lbm_lattice *) { return reduce_scratch_bytes(); }
+
+int lbm_reduce(const lbm_lattice *lat, int what, const void *d_in, const uint8_t *d_mask, void *d_scratch,
+               double *d_out, void *stream) {
+    Dims dm;
+    int rc = lattice_dims(lat, dm);
+    if (rc) return rc;
+    if (!d_in || !d_scratch || !d_out) return LBM_ERR_BAD_ARGUMENT;
+    LBM_DISPATCH(lat->stencil, lat->dtype,
+                 return cuda_fail((launch_reduce<S, R>(what, (const R *)d_in, d_mask, dm.n0, dm.n1, dm.n2,
+                                                       (double *)d_scratch, d_out, (cudaStream_t)stream))));
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int64_t nsteps, double *h_energy) {
+    Dims dm;
+    int rc = validate_desc(desc, dm);
+    if (rc) return rc;
+    if (!h_f || !h_f_out || nsteps < 0) return LBM_ERR_BAD_ARGUMENT;
+    const lbm_halo &h = desc->halo;
+    if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return LBM_ERR_BAD_ARGUMENT;
+    const size_t bytes = (size_t)dm.q * dm.n0 * dm.n1 * dm.n2 * (desc->lat.dtype == LBM_F32 ? 4 : 8);
+    cudaStream_t st = nullptr;
+    void *a = nullptr, *b = nullptr, *scratch = nullptr;
+    double *d_e = nullptr;
+    int e = (int)cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e) return cuda_fail(e);
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(st);
+        if (a) cudaFree(a);
+        if (b) cudaFree(b);
+        if (scratch) cudaFree(scratch);
+        if (d_e) cudaFree(d_e);
+        cudaStreamDestroy(st);
+        return code;
+    };
+    if ((e = (int)cudaMalloc(&a, bytes)) || (e = (int)cudaMalloc(&b, bytes)) ||
+        (e = (int)cudaMalloc(&scratch, reduce_scratch_bytes())) || (e = (int)cudaMalloc(&d_e, sizeof(double))))
+        return cleanup(cuda_fail(e));
+    if ((e = (int)cudaMemcpyAsync(a, h_f, bytes, cudaMemcpyHostToDevice, st))) return cleanup(cuda_fail(e));
+    for (int64_t k = 0; k < nsteps; ++k) {
+        rc = lbm_step(desc, a, b, st);
+        if (rc) return cleanup(rc);
+        void *t = a; a = b; b = t;
+        if (h_energy) {
+            rc = lbm_reduce(&desc->lat, LBM_SUM_HALF_U2, a, nullptr, scratch, d_e, st);
+            if (rc) return cleanup(rc);
+            // result of this step read back to the host (reporter with interval 1)
+            if ((e = (int)cudaMemcpyAsync(h_energy + k, d_e, sizeof(double), cudaMemcpyDeviceToHost, st)))
+                return cleanup(cuda_fail(e));
+        }
+    }
+    if ((e = (int)cudaMemcpyAsync(h_f_out, a, bytes, cudaMemcpyDeviceToHost, st))) return cleanup(cuda_fail(e));
+    e = (int)cudaStreamSynchronize(st);
+    return cleanup(e ? cuda_fail(e) : LBM_OK);
+}
+
+}  // extern "C"

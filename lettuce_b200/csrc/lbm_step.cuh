@@ -1,0 +1,308 @@
+// lbm_step.cuh -- fused stream+collide kernels.
+//
+// One launch = one lettuce time step (lettuce/_simulation.py:149-166, 241-305):
+// every population is read once and written once.  PULL gathers f_q(x - e_q)
+// (stream-before-collide), PUSH scatters the post-collision value to x + e_q
+// (stream-after-collide); the four StreamingStrategy values are the four
+// (PULL, PUSH) combinations.  Boundaries are folded in through a per-node label
+// byte; nodes whose label is the plain collision label and that touch no frozen
+// slot take the register-only fast path, everything else goes through
+// `general_node`, which restates Appendix A.2 of SURVEY.md node by node.
+#pragma once
+#include "lbm_core.cuh"
+
+namespace lbm {
+
+constexpr uint8_t kLabelGeneral = 0x80;  // label bit 7: node needs the general path
+
+template <class R>
+struct OpDev {
+    int kind, axis, side, _pad;  // axis is an INTERNAL axis (0..2)
+    R a, b;                      // collision scalars / rho_outlet in a
+    const R *rho;
+    const R *u;
+    int64_t rho_stride[3];       // internal axis order
+    int64_t u_stride[4];         // component, internal axes 0..2
+};
+
+template <class R>
+struct StepParams {
+    const R *in;
+    R *out;
+    // planes x = -1 and x = n0 (peer-mapped in multi-GPU runs, wrapped otherwise)
+    const R *in_lo, *in_hi;
+    R *out_lo, *out_hi;
+    int64_t in_lo_qs, in_hi_qs, out_lo_qs, out_hi_qs;
+    int n0, n1, n2;
+    int64_t N;  // n0*n1*n2
+    const uint8_t *labels, *labels_lo, *labels_hi;
+    const uint32_t *frozen, *frozen_lo, *frozen_hi;
+    int n_ops, collision_index;
+    R ca, cb;  // scalars of the collision entry
+    OpDev<R> ops[LBM_MAX_OPS];
+};
+
+// pointer to population 0 of plane `x` (x in [-1, n0]) plus its q stride
+template <class R, class P>
+struct Plane {
+    P *p;
+    int64_t qs;
+};
+
+template <class R>
+LBM_D Plane<R, const R> in_plane(const StepParams<R> &p, int x) {
+    if (x < 0) return {p.in_lo, p.in_lo_qs};
+    if (x >= p.n0) return {p.in_hi, p.in_hi_qs};
+    return {p.in + (int64_t)x * p.n1 * p.n2, p.N};
+}
+template <class R>
+LBM_D Plane<R, R> out_plane(const StepParams<R> &p, int x) {
+    if (x < 0) return {p.out_lo, p.out_lo_qs};
+    if (x >= p.n0) return {p.out_hi, p.out_hi_qs};
+    return {p.out + (int64_t)x * p.n1 * p.n2, p.N};
+}
+template <class R>
+LBM_D const uint32_t *frozen_plane(const StepParams<R> &p, int x) {
+    if (x < 0) return p.frozen_lo;
+    if (x >= p.n0) return p.frozen_hi;
+    return p.frozen + (int64_t)x * p.n1 * p.n2;
+}
+template <class R>
+LBM_D const uint8_t *label_plane(const StepParams<R> &p, int x) {
+    if (x < 0) return p.labels_lo;
+    if (x >= p.n0) return p.labels_hi;
+    return p.labels + (int64_t)x * p.n1 * p.n2;
+}
+
+LBM_D int wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+// ---------------------------------------------------------------------------
+// general path pieces
+// ---------------------------------------------------------------------------
+
+// populations of node (x,y,z) as the collide phase sees them: after the optional
+// pre-streaming gather with the destination-side frozen-slot rule
+// (lettuce/_simulation.py:245-256).  x may be -1 or n0 (halo plane) ONLY when
+// PULL is false.
+template <class S, class R, bool PULL>
+__device__ void gather_node(const StepParams<R> &p, int x, int y, int z, R (&f)[S::Q]) {
+    uint32_t fr = 0;
+    if (PULL && p.frozen) fr = frozen_plane(p, x)[(int64_t)y * p.n2 + z];
+    ForQ<S::Q>::run([&]<int q>() {
+        int xs = x, ys = y, zs = z;
+        if (PULL && !((fr >> q) & 1u)) {
+            xs = x - S::e(q, 0);
+            ys = wrap(y - S::e(q, 1), p.n1);
+            zs = wrap(z - S::e(q, 2), p.n2);
+        }
+        const auto pl = in_plane(p, xs);
+        f[q] = pl.p[q * pl.qs + (int64_t)ys * p.n2 + zs];
+    });
+}
+
+template <class S, class R>
+LBM_D void bounce_back(R (&f)[S::Q]) {
+    // lettuce/ext/_boundary/bounce_back_boundary.py:17-18 : f <- f[opposite]
+    ForQ<S::Q>::run([&]<int q>() {
+        constexpr int o = S::opp(q);
+        if constexpr (q < o) {
+            const R t = f[q];
+            f[q] = f[o];
+            f[o] = t;
+        }
+    });
+}
+
+template <class S, class R>
+LBM_D void equilibrium_boundary(const OpDev<R> &op, int x, int y, int z, R (&f)[S::Q]) {
+    // lettuce/ext/_boundary/equilibrium_boundary_pu.py:79-84 (values pre-converted to lattice units)
+    const R rho = op.rho[x * op.rho_stride[0] + y * op.rho_stride[1] + z * op.rho_stride[2]];
+    R u[3] = {R(0), R(0), R(0)};
+#pragma unroll
+    for (int c = 0; c < S::D; ++c)
+        u[S::axis_of(c)] = op.u[c * op.u_stride[0] + x * op.u_stride[1] + y * op.u_stride[2] + z * op.u_stride[3]];
+    equilibrium_all<S, R>(rho, u, f);
+}
+
+// applies transformer entry `i` to node-local populations if the node carries label i.
+// Outlet kinds are handled by the caller (they need a neighbour).
+template <class S, class R, int COLL>
+LBM_D void apply_local_op(const StepParams<R> &p, int i, int label, int x, int y, int z, R (&f)[S::Q]) {
+    if (label != i) return;
+    const OpDev<R> &op = p.ops[i];
+    if (i == p.collision_index) {
+        Collide<S, R, COLL>::apply(f, p.ca, p.cb);
+    } else if (op.kind == LBM_OP_BOUNCE_BACK) {
+        bounce_back<S, R>(f);
+    } else if (op.kind == LBM_OP_EQUILIBRIUM) {
+        equilibrium_boundary<S, R>(op, x, y, z, f);
+    }
+}
+
+LBM_D bool in_plane_of(int axis, int side, int x, int y, int z, int n0, int n1, int n2) {
+    const int c = axis == 0 ? x : (axis == 1 ? y : z);
+    const int n = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+    return c == (side > 0 ? n - 1 : 0);
+}
+
+// velocity of the neighbour node one step inside the domain from an outlet node, as
+// the reference sees it when boundary `i` runs: populations after entries < i.
+template <class S, class R, int COLL, bool PULL>
+__device__ void neighbour_state(const StepParams<R> &p, int i, int x, int y, int z, R &rho, R (&u)[3]) {
+    R g[S::Q];
+    gather_node<S, R, PULL>(p, x, y, z, g);
+    const int label = label_plane(p, x)[(int64_t)y * p.n2 + z] & 0x7f;
+    for (int k = 0; k < i; ++k) apply_local_op<S, R, COLL>(p, k, label, x, y, z, g);
+    R j[3];
+    moments<S, R>(g, rho, j);
+    const R inv = R(1) / rho;
+    u[0] = j[0] * inv; u[1] = j[1] * inv; u[2] = j[2] * inv;
+}
+
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+__device__ __noinline__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
+    constexpr int Q = S::Q;
+    R f[Q];
+    gather_node<S, R, PULL>(p, x, y, z, f);
+
+    for (int i = 0; i < p.n_ops; ++i) {
+        const OpDev<R> &op = p.ops[i];
+        if (op.kind == LBM_OP_OUTLET_P || op.kind == LBM_OP_ANTI_BOUNCE_BACK) {
+            if (!in_plane_of(op.axis, op.side, x, y, z, p.n0, p.n1, p.n2)) continue;
+            const int xn = x - (op.axis == 0 ? op.side : 0);
+            const int yn = y - (op.axis == 1 ? op.side : 0);
+            const int zn = z - (op.axis == 2 ? op.side : 0);
+            R rho_n, u_n[3];
+            neighbour_state<S, R, COLL, PULL>(p, i, xn, yn, zn, rho_n, u_n);
+            if (op.kind == LBM_OP_OUTLET_P) {
+                // equilibrium_outlet_p.py:63-73: whole plane <- feq(rho_outlet, u[neighbour]),
+                // irrespective of the label
+                equilibrium_all<S, R>(op.a, u_n, f);
+            } else {
+                // anti_bounce_back_outlet.py:71-91, in place on the whole plane
+                R rho_h, j_h[3];
+                moments<S, R>(f, rho_h, j_h);
+                const R inv = R(1) / rho_h;
+                R uw[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const R uh = j_h[a] * inv;
+                    uw[a] = uh + R(0.5) * (uh - u_n[a]);
+                }
+                const R uw2 = uw[0] * uw[0] + uw[1] * uw[1] + uw[2] * uw[2];
+                R fnew[Q];
+                ForQ<Q>::run([&]<int q>() {
+                    fnew[q] = f[q];
+                });
+                ForQ<Q>::run([&]<int q>() {
+                    constexpr int o = S::opp(q);
+                    // q leaves through the plane when e_q . direction == 1
+                    const int en = (op.axis == 0 ? S::e(q, 0) : (op.axis == 1 ? S::e(q, 1) : S::e(q, 2))) * op.side;
+                    if (en == 1) {
+                        R eu = R(0);
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) eu += R(S::e(q, a)) * uw[a];
+                        fnew[o] = -f[q] + R(S::w(q)) * rho_h *
+                                              (R(2) + eu * eu * R(1.0 / (kCs2 * kCs2)) - uw2 * R(1.0 / kCs2));
+                    }
+                });
+                ForQ<Q>::run([&]<int q>() { f[q] = fnew[q]; });
+            }
+        } else {
+            apply_local_op<S, R, COLL>(p, i, label, x, y, z, f);
+        }
+    }
+
+    // scatter with the destination-side frozen-slot rule (_simulation.py:252-255):
+    // slot (q, dst) takes the streamed value unless it is frozen, in which case the
+    // node's own value stays.
+    const int64_t row = (int64_t)y * p.n2 + z;
+    if (!PUSH) {
+        const auto pl = out_plane(p, x);
+        ForQ<Q>::run([&]<int q>() { pl.p[q * pl.qs + row] = f[q]; });
+        return;
+    }
+    const uint32_t own = p.frozen ? frozen_plane(p, x)[row] : 0u;
+    ForQ<Q>::run([&]<int q>() {
+        if constexpr (q == 0) {
+            const auto pl = out_plane(p, x);
+            pl.p[row] = f[0];
+        } else {
+            if ((own >> q) & 1u) {
+                const auto pl = out_plane(p, x);
+                pl.p[q * pl.qs + row] = f[q];
+            }
+            const int xd = x + S::e(q, 0);
+            const int yd = wrap(y + S::e(q, 1), p.n1);
+            const int zd = wrap(z + S::e(q, 2), p.n2);
+            const int64_t drow = (int64_t)yd * p.n2 + zd;
+            uint32_t dfr = 0;
+            if (p.frozen) {
+                const uint32_t *fp = frozen_plane(p, xd);
+                dfr = fp ? fp[drow] : 0u;
+            }
+            if (!((dfr >> q) & 1u)) {
+                const auto pl = out_plane(p, xd);
+                pl.p[q * pl.qs + drow] = f[q];
+            }
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------
+// scalar kernel: one node per thread, threadIdx.x along the contiguous axis.
+// ---------------------------------------------------------------------------
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
+__global__ void __launch_bounds__(256) step_scalar_kernel(const __grid_constant__ StepParams<R> p) {
+    constexpr int Q = S::Q;
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.z;
+    if (z >= p.n2 || y >= p.n1) return;
+    const int64_t row = (int64_t)y * p.n2 + z;
+
+    if (MASKED) {
+        const int label = p.labels[(int64_t)x * p.n1 * p.n2 + row];
+        if (label != p.collision_index) {
+            general_node<S, R, COLL, PULL, PUSH>(p, x, y, z, label & 0x7f);
+            return;
+        }
+    }
+
+    // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
+    const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
+    const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
+
+    R f[Q];
+    if (PULL) {
+        const Plane<R, const R> pl[3] = {in_plane(p, x + 1), in_plane(p, x), in_plane(p, x - 1)};  // index e0+1 -> x - e0
+        ForQ<Q>::run([&]<int q>() {
+            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
+            const int ys = e1 == 0 ? y : (e1 == 1 ? ym : yp);
+            const int zs = e2 == 0 ? z : (e2 == 1 ? zm : zp);
+            const auto &s = pl[e0 + 1];
+            f[q] = __ldg(s.p + (q * s.qs + (int64_t)ys * p.n2 + zs));
+        });
+    } else {
+        const R *src = p.in + (int64_t)x * p.n1 * p.n2 + row;
+        ForQ<Q>::run([&]<int q>() { f[q] = __ldg(src + q * p.N); });
+    }
+
+    Collide<S, R, COLL>::apply(f, p.ca, p.cb);
+
+    if (PUSH) {
+        const Plane<R, R> pl[3] = {out_plane(p, x - 1), out_plane(p, x), out_plane(p, x + 1)};  // index e0+1 -> x + e0
+        ForQ<Q>::run([&]<int q>() {
+            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
+            const int yd = e1 == 0 ? y : (e1 == 1 ? yp : ym);
+            const int zd = e2 == 0 ? z : (e2 == 1 ? zp : zm);
+            const auto &d = pl[e0 + 1];
+            d.p[q * d.qs + (int64_t)yd * p.n2 + zd] = f[q];
+        });
+    } else {
+        R *dst = p.out + (int64_t)x * p.n1 * p.n2 + row;
+        ForQ<Q>::run([&]<int q>() { dst[q * p.N] = f[q]; });
+    }
+}
+
+}  // namespace lbm

@@ -1,0 +1,4 @@
+from .boundary import *
+from .collision import *
+from .flows import *
+from .reporter import *

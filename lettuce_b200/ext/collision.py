@@ -1,0 +1,45 @@
+"""Collision operators (API of lettuce/ext/_collision/{bgk,trt,kbc,no}_collision.py).
+
+On the B200 engine these are parameter holders: the arithmetic lives in
+csrc/lbm_core.cuh (`Collide<S, R, COLL>`), fused into the stream+collide kernel.
+"""
+from __future__ import annotations
+
+from .._simulation import Collision
+
+__all__ = ["NoCollision", "BGKCollision", "TRTCollision", "KBCCollision"]
+
+
+class NoCollision(Collision):
+    """identity (lettuce/ext/_collision/no_collision.py:9-11)"""
+
+
+class BGKCollision(Collision):
+    """f - (f - feq)/tau (lettuce/ext/_collision/bgk_collision.py:12-22).  `tau` is re-read
+    before every launch, like the reference's generated call passes 1/tau per step."""
+
+    def __init__(self, tau, force=None):
+        if force is not None:
+            raise NotImplementedError("forcing (Guo / ShanChen) is outside the B200 hot path (SURVEY.md 8f)")
+        self.tau = tau
+        self.force = None
+
+
+class TRTCollision(Collision):
+    """two relaxation times; tau_minus defaults to 1 (lettuce/ext/_collision/trt_collision.py:12-27)"""
+
+    def __init__(self, tau, tau_minus=1.0):
+        self.tau_plus = tau
+        self.tau_minus = tau_minus
+
+
+class KBCCollision(Collision):
+    """entropic multi-relaxation (Karlin-Boesch-Chikatamarla), D2Q9 and D3Q27 only
+    (lettuce/ext/_collision/kbc_collision.py:11-160).
+
+    As in the reference, the constructor argument is ignored: on first use `tau` is replaced by
+    `flow.units.relaxation_parameter_lu` and `beta = 1/(2 tau)` (kbc_collision.py:97-99)."""
+
+    def __init__(self, tau: float = None):
+        self.tau = tau
+        self.beta = None

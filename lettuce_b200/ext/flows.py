@@ -1,0 +1,159 @@
+"""Flows of the benchmark configurations (API of lettuce/ext/_flows/{_ext_flow,taylorgreen,obstacle}.py).
+Initial conditions are evaluated once, in torch, on the context device."""
+from __future__ import annotations
+
+import warnings
+from abc import abstractmethod
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from .._flow import Flow
+from .._stencil import D2Q9, D3Q19
+from .._unit import UnitConversion
+from .boundary import AntiBounceBackOutlet, BounceBackBoundary, EquilibriumBoundaryPU
+
+__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle"]
+
+
+class ExtFlow(Flow):
+    """Common constructor: resolution + Reynolds + Mach + stencil (lettuce/ext/_flows/_ext_flow.py:8-42)."""
+
+    def __init__(self, context, resolution: Union[int, List[int]], reynolds_number, mach_number,
+                 stencil=None, equilibrium=None):
+        resolution = self.make_resolution(resolution, stencil)
+        assert len(resolution) in (2, 3), f"the B200 engine supports 2 and 3 dimensions, got {len(resolution)}"
+        stencil = stencil or (D2Q9() if len(resolution) == 2 else D3Q19())
+        stencil = stencil() if callable(stencil) else stencil
+        Flow.__init__(self, context, resolution, self.make_units(reynolds_number, mach_number, resolution),
+                      stencil, equilibrium)
+
+    @abstractmethod
+    def make_resolution(self, resolution, stencil=None) -> List[int]:
+        ...
+
+    @abstractmethod
+    def make_units(self, reynolds_number, mach_number, resolution: List[int]) -> UnitConversion:
+        ...
+
+
+class TaylorGreenVortex(ExtFlow):
+    """Taylor-Green vortex in 2-D and 3-D on the periodic box [0, 2 pi)^d
+    (lettuce/ext/_flows/taylorgreen.py:16-98); f_neq initialisation is on by default."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None,
+                 initialize_fneq: bool = True):
+        self.initialize_fneq = initialize_fneq
+        if stencil is None and not isinstance(resolution, list):
+            warnings.warn("Requiring information about dimensionality! Either via stencil or resolution. "
+                          "Setting dimension to 2.", UserWarning)
+            self.stencil = D2Q9()
+        else:
+            self.stencil = stencil() if callable(stencil) else stencil
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, self.stencil, equilibrium)
+
+    def make_resolution(self, resolution, stencil=None) -> List[int]:
+        if isinstance(resolution, int):
+            return [resolution] * self.stencil.d
+        assert len(resolution) in (2, 3), "the resolution of a taylor-green-vortex must be 2- or 3-dimensional!"
+        return list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution) -> UnitConversion:
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0] / (2 * torch.pi),
+                              characteristic_length_pu=1, characteristic_velocity_pu=1)
+
+    @property
+    def grid(self):
+        axes = [torch.linspace(0, 2 * torch.pi * (1 - 1 / n), steps=n, device=self.context.device,
+                               dtype=self.context.dtype) for n in self.resolution]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    def initial_pu(self):
+        return self.analytic_solution(t=0)
+
+    def analytic_solution(self, t: float):
+        if t > 0 and self.stencil.d > 2:
+            warnings.warn("The analytic solution is only true for the 2D TGV!")
+        g = self.grid
+        nu = self.context.convert_to_tensor(self.units.viscosity_pu)
+        if len(self.resolution) == 2:
+            decay = torch.exp(-2 * nu * t)
+            u = torch.stack([torch.cos(g[0]) * torch.sin(g[1]) * decay,
+                             -torch.sin(g[0]) * torch.cos(g[1]) * decay])
+            p = -torch.stack([0.25 * (torch.cos(2 * g[0]) + torch.cos(2 * g[1])) * torch.exp(-4 * nu * t)])
+        else:
+            u = torch.stack([torch.sin(g[0]) * torch.cos(g[1]) * torch.cos(g[2]),
+                             -torch.cos(g[0]) * torch.sin(g[1]) * torch.cos(g[2]),
+                             torch.zeros_like(g[0])])
+            p = torch.stack([1 / 16. * (torch.cos(2 * g[0]) + torch.cos(2 * g[1])) * (torch.cos(2 * g[2]) + 2)])
+        return p, u
+
+    @property
+    def post_boundaries(self):
+        return []
+
+
+class Obstacle(ExtFlow):
+    """Flow in +x around a solid `mask`: equilibrium inlet at x = 0, outlet at x = nx-1,
+    bounce-back on the mask (lettuce/ext/_flows/obstacle.py:16-125).  Set `flow.mask` after
+    construction and call `flow.initialize()` to start from rest inside the solid."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, domain_length_x, char_length=1,
+                 char_velocity=1, stencil=None, equilibrium=None):
+        self.char_length_lu = resolution[0] / domain_length_x * char_length
+        self.char_length = char_length
+        self.char_velocity = char_velocity
+        self.resolution = self.make_resolution(resolution, stencil)
+        self._mask = torch.zeros(self.resolution, dtype=torch.bool, device=context.device)
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, stencil, equilibrium)
+
+    def make_units(self, reynolds_number, mach_number, resolution) -> UnitConversion:
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=self.char_length_lu,
+                              characteristic_length_pu=self.char_length,
+                              characteristic_velocity_pu=self.char_velocity)
+
+    def make_resolution(self, resolution, stencil=None) -> List[int]:
+        if isinstance(resolution, int):
+            st = stencil() if callable(stencil) else stencil
+            return [resolution] * st.d
+        return list(resolution)
+
+    @property
+    def mask(self):
+        return self._mask
+
+    @mask.setter
+    def mask(self, m):
+        assert isinstance(m, (np.ndarray, torch.Tensor)) and list(m.shape) == list(self.resolution)
+        self._mask = self.context.convert_to_tensor(m, dtype=torch.bool)
+
+    def initial_pu(self):
+        """p = 0, u = U e_x outside the solid (obstacle.py:94-99).  As in the reference the
+        velocity is assembled in torch's default dtype (float32) and converted to lattice units
+        before the context dtype is applied."""
+        d = self.stencil.d
+        p = np.zeros([1, *self.resolution], dtype=float)
+        u_char = (self.units.characteristic_velocity_pu * self._unit_vector()).reshape([d] + [1] * d)
+        u = (~self._mask).cpu() * u_char
+        return p, u
+
+    @property
+    def grid(self):
+        """node coordinates in physical units; float32 like the reference's (int64 arange divided by a
+        Python float, obstacle.py:101-105)"""
+        axes = [self.units.convert_length_to_pu(torch.arange(n)) for n in self.resolution]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    @property
+    def post_boundaries(self):
+        x = self.grid[0]
+        return [EquilibriumBoundaryPU(flow=self, context=self.context, mask=torch.abs(x) < 1e-6,
+                                      velocity=self.units.characteristic_velocity_pu * self._unit_vector()),
+                AntiBounceBackOutlet(self._unit_vector().tolist(), self),
+                BounceBackBoundary(self.mask)]
+
+    def _unit_vector(self, i=0):
+        return torch.eye(self.stencil.d)[i]

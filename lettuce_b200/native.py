@@ -1,0 +1,358 @@
+"""ctypes binding of include/lbm_b200.h and the `invoke(simulation)` plug.
+
+This module is what `Simulation._collide_and_stream` is pointed at, in the same
+place where the reference installs its generated extension
+(lettuce/_simulation.py:229) and with the same call signature
+(`invoke(simulation)`, lettuce/cuda_native/_template.py:35-39): one call = one
+time step, `flow.f` and `flow.f_next` are swapped afterwards.
+
+There is no CPU or torch fallback: if the shared library is missing, the
+populations are not CUDA tensors, or an operator has no native kernel, this
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblbm_b200.so")
+
+LBM_MAX_OPS = 8
+# enums of include/lbm_b200.h
+D2Q9, D3Q19, D3Q27 = 0, 1, 2
+F32, F64 = 0, 1
+OP_NO_COLLISION, OP_BGK, OP_TRT, OP_KBC = 0, 1, 2, 3
+OP_BOUNCE_BACK, OP_EQUILIBRIUM, OP_OUTLET_P, OP_ANTI_BOUNCE_BACK = 16, 17, 18, 19
+SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED, ENSTROPHY = range(6)
+
+
+class LbmOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("axis", C.c_int32), ("side", C.c_int32), ("_pad", C.c_int32),
+                ("p0", C.c_double), ("p1", C.c_double),
+                ("rho", C.c_void_p), ("u", C.c_void_p),
+                ("rho_stride", C.c_int64 * 3), ("u_stride", C.c_int64 * 4)]
+
+
+class LbmLattice(C.Structure):
+    _fields_ = [("stencil", C.c_int32), ("dtype", C.c_int32),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("_pad", C.c_int32)]
+
+
+class LbmHalo(C.Structure):
+    _fields_ = [("in_lo", C.c_void_p), ("in_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_hi", C.c_void_p),
+                ("in_lo_qstride", C.c_int64), ("in_hi_qstride", C.c_int64),
+                ("out_lo_qstride", C.c_int64), ("out_hi_qstride", C.c_int64),
+                ("label_lo", C.c_void_p), ("label_hi", C.c_void_p),
+                ("frozen_lo", C.c_void_p), ("frozen_hi", C.c_void_p)]
+
+
+class LbmStepDesc(C.Structure):
+    _fields_ = [("lat", LbmLattice), ("streaming", C.c_int32), ("n_ops", C.c_int32),
+                ("collision_index", C.c_int32), ("variant", C.c_int32),
+                ("ops", LbmOp * LBM_MAX_OPS),
+                ("labels", C.c_void_p), ("frozen", C.c_void_p), ("halo", LbmHalo)]
+
+
+EXPORTS = ["lbm_step", "lbm_step_n", "lbm_pack_masks", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
+           "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
+           "lbm_launch_count", "lbm_step_variant_name"]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load liblbm_b200.so (built by `python -m lettuce_b200.build`).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m lettuce_b200.build` "
+                           f"(lettuce_b200 has no CPU or torch fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.lbm_step.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp]
+    L.lbm_step.restype = i32
+    L.lbm_step_n.argtypes = [C.POINTER(LbmStepDesc), vp, vp, i64, vp]
+    L.lbm_step_n.restype = i32
+    L.lbm_pack_masks.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, vp, vp]
+    L.lbm_pack_masks.restype = i32
+    L.lbm_moments.argtypes = [C.POINTER(LbmLattice), vp, vp, vp, vp]
+    L.lbm_moments.restype = i32
+    L.lbm_reduce_scratch_bytes.argtypes = [C.POINTER(LbmLattice)]
+    L.lbm_reduce_scratch_bytes.restype = C.c_size_t
+    L.lbm_reduce.argtypes = [C.POINTER(LbmLattice), i32, vp, vp, vp, vp, vp]
+    L.lbm_reduce.restype = i32
+    L.lbm_run_host.argtypes = [C.POINTER(LbmStepDesc), vp, vp, i64, vp]
+    L.lbm_run_host.restype = i32
+    L.lbm_abi_version.restype = i32
+    L.lbm_status_string.argtypes = [i32]
+    L.lbm_status_string.restype = C.c_char_p
+    L.lbm_last_cuda_error.restype = C.c_char_p
+    L.lbm_launch_count.restype = i64
+    L.lbm_step_variant_name.argtypes = [C.POINTER(LbmStepDesc)]
+    L.lbm_step_variant_name.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(status: int, what: str = "lbm call"):
+    if status != 0:
+        L = lib()
+        msg = L.lbm_status_string(status).decode()
+        if status == -3:
+            msg += ": " + L.lbm_last_cuda_error().decode()
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().lbm_launch_count())
+
+
+# --------------------------------------------------------------------------
+# descriptor construction from lettuce-style objects (duck typed by class name,
+# so the reference's own classes are accepted as well as lettuce_b200's)
+# --------------------------------------------------------------------------
+_STENCIL_IDS = {"D2Q9": D2Q9, "D3Q19": D3Q19, "D3Q27": D3Q27}
+_KIND_BY_NAME = {"NoCollision": OP_NO_COLLISION, "BGKCollision": OP_BGK, "TRTCollision": OP_TRT,
+                 "KBCCollision": OP_KBC, "BounceBackBoundary": OP_BOUNCE_BACK,
+                 "EquilibriumBoundaryPU": OP_EQUILIBRIUM, "EquilibriumOutletP": OP_OUTLET_P,
+                 "AntiBounceBackOutlet": OP_ANTI_BOUNCE_BACK}
+
+
+def op_kind(op) -> int:
+    """Native kind of a collision / boundary object; most-derived class name wins."""
+    for cls in type(op).__mro__:
+        if cls.__name__ in _KIND_BY_NAME:
+            return _KIND_BY_NAME[cls.__name__]
+    raise NotImplementedError(
+        f"{type(op).__name__} has no B200 kernel (supported: {sorted(_KIND_BY_NAME)}); "
+        f"lettuce_b200 does not fall back to torch")
+
+
+def stencil_id(stencil) -> int:
+    for cls in type(stencil).__mro__:
+        if cls.__name__ in _STENCIL_IDS:
+            return _STENCIL_IDS[cls.__name__]
+    raise NotImplementedError(f"stencil {type(stencil).__name__} has no B200 kernel (D2Q9, D3Q19, D3Q27)")
+
+
+def dtype_id(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.float64:
+        return F64
+    raise NotImplementedError(f"dtype {dtype} has no B200 kernel (float32, float64); the reference's native "
+                              f"dispatch has the same limit (cuda_native/_template.py:76)")
+
+
+def lattice_of(stencil, resolution, dtype) -> LbmLattice:
+    res = [int(r) for r in resolution]
+    if len(res) != stencil.d:
+        raise ValueError(f"resolution {res} does not match a {stencil.d}-dimensional stencil")
+    nx, ny = res[0], res[1]
+    nz = res[2] if len(res) == 3 else 1
+    return LbmLattice(stencil_id(stencil), dtype_id(dtype), nx, ny, nz, 0)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} lives on {t.device}: lettuce_b200 runs on CUDA devices only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous [q, *resolution]")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _direction_axis_side(direction):
+    direction = [int(round(float(c))) for c in direction]
+    nz = [i for i, c in enumerate(direction) if c != 0]
+    if len(nz) != 1 or abs(direction[nz[0]]) != 1:
+        raise ValueError(f"outlet direction must have exactly one entry of +-1, got {direction}")
+    return nz[0], direction[nz[0]]
+
+
+class Engine:
+    """Everything `invoke` needs for one Simulation: the packed descriptor, the
+    label / frozen-slot fields and the boundary parameter tensors it borrows."""
+
+    def __init__(self, simulation):
+        self.lib = lib()
+        flow = simulation.flow
+        self.flow = flow
+        self.simulation = simulation
+        _require_cuda(flow.f, "flow.f")
+        self.device = flow.f.device
+        self.lat = lattice_of(flow.stencil, flow.f.shape[1:], flow.f.dtype)
+        transformer = list(simulation.transformer)
+        if len(transformer) > LBM_MAX_OPS:
+            raise NotImplementedError(f"at most {LBM_MAX_OPS} transformer entries, got {len(transformer)}")
+        self.desc = LbmStepDesc()
+        self.desc.lat = self.lat
+        self.desc.streaming = int(simulation.streaming_strategy.value)
+        self.desc.n_ops = len(transformer)
+        self.desc.collision_index = int(simulation.collision_index)
+        self.desc.variant = int(os.environ.get("LBM_B200_VARIANT", "0"))
+        self._keep: List[torch.Tensor] = []     # tensors whose pointers the descriptor borrows
+        self.transformer = transformer
+        for i, op in enumerate(transformer):
+            self._fill_op(i, op)
+        self.refresh_parameters()
+        self.labels: Optional[torch.Tensor] = None
+        self.frozen: Optional[torch.Tensor] = None
+        if len(transformer) > 1:
+            self._pack_masks()
+        self.variant_name = self.lib.lbm_step_variant_name(C.byref(self.desc)).decode()
+
+    # -- descriptor pieces ---------------------------------------------------
+    def _fill_op(self, i, op):
+        o = self.desc.ops[i]
+        kind = op_kind(op)
+        o.kind = kind
+        flow, units = self.flow, self.flow.units
+        if kind == OP_BGK and getattr(op, "force", None) is not None:
+            raise NotImplementedError("BGKCollision with a force term has no B200 kernel")
+        if kind == OP_KBC:
+            # the reference replaces tau by the flow's relaxation parameter on first call
+            # (lettuce/ext/_collision/kbc_collision.py:97-99); mirror that state change
+            op.tau = units.relaxation_parameter_lu
+            op.beta = 1.0 / (2 * op.tau)
+        if kind == OP_EQUILIBRIUM:
+            rho = units.convert_pressure_pu_to_density_lu(op.pressure)
+            u = units.convert_velocity_to_lu(op.velocity)
+            rho = rho.to(device=self.device, dtype=flow.f.dtype).contiguous()
+            u = u.to(device=self.device, dtype=flow.f.dtype).contiguous()
+            d = flow.stencil.d
+            if rho.dim() != d + 1 or u.dim() != d + 1 or rho.shape[0] != 1:
+                raise ValueError("EquilibriumBoundaryPU needs pressure of shape [1,...] and velocity [d or 1,...]")
+            self._keep += [rho, u]
+            o.rho, o.u = rho.data_ptr(), u.data_ptr()
+            for a in range(d):
+                o.rho_stride[a] = rho.stride(a + 1) if rho.shape[a + 1] > 1 else 0
+                o.u_stride[a + 1] = u.stride(a + 1) if u.shape[a + 1] > 1 else 0
+            o.u_stride[0] = u.stride(0) if u.shape[0] > 1 else 0
+        if kind in (OP_OUTLET_P, OP_ANTI_BOUNCE_BACK):
+            direction = getattr(op, "direction", None)
+            if direction is None:       # the reference keeps only index lists (equilibrium_outlet_p.py:36-49)
+                direction = [0 if isinstance(ix, slice) else (1 if ix == -1 else -1) for ix in op.index]
+            o.axis, o.side = _direction_axis_side(direction)
+            if kind == OP_OUTLET_P:
+                o.p0 = float(op.rho_outlet)
+
+    def refresh_parameters(self):
+        """Re-read scalar operator parameters (the reference passes 1/tau on every call,
+        cuda_native/ext/_collision/bgk_collision.py:29-33)."""
+        for i, op in enumerate(self.transformer):
+            o = self.desc.ops[i]
+            if o.kind == OP_BGK:
+                o.p0 = float(op.tau)
+            elif o.kind == OP_TRT:
+                o.p0, o.p1 = float(op.tau_plus), float(op.tau_minus)
+            elif o.kind == OP_KBC:
+                o.p0 = float(op.tau)
+
+    def _pack_masks(self):
+        sim = self.simulation
+        ncm, nsm = sim.no_collision_mask, sim.no_streaming_mask
+        if ncm is None or nsm is None:
+            raise RuntimeError("boundaries are present but the simulation has no masks "
+                               "(lettuce/cuda_native/_template.py python_pre asserts the same)")
+        ncm = ncm.to(device=self.device, dtype=torch.uint8).contiguous()
+        nsm = nsm.to(device=self.device, dtype=torch.uint8).contiguous()
+        n = ncm.numel()
+        self.labels = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.frozen = torch.empty(n, dtype=torch.int32, device=self.device)
+        check(self.lib.lbm_pack_masks(C.byref(self.desc), ncm.data_ptr(), nsm.data_ptr(),
+                                      self.labels.data_ptr(), self.frozen.data_ptr(), _stream_ptr(self.device)),
+              "lbm_pack_masks")
+        self.desc.labels = self.labels.data_ptr()
+        self.desc.frozen = self.frozen.data_ptr()
+
+    # -- stepping ------------------------------------------------------------
+    def _buffers(self):
+        flow = self.flow
+        f, g = flow.f, flow.f_next
+        _require_cuda(f, "flow.f")
+        _require_cuda(g, "flow.f_next")
+        if g.shape != f.shape or g.dtype != f.dtype:
+            raise RuntimeError("flow.f_next does not match flow.f")
+        return f, g
+
+    def step(self, n: int = 1):
+        """Advance `n` time steps; afterwards flow.f holds the new populations."""
+        if n <= 0:
+            return
+        self.refresh_parameters()
+        f, g = self._buffers()
+        flow = self.flow
+        with torch.cuda.device(self.device):
+            stream = _stream_ptr(self.device)
+            if n == 1:
+                check(self.lib.lbm_step(C.byref(self.desc), f.data_ptr(), g.data_ptr(), stream), "lbm_step")
+            else:
+                check(self.lib.lbm_step_n(C.byref(self.desc), f.data_ptr(), g.data_ptr(), n, stream), "lbm_step_n")
+        if n % 2 == 1:
+            flow.f, flow.f_next = g, f
+
+
+def engine_of(simulation) -> Engine:
+    eng = getattr(simulation, "_b200_engine", None)
+    if eng is None or eng.flow is not simulation.flow:
+        eng = Engine(simulation)
+        simulation._b200_engine = eng
+    return eng
+
+
+def invoke(simulation):
+    """One time step on the B200 engine; drop-in for the reference's generated
+    `invoke(simulation)` (lettuce/cuda_native/_template.py:35-39)."""
+    engine_of(simulation).step(1)
+
+
+def invoke_n(simulation, num_steps: int):
+    """`num_steps` time steps without returning to Python in between."""
+    engine_of(simulation).step(int(num_steps))
+
+
+# --------------------------------------------------------------------------
+# moments and reductions on populations (Flow.rho/j/u and the observables)
+# --------------------------------------------------------------------------
+def moments(stencil, f: torch.Tensor, want_rho=True, want_u=True):
+    """(rho [1,*res] or None, u [d,*res] or None) of populations `f` (lettuce/_flow.py:157-193)."""
+    _require_cuda(f, "f")
+    lat = lattice_of(stencil, f.shape[1:], f.dtype)
+    res = list(f.shape[1:])
+    rho = torch.empty([1, *res], dtype=f.dtype, device=f.device) if want_rho else None
+    u = torch.empty([stencil.d, *res], dtype=f.dtype, device=f.device) if want_u else None
+    with torch.cuda.device(f.device):
+        check(lib().lbm_moments(C.byref(lat), f.data_ptr(), rho.data_ptr() if want_rho else None,
+                                u.data_ptr() if want_u else None, _stream_ptr(f.device)), "lbm_moments")
+    return rho, u
+
+
+_scratch = {}
+
+
+def reduce(stencil, what: int, t: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Deterministic reduction `what` (one of SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED,
+    ENSTROPHY); returns a 0-d float64 CUDA tensor (no host sync)."""
+    _require_cuda(t, "input")
+    lat = lattice_of(stencil, t.shape[1:], t.dtype)
+    L = lib()
+    key = (t.device, torch.cuda.current_stream(t.device).cuda_stream)
+    if key not in _scratch:
+        _scratch[key] = torch.empty(int(L.lbm_reduce_scratch_bytes(C.byref(lat))), dtype=torch.uint8, device=t.device)
+    out = torch.empty((), dtype=torch.float64, device=t.device)
+    mptr = None
+    if mask is not None:
+        mask = mask.to(device=t.device, dtype=torch.uint8).contiguous()
+        mptr = mask.data_ptr()
+    with torch.cuda.device(t.device):
+        check(L.lbm_reduce(C.byref(lat), what, t.data_ptr(), mptr, _scratch[key].data_ptr(), out.data_ptr(),
+                           _stream_ptr(t.device)), "lbm_reduce")
+    return out

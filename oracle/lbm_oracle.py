@@ -67,7 +67,9 @@ def stencil(name: str):
     return dict(name=name, e=e, w=w, opposite=opposite, d=e.shape[1], q=e.shape[0])
 
 
-CS = 1.0 / np.sqrt(3.0)           # lettuce/_stencil.py:19
+# Python floats (not np.float64 scalars) so that float32 populations stay float32 under NumPy's
+# promotion rules, like torch keeps the context dtype when multiplying by Python scalars.
+CS = float(1.0 / np.sqrt(3.0))    # lettuce/_stencil.py:19
 CS2 = CS ** 2                     # the reference squares the rounded 1/sqrt(3)
 
 

@@ -1,0 +1,244 @@
+"""CPU-only tests of the host side: API surface, stencil tables, unit conversion, initial
+conditions and mask construction against the golden vectors, descriptor packing, the C ABI's
+exported symbols, and that nothing steps on the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, max_rel
+import lettuce_b200 as lt
+from lettuce_b200 import native
+from oracle import lbm_oracle as lo
+
+STENCILS = {"D2Q9": lt.D2Q9, "D3Q19": lt.D3Q19, "D3Q27": lt.D3Q27}
+
+
+def cpu(dtype=torch.float64):
+    return lt.Context("cpu", dtype=dtype)
+
+
+def test_stencils_match_oracle_tables():
+    for name, cls in STENCILS.items():
+        s, o = cls(), lo.stencil(name)
+        assert np.array_equal(np.asarray(s.e), o["e"])
+        assert np.allclose(np.asarray(s.w), o["w"], rtol=0, atol=0)
+        assert list(s.opposite) == list(o["opposite"])
+        assert (s.d, s.q) == (o["d"], o["q"])
+
+
+def test_cuda_stencil_tables_match_host_tables():
+    """parse the constexpr tables in csrc/lbm_core.cuh and compare with the Python ones"""
+    src = open(os.path.join(ROOT, "lettuce_b200", "csrc", "lbm_core.cuh")).read()
+    for name, cls in STENCILS.items():
+        body = src[src.index(f"struct {name} "):]
+        table = body[body.index("constexpr int t["):body.index("};") + 2]
+        nums = [int(x) for x in re.findall(r"-?\d+", table[table.index("=") + 1:])]
+        e = np.array(nums).reshape(-1, 3)
+        ref = np.asarray(cls().e)
+        if name == "D2Q9":      # internal axes (x, -, y)
+            assert np.array_equal(e[:, [0, 2]], ref) and (e[:, 1] == 0).all()
+        else:
+            assert np.array_equal(e, ref)
+
+
+def test_context_rules():
+    c = lt.Context("cpu")
+    assert c.dtype == torch.float32 and c.use_native is False
+    with pytest.raises(AssertionError):
+        lt.Context("cpu", use_native=True)
+    with pytest.raises(AssertionError):
+        lt.Context("cpu", dtype=torch.int32)
+    assert c.convert_to_tensor(np.array([True, False])).dtype == torch.uint8
+    assert c.convert_to_tensor([1, 2]).dtype == torch.float32
+
+
+def test_units_match_oracle():
+    u = lt.UnitConversion(reynolds_number=1600, mach_number=0.05, characteristic_length_lu=32 / (2 * np.pi))
+    o = lo.Units(1600, 0.05, 32 / (2 * np.pi))
+    assert u.relaxation_parameter_lu == o.tau
+    assert u.convert_velocity_to_lu(0.7) == o.velocity_to_lu(0.7)
+    assert u.convert_pressure_pu_to_density_lu(0.3) == o.pressure_pu_to_density_lu(0.3)
+    assert u.convert_incompressible_energy_to_pu(2.0) == o.incompressible_energy_to_pu(2.0)
+    assert u.convert_time_to_pu(10) == o.time_to_pu(10)
+    for a, b in (("velocity", 0.3), ("time", 4.0), ("length", 2.0), ("pressure", 0.1), ("density", 1.1),
+                 ("energy", 0.2), ("incompressible_energy", 0.2), ("acceleration", 0.4)):
+        there = getattr(u, f"convert_{a}_to_lu")(b)
+        assert getattr(u, f"convert_{a}_to_pu")(there) == pytest.approx(b, rel=1e-14)
+
+
+@pytest.mark.parametrize("name", ["tgv2d_d2q9_bgk", "tgv3d_d3q19_bgk", "tgv3d_d3q27_kbc", "tgv3d_d3q27_trt"])
+def test_tgv_initial_condition_matches_reference(name):
+    g = load_golden(name)
+    stencil, coll, steps, re_, ma = g["meta"]
+    flow = lt.TaylorGreenVortex(cpu(), [int(r) for r in g["res"]], float(re_), float(ma), stencil=STENCILS[stencil]())
+    assert max_rel(flow.f.numpy(), g["f0"]) < 1e-14
+    assert flow.units.relaxation_parameter_lu == pytest.approx(float(g["tau"]), rel=1e-15)
+    assert flow.f.is_contiguous()
+
+
+class ObstacleEqOut(lt.Obstacle):
+    @property
+    def post_boundaries(self):
+        x = self.grid[0]
+        return [lt.EquilibriumBoundaryPU(flow=self, context=self.context, mask=torch.abs(x) < 1e-6,
+                                         velocity=self.units.characteristic_velocity_pu * self._unit_vector()),
+                lt.EquilibriumOutletP(direction=self._unit_vector().tolist(), flow=self, rho_outlet=1.0),
+                lt.BounceBackBoundary(self.mask)]
+
+
+def make_obstacle(cls, ctx, res, stencil):
+    D = res[1] / 8
+    flow = cls(ctx, list(res), reynolds_number=100, mach_number=0.05, domain_length_x=res[0] / D, stencil=stencil)
+    g = flow.grid
+    c = [0.25 * g[0].max()] + [0.5 * gi.max() for gi in g[1:]]
+    flow.mask = sum((gi - ci) ** 2 for gi, ci in zip(g, c)) < 0.5 ** 2
+    flow.initialize()
+    return flow
+
+
+@pytest.mark.parametrize("name,cls", [("cylinder_d2q9_bgk", ObstacleEqOut), ("sphere_d3q27_trt", ObstacleEqOut),
+                                      ("obstacle2d_abb_bgk", lt.Obstacle), ("obstacle3d_abb_bgk", lt.Obstacle)])
+def test_obstacle_state_and_masks_match_reference(name, cls):
+    g = load_golden(name)
+    stencil = str(g["meta"][0])
+    flow = make_obstacle(cls, cpu(), [int(r) for r in g["res"]], STENCILS[stencil]())
+    assert np.array_equal(flow.mask.numpy(), g["solid"].astype(bool))
+    assert max_rel(flow.f.numpy(), g["f0"]) < 1e-14
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+    assert sim.no_collision_mask.dtype == torch.uint8 and sim.no_streaming_mask.dtype == torch.uint8
+    assert np.array_equal(sim.no_collision_mask.numpy(), g["ncm"])
+    assert np.array_equal(sim.no_streaming_mask.numpy(), g["nsm"])
+    assert sim.collision_index == 0 and len(sim.transformer) == 4
+
+
+def test_checked_tensor_rules():
+    """equilibrium_boundary_pu.py:23-69"""
+    flow = lt.TaylorGreenVortex(cpu(), [6, 5], 10, 0.05, stencil=lt.D2Q9())
+    ct = lambda t: lt.EquilibriumBoundaryPU.checked_tensor(t, flow.context, flow)
+    assert list(ct(0.5).shape) == [1, 1, 1]
+    assert list(ct([0.1, 0.2]).shape) == [2, 1, 1]
+    assert list(ct(np.zeros((6, 5))).shape) == [1, 6, 5]
+    assert list(ct(np.zeros((2, 6, 1))).shape) == [2, 6, 1]
+    with pytest.raises(ValueError):
+        ct(np.zeros((3, 6, 5)))
+    with pytest.raises(ValueError):
+        ct(np.zeros((2, 4, 5)))
+    with pytest.raises(ValueError):
+        ct(np.zeros((2, 2, 2, 2)))
+    with pytest.raises(TypeError):
+        ct("nope")
+
+
+def test_outlet_direction_validation():
+    flow = lt.TaylorGreenVortex(cpu(), [6, 5], 10, 0.05, stencil=lt.D2Q9())
+    with pytest.raises(AssertionError):
+        lt.EquilibriumOutletP([1, 1], flow)
+    with pytest.raises(AssertionError):
+        lt.EquilibriumOutletP([0, 0], flow)
+    o = lt.EquilibriumOutletP([0, -1], flow, rho_outlet=1.2)
+    assert list(o.velocities) == [4, 7, 8] and o.index == [slice(None), 0] and o.neighbor == [slice(None), 1]
+
+
+def test_no_cpu_path():
+    flow = lt.TaylorGreenVortex(cpu(), [8, 8], 10, 0.05, stencil=lt.D2Q9())
+    sim = lt.Simulation(flow, lt.BGKCollision(0.8), [])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sim(1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        flow.rho()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lt.IncompressibleKineticEnergy(flow)()
+
+
+def test_unsupported_operators_raise():
+    class Smagorinsky(lt.Collision):
+        pass
+
+    with pytest.raises(NotImplementedError):
+        native.op_kind(Smagorinsky())
+    with pytest.raises(NotImplementedError):
+        lt.BGKCollision(0.6, force=object())
+    assert native.op_kind(lt.KBCCollision()) == native.OP_KBC
+
+    class MyBB(lt.BounceBackBoundary):
+        pass
+
+    assert native.op_kind(MyBB(None)) == native.OP_BOUNCE_BACK
+    assert MyBB(None).native_available() and not Smagorinsky().native_available()
+
+
+def test_streaming_strategy_bits():
+    S = lt.StreamingStrategy
+    assert [s.value for s in (S.NO_STREAMING, S.POST_STREAMING, S.PRE_STREAMING, S.DOUBLE_STREAMING)] == [0, 1, 2, 3]
+    assert S.DOUBLE_STREAMING.pre_streaming() and S.DOUBLE_STREAMING.post_streaming()
+    assert S.PRE_STREAMING.pre_streaming() and not S.PRE_STREAMING.post_streaming()
+
+
+def test_batch_length_respects_reporters():
+    flow = lt.TaylorGreenVortex(cpu(), [8, 8], 10, 0.05, stencil=lt.D2Q9())
+    rep = lt.ObservableReporter(lt.Mass(flow), interval=7, out=None)
+    sim = lt.Simulation(flow, lt.BGKCollision(0.8), [rep])
+    flow.i = 0
+    assert sim._batch_length(100) == 7
+    flow.i = 5
+    assert sim._batch_length(100) == 2
+    assert sim._batch_length(1) == 1
+
+    class EveryStep(lt.Reporter):
+        def __call__(self, simulation):
+            pass
+
+    sim.reporter.append(EveryStep(3))
+    assert sim._batch_length(100) == 1
+    sim.reporter.pop()
+    sim._collide_and_stream = lambda s: None          # user-installed step
+    assert sim._batch_length(100) == 1
+
+
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    L = native.lib()
+    header = open(os.path.join(ROOT, "include", "lbm_b200.h")).read()
+    declared = set(re.findall(r"\b(lbm_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in include/lbm_b200.h but not exported"
+    assert set(native.EXPORTS) == declared
+    assert L.lbm_abi_version() == 1
+    assert b"unsupported" in L.lbm_status_string(-2)
+
+
+def test_ctypes_struct_layout_matches_header():
+    """sizes computed from the C declaration: lbm_op = 4*4 + 2*8 + 2*8 + 3*8 + 4*8 = 104 bytes"""
+    assert ctypes.sizeof(native.LbmOp) == 104
+    assert ctypes.sizeof(native.LbmLattice) == 24
+    assert ctypes.sizeof(native.LbmHalo) == 12 * 8
+    assert ctypes.sizeof(native.LbmStepDesc) == 24 + 16 + 8 * 104 + 16 + 96
+
+
+def test_descriptor_validation_without_gpu():
+    """argument validation happens before any CUDA call, so it is testable here"""
+    L = native.lib()
+    d = native.LbmStepDesc()
+    d.lat = native.LbmLattice(native.D3Q19, native.F32, 8, 8, 8, 0)
+    d.streaming, d.n_ops, d.collision_index = 1, 1, 0
+    d.ops[0].kind, d.ops[0].p0 = native.OP_KBC, 0.6
+    assert L.lbm_step(ctypes.byref(d), 1 << 20, 1 << 30, None) == -2          # KBC on D3Q19
+    d.ops[0].kind = native.OP_BGK
+    assert L.lbm_step(ctypes.byref(d), None, 1 << 30, None) == -1            # NULL buffer
+    assert L.lbm_step(ctypes.byref(d), 1 << 20, (1 << 20) + 64, None) == -4  # overlap
+    d.lat.nx = 0
+    assert L.lbm_step(ctypes.byref(d), 1 << 20, 1 << 30, None) == -1
+    d.lat = native.LbmLattice(native.D2Q9, native.F32, 8, 8, 2, 0)
+    assert L.lbm_step(ctypes.byref(d), 1 << 20, 1 << 30, None) == -1          # D2Q9 needs nz = 1
+    d.lat = native.LbmLattice(native.D3Q27, native.F32, 2048, 2048, 1024, 0)
+    assert L.lbm_step(ctypes.byref(d), 1 << 20, 1 << 50, None) == -5          # >= 2^31 nodes
+    d.lat = native.LbmLattice(native.D3Q27, native.F32, 8, 8, 8, 0)
+    d.n_ops = 3
+    d.ops[1].kind, d.ops[1].axis, d.ops[1].side = native.OP_OUTLET_P, 0, 1
+    d.ops[2].kind, d.ops[2].axis, d.ops[2].side = native.OP_OUTLET_P, 1, 1
+    d.labels, d.frozen = 1 << 20, 1 << 21
+    assert L.lbm_step(ctypes.byref(d), 1 << 22, 1 << 30, None) == -2          # outlets on two axes
