@@ -187,6 +187,46 @@ int lbm_reduce(const lbm_lattice *lat, int what, const void *d_in, const uint8_t
 int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int64_t nsteps,
                  double *h_energy);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU x-slabs, one process per GPU (no counterpart in the reference, which is single-device:
+ * lettuce/_context.py:60 stores one torch.device).  Each rank owns nx_local planes; the step kernel
+ * of a rank loads (pull) or stores (push) the neighbour ranks' boundary planes DIRECTLY through
+ * peer-mapped pointers over NVLink -- there are no ghost planes, no pack kernels and no separate
+ * exchange step.  Buffers that peers must see are allocated with lbm_ipc_alloc and opened on the
+ * neighbour with lbm_ipc_open (CUDA IPC).  Ranks stay in lock step through one 8-byte progress
+ * counter per neighbour written over NVLink after every step.
+ * ------------------------------------------------------------------------------------------- */
+#define LBM_IPC_HANDLE_BYTES 64
+
+/* cudaMalloc + zero fill + cudaIpcGetMemHandle.  `handle` receives LBM_IPC_HANDLE_BYTES bytes to ship
+ * to the neighbour process. */
+int lbm_ipc_alloc(size_t bytes, void **d_ptr, void *handle);
+/* Map a neighbour's allocation into this process (cudaIpcOpenMemHandle, peer access enabled lazily). */
+int lbm_ipc_open(const void *handle, void **d_ptr);
+int lbm_ipc_close(void *d_ptr);
+int lbm_ipc_free(void *d_ptr);
+
+typedef struct lbm_slab {
+    /* peer-mapped base addresses of the neighbours' two population buffers, in the same (a, b) order
+     * as the arguments of lbm_slab_step_n.  lo = rank owning the planes below x = 0, hi = the rank
+     * owning the planes from x = nx_local on (periodic ring). */
+    void *lo_a, *lo_b, *hi_a, *hi_b;
+    int32_t lo_nx, hi_nx;          /* slab thickness of the neighbours */
+    /* peer-mapped addresses where this rank publishes the number of steps it has completed: slot 1 of
+     * the lo neighbour's counter pair and slot 0 of the hi neighbour's */
+    uint64_t *signal_lo, *signal_hi;
+    /* this rank's own counter pair (in lbm_ipc_alloc memory): [0] written by lo, [1] written by hi */
+    const uint64_t *wait_slots;
+    uint64_t epoch;                /* steps completed before this call; identical on all ranks */
+} lbm_slab;
+
+/* n lock-stepped time steps on an x-slab.  After every step the rank publishes its progress to both
+ * neighbours and waits (on the device, inside a 1-thread kernel) until both have completed the same
+ * step, which orders the peer reads/writes of consecutive steps.  desc->halo's population pointers
+ * are ignored (they are derived from `slab`); its label/frozen pointers are used as given. */
+int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
+                    void *stream);
+
 /* Introspection. */
 int lbm_abi_version(void);
 const char *lbm_status_string(int status);

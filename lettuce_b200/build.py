@@ -32,7 +32,8 @@ REALS = ("float", "double")
 
 def _units():
     units = [("lbm_api", os.path.join(CSRC, "lbm_api.cu"), []),
-             ("lbm_moments", os.path.join(CSRC, "lbm_moments.cu"), [])]
+             ("lbm_moments", os.path.join(CSRC, "lbm_moments.cu"), []),
+             ("lbm_slab", os.path.join(CSRC, "lbm_slab.cu"), [])]
     for s in STENCILS:
         for r in REALS:
             units.append((f"lbm_step_{s}_{r}", os.path.join(CSRC, "lbm_step_inst.cu"),

@@ -25,6 +25,8 @@ static int cuda_fail(int e) {
     return LBM_ERR_CUDA;
 }
 
+int cuda_fail_public(int e) { return cuda_fail(e); }
+
 struct Dims {
     int n0, n1, n2, d, q;
 };

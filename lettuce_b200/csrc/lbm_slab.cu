@@ -1,0 +1,111 @@
+// lbm_slab.cu -- multi-GPU x-slab plumbing of the C ABI: CUDA-IPC allocation, peer progress
+// counters and the lock-stepped slab step loop.  The halo "exchange" itself is not here: it is the
+// step kernel reading/writing the neighbour's boundary planes through the peer-mapped pointers that
+// lbm_slab_step_n puts into the descriptor (csrc/lbm_step.cuh, in_plane / out_plane).
+#include <cstring>
+
+#include "lbm_launch.cuh"
+
+namespace lbm {
+
+int cuda_fail_public(int e);
+
+// One thread: publish `epoch` to both neighbours, then wait until both neighbours have published it.
+// Everything this rank's step kernel wrote (also into peer memory) is complete when this kernel starts
+// (stream order); the system-scope fences order the counter against those writes for the peers.
+__global__ void peer_signal_wait_kernel(unsigned long long *sig_lo, unsigned long long *sig_hi,
+                                        const unsigned long long *wait_slots, unsigned long long epoch) {
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    *(volatile unsigned long long *)sig_lo = epoch;
+    *(volatile unsigned long long *)sig_hi = epoch;
+    __threadfence_system();
+    const volatile unsigned long long *w = wait_slots;
+    const long long t0 = clock64();
+    while (w[0] < epoch || w[1] < epoch) {
+        // a neighbour that never arrives (crashed rank) must not hang the GPU: ~20 s at 2 GHz, then fault
+        if (clock64() - t0 > 40000000000LL) __trap();
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+}  // namespace lbm
+
+using namespace lbm;
+
+extern "C" {
+
+int lbm_ipc_alloc(size_t bytes, void **d_ptr, void *handle) {
+    if (!d_ptr || !handle || bytes == 0) return LBM_ERR_BAD_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == LBM_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    int e = (int)cudaMalloc(&p, bytes);
+    if (e) return cuda_fail_public(e);
+    if ((e = (int)cudaMemset(p, 0, bytes))) { cudaFree(p); return cuda_fail_public(e); }
+    cudaIpcMemHandle_t h;
+    if ((e = (int)cudaIpcGetMemHandle(&h, p))) { cudaFree(p); return cuda_fail_public(e); }
+    memcpy(handle, &h, sizeof h);
+    *d_ptr = p;
+    return LBM_OK;
+}
+
+int lbm_ipc_open(const void *handle, void **d_ptr) {
+    if (!handle || !d_ptr) return LBM_ERR_BAD_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    const int e = (int)cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e) return cuda_fail_public(e);
+    *d_ptr = p;
+    return LBM_OK;
+}
+
+int lbm_ipc_close(void *d_ptr) {
+    if (!d_ptr) return LBM_ERR_BAD_ARGUMENT;
+    return cuda_fail_public((int)cudaIpcCloseMemHandle(d_ptr));
+}
+
+int lbm_ipc_free(void *d_ptr) {
+    if (!d_ptr) return LBM_ERR_BAD_ARGUMENT;
+    return cuda_fail_public((int)cudaFree(d_ptr));
+}
+
+int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
+                    void *stream) {
+    if (!desc || !slab || !d_f_a || !d_f_b || n < 0) return LBM_ERR_BAD_ARGUMENT;
+    if (!slab->lo_a || !slab->lo_b || !slab->hi_a || !slab->hi_b || !slab->signal_lo || !slab->signal_hi ||
+        !slab->wait_slots || slab->lo_nx < 1 || slab->hi_nx < 1)
+        return LBM_ERR_BAD_ARGUMENT;
+    const size_t es = desc->lat.dtype == LBM_F32 ? 4 : 8;
+    const int64_t plane = (int64_t)desc->lat.ny * desc->lat.nz;
+    lbm_step_desc d = *desc;
+    void *a = d_f_a, *b = d_f_b;
+    char *lo_in = (char *)slab->lo_a, *lo_out = (char *)slab->lo_b;
+    char *hi_in = (char *)slab->hi_a, *hi_out = (char *)slab->hi_b;
+    unsigned long long epoch = slab->epoch;
+    for (int64_t k = 0; k < n; ++k) {
+        // x = -1 is the LAST plane of the lo neighbour, x = nx is the FIRST plane of the hi neighbour
+        d.halo.in_lo = lo_in + (size_t)(slab->lo_nx - 1) * plane * es;
+        d.halo.out_lo = lo_out + (size_t)(slab->lo_nx - 1) * plane * es;
+        d.halo.in_lo_qstride = d.halo.out_lo_qstride = (int64_t)slab->lo_nx * plane;
+        d.halo.in_hi = hi_in;
+        d.halo.out_hi = hi_out;
+        d.halo.in_hi_qstride = d.halo.out_hi_qstride = (int64_t)slab->hi_nx * plane;
+        const int rc = lbm_step(&d, a, b, stream);
+        if (rc) return rc;
+        ++epoch;
+        peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)slab->signal_lo,
+                                                                    (unsigned long long *)slab->signal_hi,
+                                                                    (const unsigned long long *)slab->wait_slots, epoch);
+        ++g_launch_count;
+        const int e = (int)cudaGetLastError();
+        if (e) return cuda_fail_public(e);
+        void *t = a; a = b; b = t;
+        char *c = lo_in; lo_in = lo_out; lo_out = c;
+        c = hi_in; hi_in = hi_out; hi_out = c;
+    }
+    return LBM_OK;
+}
+
+}  // extern "C"

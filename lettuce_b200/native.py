@@ -57,7 +57,15 @@ class LbmStepDesc(C.Structure):
                 ("labels", C.c_void_p), ("frozen", C.c_void_p), ("halo", LbmHalo)]
 
 
-EXPORTS = ["lbm_step", "lbm_step_n", "lbm_pack_masks", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
+class LbmSlab(C.Structure):
+    _fields_ = [("lo_a", C.c_void_p), ("lo_b", C.c_void_p), ("hi_a", C.c_void_p), ("hi_b", C.c_void_p),
+                ("lo_nx", C.c_int32), ("hi_nx", C.c_int32),
+                ("signal_lo", C.c_void_p), ("signal_hi", C.c_void_p), ("wait_slots", C.c_void_p),
+                ("epoch", C.c_uint64)]
+
+
+EXPORTS = ["lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
+           "lbm_step", "lbm_step_n", "lbm_pack_masks", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
            "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
            "lbm_launch_count", "lbm_step_variant_name"]
 
@@ -78,6 +86,16 @@ def lib() -> C.CDLL:
     L.lbm_step.restype = i32
     L.lbm_step_n.argtypes = [C.POINTER(LbmStepDesc), vp, vp, i64, vp]
     L.lbm_step_n.restype = i32
+    L.lbm_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+    L.lbm_ipc_alloc.restype = i32
+    L.lbm_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    L.lbm_ipc_open.restype = i32
+    L.lbm_ipc_close.argtypes = [vp]
+    L.lbm_ipc_close.restype = i32
+    L.lbm_ipc_free.argtypes = [vp]
+    L.lbm_ipc_free.restype = i32
+    L.lbm_slab_step_n.argtypes = [C.POINTER(LbmStepDesc), C.POINTER(LbmSlab), vp, vp, i64, vp]
+    L.lbm_slab_step_n.restype = i32
     L.lbm_pack_masks.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, vp, vp]
     L.lbm_pack_masks.restype = i32
     L.lbm_moments.argtypes = [C.POINTER(LbmLattice), vp, vp, vp, vp]

@@ -1,0 +1,282 @@
+"""Multi-GPU x-slab decomposition, one process per GPU.
+
+The reference has no multi-device code at all; this module is the B200-native
+addition.  The global lattice `[nx, ny(, nz)]` is cut along x -- the slowest axis, so every plane
+`f[q, x, :, :]` stays contiguous -- into one slab per rank.  Streaming across a cut is not a separate
+exchange: every rank maps its two neighbours' population buffers with CUDA IPC and the step kernel
+loads (pull) or stores (push) the neighbour's boundary plane directly over NVLink
+(csrc/lbm_step.cuh `in_plane`/`out_plane`, csrc/lbm_slab.cu).  Ranks are kept in lock step by one
+8-byte progress counter per neighbour, written through the same peer mapping after every step.
+`torch.distributed` is only the control plane (handle exchange, reporter all-reduce).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import native
+from ._simulation import Simulation, StreamingStrategy
+from .ext.flows import TaylorGreenVortex
+from .ext.reporter import Observable
+
+__all__ = ["SlabDecomposition", "SlabTaylorGreenVortex", "SlabSimulation", "SlabEngine",
+           "GlobalSum", "GlobalMax", "make_tgv_slab_simulation"]
+
+
+class SlabDecomposition:
+    """Contiguous x-ranges per rank; the first `nx % world` ranks get one extra plane."""
+
+    def __init__(self, nx_global: int, world: int, rank: int):
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError(f"bad rank {rank} of {world}")
+        if nx_global < world:
+            raise ValueError(f"{nx_global} planes cannot be split over {world} ranks")
+        base, rem = divmod(int(nx_global), int(world))
+        self.sizes = [base + (1 if r < rem else 0) for r in range(world)]
+        self.offsets = [sum(self.sizes[:r]) for r in range(world)]
+        self.nx_global, self.world, self.rank = int(nx_global), int(world), int(rank)
+        self.x0 = self.offsets[rank]
+        self.nx_local = self.sizes[rank]
+        self.x1 = self.x0 + self.nx_local
+        self.lo = (rank - 1) % world          # owner of global plane x0 - 1 (periodic ring: the reference
+        self.hi = (rank + 1) % world          # streams with torch.roll even for inlet/outlet flows)
+
+    def owner_of(self, x: int) -> int:
+        x %= self.nx_global
+        for r in range(self.world):
+            if self.offsets[r] <= x < self.offsets[r] + self.sizes[r]:
+                return r
+        raise AssertionError
+
+    def local_slice(self) -> slice:
+        return slice(self.x0, self.x1)
+
+    def halo_indices(self, width: int) -> List[int]:
+        """global x indices of the slab extended by `width` planes on both sides (periodic)"""
+        return [(x % self.nx_global) for x in range(self.x0 - width, self.x1 + width)]
+
+
+class SlabTaylorGreenVortex(TaylorGreenVortex):
+    """The rank-local slab of a global Taylor-Green vortex.  `resolution` is the LOCAL slab,
+    `global_resolution` the whole lattice; units come from the global lattice.  The initial state is
+    evaluated on the slab extended by three planes (the radius of the 6th-order stencil in
+    `initialize_f_neq`) and cropped, so it equals the corresponding slice of the global initial state."""
+    _HALO = 3
+
+    def __init__(self, context, global_resolution, reynolds_number, mach_number, stencil,
+                 decomposition: SlabDecomposition, equilibrium=None, initialize_fneq: bool = True):
+        self.decomposition = decomposition
+        self.global_resolution = [int(r) for r in global_resolution]
+        assert decomposition.nx_global == self.global_resolution[0]
+        self._extended = False
+        local = [decomposition.nx_local] + self.global_resolution[1:]
+        TaylorGreenVortex.__init__(self, context, local, reynolds_number, mach_number, stencil, equilibrium,
+                                   initialize_fneq)
+
+    def make_units(self, reynolds_number, mach_number, resolution):
+        return TaylorGreenVortex.make_units(self, reynolds_number, mach_number, self.global_resolution)
+
+    @property
+    def grid(self):
+        g = self.global_resolution
+        axes = [torch.linspace(0, 2 * torch.pi * (1 - 1 / n), steps=n, device=self.context.device,
+                               dtype=self.context.dtype) for n in g]
+        dec = self.decomposition
+        idx = dec.halo_indices(self._HALO if self._extended else 0)
+        axes[0] = axes[0][torch.as_tensor(idx, device=self.context.device)]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    def initialize(self):
+        h = self._HALO
+        local = list(self.resolution)
+        self._extended = True
+        self.resolution = [local[0] + 2 * h] + local[1:]
+        try:
+            TaylorGreenVortex.initialize(self)
+            self.f = self.f[:, h:-h].contiguous()
+        finally:
+            self._extended = False
+            self.resolution = local
+        self._f_next = None
+
+
+class _RawCuda:
+    """exposes a raw device allocation to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class _IpcBuffer:
+    def __init__(self, nbytes: int):
+        L = native.lib()
+        self.ptr = C.c_void_p()
+        self.handle = (C.c_ubyte * 64)()
+        native.check(L.lbm_ipc_alloc(C.c_size_t(nbytes), C.byref(self.ptr), self.handle), "lbm_ipc_alloc")
+        self.nbytes = nbytes
+        self.freed = False
+
+    def tensor(self, shape, dtype, device) -> torch.Tensor:
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+        t = torch.as_tensor(_RawCuda(self.ptr.value, shape, typestr), device=device)
+        assert t.data_ptr() == self.ptr.value
+        return t
+
+    def free(self):
+        if not self.freed:
+            native.lib().lbm_ipc_free(self.ptr)
+            self.freed = True
+
+
+class SlabEngine(native.Engine):
+    """Engine of one rank's slab: IPC population buffers, neighbour mappings, lock-stepped stepping."""
+
+    def __init__(self, simulation, decomposition: SlabDecomposition, group=None):
+        super().__init__(simulation)
+        self.dec = decomposition
+        self.group = group
+        flow = self.flow
+        L = self.lib
+        with torch.cuda.device(self.device):
+            nbytes = flow.f.numel() * flow.f.element_size()
+            self.buf = [_IpcBuffer(nbytes), _IpcBuffer(nbytes)]
+            self.flags = _IpcBuffer(256)
+            shape = tuple(flow.f.shape)
+            self.t = [b.tensor(shape, flow.f.dtype, self.device) for b in self.buf]
+            self.t[0].copy_(flow.f)
+            torch.cuda.synchronize(self.device)
+        flow.f, flow.f_next = self.t[0], self.t[1]
+        self.cur = 0
+        self.epoch = 0
+        # control plane: ship (handles, slab thickness) to everybody, map the two neighbours
+        mine = (bytes(self.buf[0].handle), bytes(self.buf[1].handle), bytes(self.flags.handle), self.dec.nx_local)
+        if self.dec.world > 1:
+            everyone = [None] * self.dec.world
+            dist.all_gather_object(everyone, mine, group=group)
+        else:
+            everyone = [mine]
+        self._peers = {}
+        self.lo = self._map_peer(self.dec.lo, everyone)
+        self.hi = self._map_peer(self.dec.hi, everyone)
+        if self.dec.world > 1:
+            dist.barrier(group=group)       # every rank has filled its buffer and mapped its neighbours
+
+    def _map_peer(self, rank, everyone):
+        if rank in self._peers:
+            return self._peers[rank]
+        if rank == self.dec.rank:
+            ptrs = (self.buf[0].ptr.value, self.buf[1].ptr.value, self.flags.ptr.value)
+        else:
+            ptrs = []
+            with torch.cuda.device(self.device):
+                for h in everyone[rank][:3]:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(h)
+                    native.check(self.lib.lbm_ipc_open(hb, C.byref(p)), f"lbm_ipc_open(rank {rank})")
+                    ptrs.append(p.value)
+        self._peers[rank] = dict(a=ptrs[0], b=ptrs[1], flags=ptrs[2], nx=int(everyone[rank][3]))
+        return self._peers[rank]
+
+    def load(self, f: torch.Tensor):
+        """replace the rank's populations (same shape) without leaving the IPC buffers"""
+        self.t[self.cur].copy_(f)
+        self.flow.f, self.flow.f_next = self.t[self.cur], self.t[1 - self.cur]
+
+    def step(self, n: int = 1):
+        if n <= 0:
+            return
+        flow = self.flow
+        if flow.f.data_ptr() != self.t[self.cur].data_ptr():
+            raise RuntimeError("flow.f was replaced: slab populations must stay in the engine's IPC buffers "
+                               "(use engine.load(tensor))")
+        self.refresh_parameters()
+        a, b = ("a", "b") if self.cur == 0 else ("b", "a")
+        s = native.LbmSlab()
+        s.lo_a, s.lo_b, s.hi_a, s.hi_b = self.lo[a], self.lo[b], self.hi[a], self.hi[b]
+        s.lo_nx, s.hi_nx = self.lo["nx"], self.hi["nx"]
+        s.signal_lo = self.lo["flags"] + 8        # the lo neighbour's slot 1 = "written by my hi neighbour"
+        s.signal_hi = self.hi["flags"]            # the hi neighbour's slot 0 = "written by my lo neighbour"
+        s.wait_slots = self.flags.ptr.value
+        s.epoch = self.epoch
+        with torch.cuda.device(self.device):
+            native.check(self.lib.lbm_slab_step_n(C.byref(self.desc), C.byref(s), self.t[self.cur].data_ptr(),
+                                                  self.t[1 - self.cur].data_ptr(), n, native._stream_ptr(self.device)),
+                         "lbm_slab_step_n")
+        self.epoch += n
+        if n % 2 == 1:
+            self.cur = 1 - self.cur
+        flow.f, flow.f_next = self.t[self.cur], self.t[1 - self.cur]
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if self.dec.world > 1:
+            dist.barrier(group=self.group)
+        for rank, p in self._peers.items():
+            if rank != self.dec.rank:
+                for k in ("a", "b", "flags"):
+                    self.lib.lbm_ipc_close(C.c_void_p(p[k]))
+        self._peers = {}
+        if self.dec.world > 1:
+            dist.barrier(group=self.group)
+        self.flow.f = self.flow.f.clone()
+        self.flow._f_next = None
+        for b in self.buf + [self.flags]:
+            b.free()
+
+
+class SlabSimulation(Simulation):
+    """`Simulation` whose flow is one x-slab of a larger lattice.  Boundaries are not supported on
+    slabs yet (periodic flows only)."""
+
+    def __init__(self, flow, collision, reporter, streaming_strategy=StreamingStrategy.POST_STREAMING,
+                 decomposition: Optional[SlabDecomposition] = None, group=None):
+        super().__init__(flow, collision, reporter, streaming_strategy)
+        if len(self.transformer) > 1:
+            raise NotImplementedError("boundaries on multi-GPU slabs are not implemented yet")
+        self.decomposition = decomposition or flow.decomposition
+        self._b200_engine = SlabEngine(self, self.decomposition, group)
+
+    def close(self):
+        self._b200_engine.close()
+
+
+class _GlobalReduce(Observable):
+    op = None
+
+    def __init__(self, observable: Observable, group=None):
+        super().__init__(observable.flow)
+        self.observable = observable
+        self.group = group
+
+    def __call__(self, f=None):
+        v = self.observable(f).clone()
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(v, op=self.op, group=self.group)
+        return v
+
+
+class GlobalSum(_GlobalReduce):
+    """sum of a rank-local additive observable (energy, mass) over all slabs"""
+    op = dist.ReduceOp.SUM
+
+
+class GlobalMax(_GlobalReduce):
+    """max of a rank-local observable (maximum velocity) over all slabs"""
+    op = dist.ReduceOp.MAX
+
+
+def make_tgv_slab_simulation(context, global_resolution, reynolds_number, mach_number, stencil, strategy,
+                             collision_factory=None, reporter=None):
+    """(flow, simulation, stepper) for this rank's slab of a global Taylor-Green vortex."""
+    from .ext.collision import BGKCollision
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dec = SlabDecomposition(global_resolution[0], world, rank)
+    flow = SlabTaylorGreenVortex(context, global_resolution, reynolds_number, mach_number, stencil, dec)
+    collision = (collision_factory or (lambda fl: BGKCollision(fl.units.relaxation_parameter_lu)))(flow)
+    sim = SlabSimulation(flow, collision, reporter or [], strategy, dec)
+    return flow, sim, (lambda k: native.invoke_n(sim, k))

@@ -1,0 +1,133 @@
+"""Worker for the multi-rank slab tests (run under torch.distributed.run or mp.spawn).
+
+GPU mode (backend nccl): every rank steps its x-slab with the CUDA engine (peer-mapped halos), rank 0
+additionally steps the whole lattice on its own GPU; the gathered slabs must equal the single-GPU
+result BIT FOR BIT (same kernel arithmetic per node).
+
+CPU mode (backend gloo): the host-side decomposition logic is exercised with the NumPy oracle as the
+local stepper and explicit plane exchange through torch.distributed.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import lettuce_b200 as lt  # noqa: E402
+from lettuce_b200 import slab  # noqa: E402
+
+
+def gather_slabs(local: torch.Tensor, dec, device):
+    """all ranks' slabs concatenated along x on every rank"""
+    parts = []
+    for r in range(dec.world):
+        shape = list(local.shape)
+        shape[1] = dec.sizes[r]
+        buf = local.contiguous() if r == dec.rank else torch.empty(shape, dtype=local.dtype, device=device)
+        dist.broadcast(buf, src=r)
+        parts.append(buf)
+    return torch.cat(parts, dim=1)
+
+
+def gpu_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev):
+    ctx = lt.Context(dev, dtype=dtype)
+    dec = slab.SlabDecomposition(res[0], world, rank)
+    flow = slab.SlabTaylorGreenVortex(ctx, res, 1600.0, 0.05, stencil_cls(), dec)
+    make = {"bgk": lambda f: lt.BGKCollision(f.units.relaxation_parameter_lu), "kbc": lambda f: lt.KBCCollision(),
+            "trt": lambda f: lt.TRTCollision(f.units.relaxation_parameter_lu)}[coll]
+    energy = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=steps, out=None)
+    sim = slab.SlabSimulation(flow, make(flow), [energy], strategy, dec)
+    f0 = gather_slabs(flow.f, dec, dev)
+    # odd and even batch lengths exercise the buffer parity logic
+    sim(1); sim(2); sim(steps - 3)
+    got = gather_slabs(flow.f, dec, dev)
+    ok = True
+    if rank == 0:
+        ref_flow = lt.TaylorGreenVortex(ctx, res, 1600.0, 0.05, stencil=stencil_cls())
+        init_err = float((ref_flow.f - f0).abs().max())
+        ref_flow.f = f0.clone()
+        ref_energy = lt.ObservableReporter(lt.IncompressibleKineticEnergy(ref_flow), interval=steps, out=None)
+        ref = lt.Simulation(ref_flow, make(ref_flow), [ref_energy], strategy)
+        ref(steps)
+        same = torch.equal(ref_flow.f, got)
+        e_rel = abs(energy.out[-1][2] - ref_energy.out[-1][2]) / abs(ref_energy.out[-1][2])
+        print(f"[slab] {stencil_cls.__name__} {res} {coll} {strategy.name} {dtype} world={world}: "
+              f"bit-exact={same} init_err={init_err:.1e} energy_rel={e_rel:.1e}", flush=True)
+        ok = same and init_err < 1e-6 and e_rel < 1e-6
+    sim.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    return bool(flag.item())
+
+
+def gpu_main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    S = lt.StreamingStrategy
+    cases = [(lt.D3Q19, [32, 24, 40], "bgk", S.PRE_STREAMING, torch.float32, 9),
+             (lt.D3Q19, [32, 24, 40], "bgk", S.POST_STREAMING, torch.float32, 9),
+             (lt.D3Q27, [19, 16, 24], "kbc", S.POST_STREAMING, torch.float64, 8),
+             (lt.D3Q27, [19, 16, 24], "trt", S.DOUBLE_STREAMING, torch.float32, 8),
+             (lt.D2Q9, [48, 40], "bgk", S.PRE_STREAMING, torch.float64, 10),
+             (lt.D2Q9, [50, 32], "kbc", S.POST_STREAMING, torch.float32, 10),
+             (lt.D3Q19, [world * 2, 16, 32], "bgk", S.POST_STREAMING, torch.float32, 7)]
+    ok = all([gpu_case(*c, rank, world, dev) for c in cases])
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+# ------------------------------------------------------------------------------- CPU / gloo
+def cpu_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import lbm_oracle as lo
+        ctx = lt.Context("cpu", dtype=torch.float64)
+        dev = torch.device("cpu")
+        out = {}
+        for name, cls, res in (("D3Q19", lt.D3Q19, [11, 6, 8]), ("D2Q9", lt.D2Q9, [10, 12])):
+            dec = slab.SlabDecomposition(res[0], world, rank)
+            flow = slab.SlabTaylorGreenVortex(ctx, res, 400.0, 0.05, cls(), dec)
+            assert list(flow.f.shape[1:]) == [dec.nx_local] + res[1:]
+            whole = gather_slabs(flow.f, dec, dev)
+            ref = lt.TaylorGreenVortex(ctx, res, 400.0, 0.05, stencil=cls())
+            out[name + "_init"] = float((whole - ref.f).abs().max())
+            assert flow.units.relaxation_parameter_lu == ref.units.relaxation_parameter_lu
+            # lock-stepped slab stepping with explicit plane exchange, oracle as the local stepper
+            st = lo.stencil(name)
+            coll = dict(kind="bgk", tau=ref.units.relaxation_parameter_lu)
+            f = flow.f.numpy().copy()
+            g = ref.f.numpy().copy()
+            for _ in range(4):
+                fc = lo.collide(st, f, coll)                      # node-local
+                # ring exchange of the boundary planes (post-collision), then stream on the extended slab
+                send_hi, send_lo = torch.from_numpy(fc[:, -1].copy()), torch.from_numpy(fc[:, 0].copy())
+                recv_lo, recv_hi = torch.empty_like(send_hi), torch.empty_like(send_lo)
+                reqs = [dist.isend(send_hi, dec.hi), dist.isend(send_lo, dec.lo),
+                        dist.irecv(recv_lo, dec.lo), dist.irecv(recv_hi, dec.hi)] if world > 2 else None
+                if world == 2:      # both neighbours are the same rank: order the messages by tag
+                    reqs = [dist.isend(send_hi, dec.hi, tag=1), dist.isend(send_lo, dec.lo, tag=2),
+                            dist.irecv(recv_lo, dec.lo, tag=1), dist.irecv(recv_hi, dec.hi, tag=2)]
+                for r_ in reqs:
+                    r_.wait()
+                ext = np.concatenate([recv_lo.numpy()[:, None], fc, recv_hi.numpy()[:, None]], axis=1)
+                f = lo.stream(st, ext)[:, 1:-1]
+                g = lo.step(st, g, coll)
+            whole = gather_slabs(torch.from_numpy(np.ascontiguousarray(f)), dec, dev).numpy()
+            out[name + "_step"] = float(np.abs(whole - g).max())
+        results[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    gpu_main()
