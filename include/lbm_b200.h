@@ -134,6 +134,10 @@ typedef struct lbm_step_desc {
      * not overwritten by streaming).  Both NULL for unmasked runs. */
     const uint8_t *labels;
     const uint32_t *frozen;
+    /* flat node indices (x*ny*nz + y*nz + z) of all nodes whose label has bit 7 set, from
+     * lbm_list_general_nodes(); they are stepped by a separate sparse kernel. */
+    const int32_t *general_nodes;
+    int64_t n_general;
     lbm_halo halo;
 } lbm_step_desc;
 
@@ -150,13 +154,27 @@ int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, v
 /* Builds the per-node label byte and frozen-slot word from lettuce's masks
  * (`no_collision_mask` uint8 [nx,ny,nz] and `no_streaming_mask` uint8 [q,nx,ny,nz],
  * lettuce/_simulation.py:100-146).  label = ncm value, with bit 7 set on every node
- * that needs the general path: a frozen slot of its own, a neighbour slot it would
- * stream into that is frozen, or membership in an outlet plane of `desc`. */
+ * that needs the general path: a label other than the collision's, a frozen slot of its own,
+ * a neighbour slot it would stream into that is frozen, or membership in an outlet plane of `desc`. */
 int lbm_pack_masks(const lbm_step_desc *desc, const uint8_t *d_ncm, const uint8_t *d_nsm,
                    uint8_t *d_labels, uint32_t *d_frozen, void *stream);
 
+/* Compacts the indices of the nodes with label bit 7 set into d_list (capacity entries) and writes
+ * their total number to *d_count (device int64; may exceed capacity, then only `capacity` entries
+ * were stored -- call with capacity 0 first to size the list).  Order is unspecified. */
+int lbm_list_general_nodes(const lbm_lattice *lat, const uint8_t *d_labels, int32_t *d_list, int64_t capacity,
+                           int64_t *d_count, void *stream);
+
 /* Density [nx,ny,nz] and velocity [d,nx,ny,nz] fields (either may be NULL). */
 int lbm_moments(const lbm_lattice *lat, const void *d_f, void *d_rho, void *d_u, void *stream);
+
+/* Equilibrium populations f_q = feq_q(rho, u) for every node (QuadraticEquilibrium.__call__,
+ * lettuce/ext/_equilibrium/quadratic_equilibrium.py:11-24, as used by Flow.initialize,
+ * lettuce/_flow.py:127-143) written straight into d_f_out without full-size temporaries.
+ * rho / u are fields in lattice units with element strides per spatial axis x,y,z (0 broadcasts
+ * the axis); u has a leading component stride. */
+int lbm_equilibrium(const lbm_lattice *lat, const void *d_rho, const int64_t rho_stride[3], const void *d_u,
+                    const int64_t u_stride[4], void *d_f_out, void *stream);
 
 typedef enum lbm_reduction {
     LBM_SUM_HALF_U2 = 0, /* sum over nodes of 0.5*|u|^2 in lattice units (_flow.py:200-204) */

@@ -122,7 +122,11 @@ class Flow(ABC):
         p, u = self.initial_pu()
         rho = self.context.convert_to_tensor(self.units.convert_pressure_pu_to_density_lu(p))
         u = self.context.convert_to_tensor(self.units.convert_velocity_to_lu(u))
-        self.f = self.equilibrium(self, rho=rho, u=u).contiguous()
+        if u.is_cuda and type(self.equilibrium) is QuadraticEquilibrium and u.dim() == self.stencil.d + 1:
+            # one kernel, no full-size temporaries (the torch expression needs ~6x the size of f)
+            self.f = native.equilibrium_field(self.stencil, rho, u, self.resolution)
+        else:
+            self.f = self.equilibrium(self, rho=rho, u=u).contiguous()
         if self.initialize_fneq:
             self.f = initialize_f_neq(self).contiguous()
         self._f_next = None

@@ -17,6 +17,9 @@ template <class S, class R>
 int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, int n2, double *partials, double *out,
                   cudaStream_t st);
 size_t reduce_scratch_bytes();
+template <class S, class R>
+int launch_equilibrium(const R *rho, const int64_t *rs, const R *u, const int64_t *us, int n0, int n1, int n2, R *f,
+                       cudaStream_t stream);
 
 static int cuda_fail(int e) {
     if (e <= 0) return e;  // already an lbm_status
@@ -84,6 +87,7 @@ static int validate_desc(const lbm_step_desc *d, Dims &dm) {
         }
     }
     if (d->n_ops > 1 && (!d->labels || !d->frozen)) return LBM_ERR_BAD_ARGUMENT;
+    if (d->n_general < 0 || (d->n_general > 0 && !d->general_nodes)) return LBM_ERR_BAD_ARGUMENT;
     if (d->ops[d->collision_index].kind == LBM_OP_KBC && d->lat.stencil == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
     return LBM_OK;
 }
@@ -112,6 +116,8 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
     p.labels_hi = h.label_hi ? h.label_hi : d->labels;
     p.frozen_lo = h.frozen_lo ? h.frozen_lo : (d->frozen ? d->frozen + (dm.n0 - 1) * plane : nullptr);
     p.frozen_hi = h.frozen_hi ? h.frozen_hi : d->frozen;
+    p.general_nodes = d->general_nodes;
+    p.n_general = (int)d->n_general;
     p.n_ops = d->n_ops;
     p.collision_index = d->collision_index;
     const lbm_op &c = d->ops[d->collision_index];
@@ -164,8 +170,9 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
 // ---------------------------------------------------------------------------
 template <class S>
 __global__ void pack_masks_kernel(const uint8_t *__restrict__ ncm, const uint8_t *__restrict__ nsm, int n0, int n1,
-                                  int n2, int n_ops, const int *__restrict__ op_kind, const int *__restrict__ op_axis,
-                                  const int *__restrict__ op_side, uint8_t *labels, uint32_t *frozen) {
+                                  int n2, int n_ops, int collision_index, const int *__restrict__ op_kind,
+                                  const int *__restrict__ op_axis, const int *__restrict__ op_side,
+                                  uint8_t *labels, uint32_t *frozen) {
     const int64_t N = (int64_t)n0 * n1 * n2;
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
         const int z = (int)(n % n2);
@@ -179,6 +186,7 @@ __global__ void pack_masks_kernel(const uint8_t *__restrict__ ncm, const uint8_t
             if (nsm[q * N + ((int64_t)xd * n1 + yd) * n2 + zd] == 1) general = true;
         });
         if (own) general = true;
+        if (ncm[n] != collision_index) general = true;
         for (int i = 0; i < n_ops; ++i) {
             if (op_kind[i] != LBM_OP_OUTLET_P && op_kind[i] != LBM_OP_ANTI_BOUNCE_BACK) continue;
             if (op_side[i] != 0 && in_plane_of(op_axis[i], op_side[i], x, y, z, n0, n1, n2)) general = true;
@@ -206,7 +214,8 @@ static int pack_typed(const lbm_step_desc *d, const Dims &dm, const uint8_t *ncm
     const int64_t N = (int64_t)dm.n0 * dm.n1 * dm.n2;
     int64_t b = (N + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
-    pack_masks_kernel<S><<<(int)b, 256, 0, st>>>(ncm, nsm, dm.n0, dm.n1, dm.n2, d->n_ops, dev, dev + LBM_MAX_OPS,
+    pack_masks_kernel<S><<<(int)b, 256, 0, st>>>(ncm, nsm, dm.n0, dm.n1, dm.n2, d->n_ops, d->collision_index, dev,
+                                                  dev + LBM_MAX_OPS,
                                                   dev + 2 * LBM_MAX_OPS, labels, frozen);
     ++g_launch_count;
     e = (int)cudaGetLastError();
@@ -214,6 +223,16 @@ static int pack_typed(const lbm_step_desc *d, const Dims &dm, const uint8_t *ncm
     // the staging copy reads `host` from this stack frame
     cudaStreamSynchronize(st);
     return e;
+}
+
+__global__ void list_general_nodes_kernel(const uint8_t *__restrict__ labels, int64_t N, int32_t *list,
+                                          long long capacity, unsigned long long *count) {
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        if (labels[n] & kLabelGeneral) {
+            const unsigned long long slot = atomicAdd(count, 1ULL);
+            if ((long long)slot < capacity) list[slot] = (int32_t)n;
+        }
+    }
 }
 
 }  // namespace lbm
@@ -291,6 +310,23 @@ int lbm_pack_masks(const lbm_step_desc *desc, const uint8_t *d_ncm, const uint8_
     }
 }
 
+int lbm_list_general_nodes(const lbm_lattice *lat, const uint8_t *d_labels, int32_t *d_list, int64_t capacity,
+                           int64_t *d_count, void *stream) {
+    Dims dm;
+    int rc = lattice_dims(lat, dm);
+    if (rc) return rc;
+    if (!d_labels || !d_count || capacity < 0 || (capacity > 0 && !d_list)) return LBM_ERR_BAD_ARGUMENT;
+    const int64_t N = (int64_t)dm.n0 * dm.n1 * dm.n2;
+    int e = (int)cudaMemsetAsync(d_count, 0, sizeof(int64_t), (cudaStream_t)stream);
+    if (e) return cuda_fail(e);
+    int64_t b = (N + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    list_general_nodes_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(d_labels, N, d_list, (long long)capacity,
+                                                                       (unsigned long long *)d_count);
+    ++g_launch_count;
+    return cuda_fail((int)cudaGetLastError());
+}
+
 int lbm_moments(const lbm_lattice *lat, const void *d_f, void *d_rho, void *d_u, void *stream) {
     Dims dm;
     int rc = lattice_dims(lat, dm);
@@ -299,6 +335,18 @@ int lbm_moments(const lbm_lattice *lat, const void *d_f, void *d_rho, void *d_u,
     const int64_t N = (int64_t)dm.n0 * dm.n1 * dm.n2;
     LBM_DISPATCH(lat->stencil, lat->dtype,
                  return cuda_fail((launch_moments<S, R>((const R *)d_f, (R *)d_rho, (R *)d_u, N, (cudaStream_t)stream))));
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+int lbm_equilibrium(const lbm_lattice *lat, const void *d_rho, const int64_t rho_stride[3], const void *d_u,
+                    const int64_t u_stride[4], void *d_f_out, void *stream) {
+    Dims dm;
+    int rc = lattice_dims(lat, dm);
+    if (rc) return rc;
+    if (!d_rho || !d_u || !d_f_out || !rho_stride || !u_stride) return LBM_ERR_BAD_ARGUMENT;
+    LBM_DISPATCH(lat->stencil, lat->dtype,
+                 return cuda_fail((launch_equilibrium<S, R>((const R *)d_rho, rho_stride, (const R *)d_u, u_stride, dm.n0,
+                                                            dm.n1, dm.n2, (R *)d_f_out, (cudaStream_t)stream))));
     return LBM_ERR_BAD_ARGUMENT;
 }
 

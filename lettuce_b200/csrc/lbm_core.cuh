@@ -114,6 +114,21 @@ struct Equilibrium {
         const R poly = base + eu * (R(1.0 / kCs2) + eu * R(0.5 / (kCs2 * kCs2)));
         return R(S::w(q)) * rho * poly;
     }
+    // feq of q and of its opposite: they share the even part base + (e.u)^2/(2 cs^4)
+    template <int q>
+    LBM_D void pair(R &fq, R &fo) const {
+        R eu = R(0);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (S::e(q, a) == 1) eu += u[a];
+            if (S::e(q, a) == -1) eu -= u[a];
+        }
+        const R wr = R(S::w(q)) * rho;
+        const R even = base + (eu * eu) * R(0.5 / (kCs2 * kCs2));
+        const R odd = eu * R(1.0 / kCs2);
+        fq = wr * (even + odd);
+        fo = wr * (even - odd);
+    }
 };
 
 // compile-time loop helper: body.template operator()<q>() for q in [0, Q)
@@ -192,10 +207,50 @@ struct Collide<S, R, LBM_OP_TRT> {
     }
 };
 
+// dh / feq inside KBC's entropic sums.  gamma is the ratio of two sums that are dominated by
+// rounding noise in smooth flow (see tests/test_gpu_parity.py), so fp32 uses the 2-ulp fast
+// approximate reciprocal (one MUFU.RCP, ~1 ulp; feq is O(1e-3..1), far from the denormal range)
+// instead of 27 IEEE divisions with their slow-path calls per node.
+LBM_D float kbc_div(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
+}
+LBM_D double kbc_div(double a, double b) { return a / b; }
+
 // Entropic KBC in the closed form of SURVEY.md Appendix A.3
 // (lettuce/ext/_collision/kbc_collision.py:22-160).  beta = 1/(2 tau).
+//
+// Register plan: only the non-equilibrium part fn = f - feq is kept (in place of f); feq is
+// re-evaluated per opposite pair where it is needed (two FMAs per pair share the even part),
+// and delta_s is one of ten scalars derived from the six second moments.  With
+// dh = fn - ds the result is  f' = feq + (1 - beta gamma) fn + beta (gamma - 2) ds.
 template <class S, class R>
 struct Collide<S, R, LBM_OP_KBC> {
+    // shear part of population q from the precomputed moment combinations (kbc_collision.py:44-94)
+    template <int q>
+    LBM_D static R ds_of(const R (&c)[7]) {
+        if constexpr (q == 0) return c[0];
+        if constexpr (S::D == 2) {
+            // c[1] = (T+N)/4 (x axis pops 1,3), c[2] = (T-N)/4 (y axis pops 2,4), c[3] = Pxy/4
+            if constexpr (q == 1 || q == 3) return c[1];
+            else if constexpr (q == 2 || q == 4) return c[2];
+            else if constexpr (q == 5 || q == 7) return c[3];
+            else return -c[3];
+        } else {
+            if constexpr (q <= 2) return c[1];
+            else if constexpr (q <= 4) return c[2];
+            else if constexpr (q <= 6) return c[3];
+            else if constexpr (q <= 8) return c[4];
+            else if constexpr (q <= 10) return -c[4];
+            else if constexpr (q <= 12) return c[5];
+            else if constexpr (q <= 14) return -c[5];
+            else if constexpr (q <= 16) return c[6];
+            else if constexpr (q <= 18) return -c[6];
+            else return R(0);
+        }
+    }
+
     LBM_D static void apply(R (&f)[S::Q], R beta, R) {
         constexpr int Q = S::Q;
         R rho, j[3];
@@ -203,65 +258,85 @@ struct Collide<S, R, LBM_OP_KBC> {
         const R inv_rho = R(1) / rho;
         const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
         Equilibrium<S, R> eq(rho, u);
-        R feq[Q], fn[Q];
+        // f <- fn = f - feq
         ForQ<Q>::run([&]<int q>() {
-            feq[q] = eq.template get<q>();
-            fn[q] = f[q] - feq[q];
+            constexpr int o = S::opp(q);
+            if constexpr (q == 0) {
+                f[0] -= eq.template get<0>();
+            } else if constexpr (q < o) {
+                R eq_q, eq_o;
+                eq.template pair<q>(eq_q, eq_o);
+                f[q] -= eq_q;
+                f[o] -= eq_o;
+            }
         });
-        // raw second moments of the non-equilibrium part; axes 0,1,2 are x,y,z in 3-D and
-        // x,(unused),y in 2-D.
+        // raw second moments of fn; internal axes 0,1,2 are x,y,z in 3-D and x,(unused),y in 2-D
         R P00 = 0, P11 = 0, P22 = 0, P01 = 0, P02 = 0, P12 = 0;
         ForQ<Q>::run([&]<int q>() {
             constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            if constexpr (e0 != 0) P00 += fn[q];
-            if constexpr (e1 != 0) P11 += fn[q];
-            if constexpr (e2 != 0) P22 += fn[q];
-            if constexpr (e0 * e1 == 1) P01 += fn[q];
-            if constexpr (e0 * e1 == -1) P01 -= fn[q];
-            if constexpr (e0 * e2 == 1) P02 += fn[q];
-            if constexpr (e0 * e2 == -1) P02 -= fn[q];
-            if constexpr (e1 * e2 == 1) P12 += fn[q];
-            if constexpr (e1 * e2 == -1) P12 -= fn[q];
+            if constexpr (e0 != 0) P00 += f[q];
+            if constexpr (e1 != 0) P11 += f[q];
+            if constexpr (e2 != 0) P22 += f[q];
+            if constexpr (e0 * e1 == 1) P01 += f[q];
+            if constexpr (e0 * e1 == -1) P01 -= f[q];
+            if constexpr (e0 * e2 == 1) P02 += f[q];
+            if constexpr (e0 * e2 == -1) P02 -= f[q];
+            if constexpr (e1 * e2 == 1) P12 += f[q];
+            if constexpr (e1 * e2 == -1) P12 -= f[q];
         });
-        R ds[Q];
+        R c[7];
         if constexpr (S::D == 2) {
-            // kbc_collision.py:76-94 ; internal axis 2 is y
-            const R T = P00 + P22, N = P00 - P22, Pxy = P02;
-            ds[0] = -T;
-            ds[1] = ds[3] = R(0.25) * (T + N);
-            ds[2] = ds[4] = R(0.25) * (T - N);
-            ds[5] = ds[7] = R(0.25) * Pxy;
-            ds[6] = ds[8] = R(-0.25) * Pxy;
+            const R T = P00 + P22, N = P00 - P22;        // internal axis 2 is y
+            c[0] = -T;
+            c[1] = R(0.25) * (T + N);
+            c[2] = R(0.25) * (T - N);
+            c[3] = R(0.25) * P02;
+            c[4] = c[5] = c[6] = R(0);
         } else {
-            // kbc_collision.py:44-74 ; entries 19..26 stay zero
             const R T = P00 + P11 + P22, Nxz = P00 - P22, Nyz = P11 - P22;
-            ds[0] = -T;
-            ds[1] = ds[2] = (R(2) * Nxz - Nyz + T) * R(1.0 / 6.0);
-            ds[3] = ds[4] = (R(2) * Nyz - Nxz + T) * R(1.0 / 6.0);
-            ds[5] = ds[6] = (-Nxz - Nyz + T) * R(1.0 / 6.0);
-            ds[7] = ds[8] = R(0.25) * P12;
-            ds[9] = ds[10] = R(-0.25) * P12;
-            ds[11] = ds[12] = R(0.25) * P02;
-            ds[13] = ds[14] = R(-0.25) * P02;
-            ds[15] = ds[16] = R(0.25) * P01;
-            ds[17] = ds[18] = R(-0.25) * P01;
-#pragma unroll
-            for (int q = 19; q < Q; ++q) ds[q] = R(0);
+            c[0] = -T;
+            c[1] = (R(2) * Nxz - Nyz + T) * R(1.0 / 6.0);
+            c[2] = (R(2) * Nyz - Nxz + T) * R(1.0 / 6.0);
+            c[3] = (-Nxz - Nyz + T) * R(1.0 / 6.0);
+            c[4] = R(0.25) * P12;
+            c[5] = R(0.25) * P02;
+            c[6] = R(0.25) * P01;
         }
+        // entropic stabiliser gamma = 1/beta - (2 - 1/beta) <ds|dh>/<dh|dh>, weights 1/feq
         R sum_s = 0, sum_h = 0;
         ForQ<Q>::run([&]<int q>() {
-            const R dh = fn[q] - ds[q];
-            const R r = dh / feq[q];
-            sum_s += ds[q] * r;
-            sum_h += dh * r;
+            constexpr int o = S::opp(q);
+            if constexpr (q == 0) {
+                const R ds = ds_of<0>(c), dh = f[0] - ds;
+                const R r = kbc_div(dh, eq.template get<0>());
+                sum_s += ds * r;
+                sum_h += dh * r;
+            } else if constexpr (q < o) {
+                R eq_q, eq_o;
+                eq.template pair<q>(eq_q, eq_o);
+                const R ds = ds_of<q>(c);          // even in e: same for q and its opposite
+                const R dh_q = f[q] - ds, dh_o = f[o] - ds;
+                const R r_q = kbc_div(dh_q, eq_q), r_o = kbc_div(dh_o, eq_o);
+                sum_s += ds * (r_q + r_o);
+                sum_h += dh_q * r_q + dh_o * r_o;
+            }
         });
         const R inv_beta = R(1) / beta;
         R gamma = inv_beta - (R(2) - inv_beta) * (sum_s / sum_h);
         // kbc_collision.py:154-157: gamma < 1e-15 -> 2 ; NaN -> 2
         if (!(gamma >= R(1e-15))) gamma = R(2);
+        const R a = R(1) - beta * gamma, b = beta * (gamma - R(2));
         ForQ<Q>::run([&]<int q>() {
-            const R dh = fn[q] - ds[q];
-            f[q] = f[q] - beta * (R(2) * ds[q] + gamma * dh);
+            constexpr int o = S::opp(q);
+            if constexpr (q == 0) {
+                f[0] = eq.template get<0>() + (a * f[0] + b * ds_of<0>(c));
+            } else if constexpr (q < o) {
+                R eq_q, eq_o;
+                eq.template pair<q>(eq_q, eq_o);
+                const R bds = b * ds_of<q>(c);
+                f[q] = eq_q + (a * f[q] + bds);
+                f[o] = eq_o + (a * f[o] + bds);
+            }
         });
     }
 };

@@ -27,6 +27,47 @@ __global__ void moments_kernel(const R *__restrict__ f, R *__restrict__ rho_out,
     }
 }
 
+struct FieldStrides {
+    int64_t rho[3];  // internal axis order
+    int64_t u[4];    // component, internal axes
+};
+
+template <class S, class R>
+__global__ void equilibrium_kernel(const R *__restrict__ rho, const R *__restrict__ u, FieldStrides st, int n0, int n1,
+                                   int n2, R *__restrict__ f) {
+    const int64_t N = (int64_t)n0 * n1 * n2;
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(n % n2);
+        const int y = (int)((n / n2) % n1);
+        const int x = (int)(n / ((int64_t)n1 * n2));
+        const R r = rho[x * st.rho[0] + y * st.rho[1] + z * st.rho[2]];
+        R v[3] = {R(0), R(0), R(0)};
+#pragma unroll
+        for (int c = 0; c < S::D; ++c) v[S::axis_of(c)] = u[c * st.u[0] + x * st.u[1] + y * st.u[2] + z * st.u[3]];
+        Equilibrium<S, R> eq(r, v);
+        ForQ<S::Q>::run([&]<int q>() { f[q * N + n] = eq.template get<q>(); });
+    }
+}
+
+template <class S, class R>
+int launch_equilibrium(const R *rho, const int64_t *rs, const R *u, const int64_t *us, int n0, int n1, int n2, R *f,
+                       cudaStream_t stream) {
+    FieldStrides st;
+    for (int a = 0; a < 3; ++a) st.rho[a] = 0;
+    for (int a = 0; a < 4; ++a) st.u[a] = 0;
+    st.u[0] = us[0];
+    for (int c = 0; c < S::D; ++c) {
+        st.rho[S::axis_of(c)] = rs[c];
+        st.u[1 + S::axis_of(c)] = us[1 + c];
+    }
+    const int64_t N = (int64_t)n0 * n1 * n2;
+    int64_t b = (N + 255) / 256;
+    if (b > 148 * 32) b = 148 * 32;
+    equilibrium_kernel<S, R><<<(int)b, 256, 0, stream>>>(rho, u, st, n0, n1, n2, f);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
 template <bool MAX>
 LBM_D double warp_fold(double v) {
 #pragma unroll
@@ -207,6 +248,8 @@ int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, in
 }
 
 #define LBM_INSTANTIATE(S, R)                                                        \
+    template int launch_equilibrium<S, R>(const R *, const int64_t *, const R *, const int64_t *, int, int, int, R *, \
+                                          cudaStream_t);                              \
     template int launch_moments<S, R>(const R *, R *, R *, int64_t, cudaStream_t);   \
     template int launch_reduce<S, R>(int, const R *, const uint8_t *, int, int, int, double *, double *, cudaStream_t);
 LBM_INSTANTIATE(D2Q9, float)

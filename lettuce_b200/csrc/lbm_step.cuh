@@ -37,6 +37,8 @@ struct StepParams {
     int64_t N;  // n0*n1*n2
     const uint8_t *labels, *labels_lo, *labels_hi;
     const uint32_t *frozen, *frozen_lo, *frozen_hi;
+    const int32_t *general_nodes;  // flat indices of the nodes with label bit 7 set
+    int n_general;
     int n_ops, collision_index;
     R ca, cb;  // scalars of the collision entry
     OpDev<R> ops[LBM_MAX_OPS];
@@ -142,6 +144,7 @@ LBM_D void apply_local_op(const StepParams<R> &p, int i, int label, int x, int y
 LBM_D bool in_plane_of(int axis, int side, int x, int y, int z, int n0, int n1, int n2) {
     const int c = axis == 0 ? x : (axis == 1 ? y : z);
     const int n = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+    if (side == 0) return false;  // plane owned by another slab
     return c == (side > 0 ? n - 1 : 0);
 }
 
@@ -160,7 +163,7 @@ __device__ void neighbour_state(const StepParams<R> &p, int i, int x, int y, int
 }
 
 template <class S, class R, int COLL, bool PULL, bool PUSH>
-__device__ __noinline__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
+__device__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
     constexpr int Q = S::Q;
     R f[Q];
     gather_node<S, R, PULL>(p, x, y, z, f);
@@ -262,11 +265,9 @@ __global__ void __launch_bounds__(256) step_scalar_kernel(const __grid_constant_
     const int64_t row = (int64_t)y * p.n2 + z;
 
     if (MASKED) {
-        const int label = p.labels[(int64_t)x * p.n1 * p.n2 + row];
-        if (label != p.collision_index) {
-            general_node<S, R, COLL, PULL, PUSH>(p, x, y, z, label & 0x7f);
-            return;
-        }
+        // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
+        // bit 7 and are left to general_nodes_kernel; every output slot still has exactly one writer.
+        if (p.labels[(int64_t)x * p.n1 * p.n2 + row] != p.collision_index) return;
     }
 
     // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
@@ -303,6 +304,22 @@ __global__ void __launch_bounds__(256) step_scalar_kernel(const __grid_constant_
         R *dst = p.out + (int64_t)x * p.n1 * p.n2 + row;
         ForQ<Q>::run([&]<int q>() { dst[q * p.N] = f[q]; });
     }
+}
+
+// ---------------------------------------------------------------------------
+// sparse kernel: one thread per node of the precomputed list of general nodes
+// (boundaries, frozen slots).  Runs next to step_scalar_kernel<MASKED> on the same
+// stream; the two kernels write disjoint slots of the output buffer.
+// ---------------------------------------------------------------------------
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+__global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constant__ StepParams<R> p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_general) return;
+    const int n = p.general_nodes[i];
+    const int z = n % p.n2;
+    const int y = (n / p.n2) % p.n1;
+    const int x = n / (p.n1 * p.n2);
+    general_node<S, R, COLL, PULL, PUSH>(p, x, y, z, p.labels[n] & 0x7f);
 }
 
 }  // namespace lbm

@@ -24,6 +24,10 @@ int launch_scalar(const StepParams<R> &p, cudaStream_t stream) {
     dim3 grid((p.n2 + tz - 1) / tz, (p.n1 + ty - 1) / ty, p.n0);
     step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED><<<grid, block, 0, stream>>>(p);
     ++g_launch_count;
+    if (MASKED && p.n_general > 0) {
+        general_nodes_kernel<S, R, COLL, PULL, PUSH><<<(p.n_general + 127) / 128, 128, 0, stream>>>(p);
+        ++g_launch_count;
+    }
     return (int)cudaGetLastError();
 }
 
@@ -63,7 +67,7 @@ int launch_step(const StepParams<R> &p, int coll, int streaming, bool masked, in
 
 template <class S, class R>
 const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int) {
-    return masked ? "scalar_masked" : "scalar";
+    return masked ? "scalar_masked+general_nodes" : "scalar";
 }
 
 template int launch_step<LBM_INST_STENCIL, LBM_INST_REAL>(const StepParams<LBM_INST_REAL> &, int, int, bool, int,

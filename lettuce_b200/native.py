@@ -54,7 +54,8 @@ class LbmStepDesc(C.Structure):
     _fields_ = [("lat", LbmLattice), ("streaming", C.c_int32), ("n_ops", C.c_int32),
                 ("collision_index", C.c_int32), ("variant", C.c_int32),
                 ("ops", LbmOp * LBM_MAX_OPS),
-                ("labels", C.c_void_p), ("frozen", C.c_void_p), ("halo", LbmHalo)]
+                ("labels", C.c_void_p), ("frozen", C.c_void_p),
+                ("general_nodes", C.c_void_p), ("n_general", C.c_int64), ("halo", LbmHalo)]
 
 
 class LbmSlab(C.Structure):
@@ -65,7 +66,7 @@ class LbmSlab(C.Structure):
 
 
 EXPORTS = ["lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
-           "lbm_step", "lbm_step_n", "lbm_pack_masks", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
+           "lbm_step", "lbm_step_n", "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
            "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
            "lbm_launch_count", "lbm_step_variant_name"]
 
@@ -98,6 +99,10 @@ def lib() -> C.CDLL:
     L.lbm_slab_step_n.restype = i32
     L.lbm_pack_masks.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, vp, vp]
     L.lbm_pack_masks.restype = i32
+    L.lbm_list_general_nodes.argtypes = [C.POINTER(LbmLattice), vp, vp, i64, vp, vp]
+    L.lbm_list_general_nodes.restype = i32
+    L.lbm_equilibrium.argtypes = [C.POINTER(LbmLattice), vp, C.POINTER(i64), vp, C.POINTER(i64), vp, vp]
+    L.lbm_equilibrium.restype = i32
     L.lbm_moments.argtypes = [C.POINTER(LbmLattice), vp, vp, vp, vp]
     L.lbm_moments.restype = i32
     L.lbm_reduce_scratch_bytes.argtypes = [C.POINTER(LbmLattice)]
@@ -290,6 +295,17 @@ class Engine:
               "lbm_pack_masks")
         self.desc.labels = self.labels.data_ptr()
         self.desc.frozen = self.frozen.data_ptr()
+        # compact list of the nodes the sparse general-nodes kernel has to visit
+        count = torch.zeros((), dtype=torch.int64, device=self.device)
+        stream = _stream_ptr(self.device)
+        check(self.lib.lbm_list_general_nodes(C.byref(self.lat), self.labels.data_ptr(), None, 0, count.data_ptr(),
+                                              stream), "lbm_list_general_nodes")
+        n_general = int(count.item())
+        self.general_nodes = torch.empty(max(n_general, 1), dtype=torch.int32, device=self.device)
+        check(self.lib.lbm_list_general_nodes(C.byref(self.lat), self.labels.data_ptr(), self.general_nodes.data_ptr(),
+                                              n_general, count.data_ptr(), stream), "lbm_list_general_nodes")
+        self.desc.general_nodes = self.general_nodes.data_ptr()
+        self.desc.n_general = n_general
 
     # -- stepping ------------------------------------------------------------
     def _buffers(self):
@@ -351,6 +367,32 @@ def moments(stencil, f: torch.Tensor, want_rho=True, want_u=True):
         check(lib().lbm_moments(C.byref(lat), f.data_ptr(), rho.data_ptr() if want_rho else None,
                                 u.data_ptr() if want_u else None, _stream_ptr(f.device)), "lbm_moments")
     return rho, u
+
+
+def equilibrium_field(stencil, rho: torch.Tensor, u: torch.Tensor, resolution) -> torch.Tensor:
+    """[q, *resolution] equilibrium populations of broadcastable fields rho [1|.., *res|1] and
+    u [d, *res|1] (lattice units), written by one kernel without full-size temporaries."""
+    _require_cuda(u, "u")
+    d = stencil.d
+    res = [int(r) for r in resolution]
+    if rho.dim() == d:
+        rho = rho.unsqueeze(0)
+    if rho.dim() != d + 1 or u.dim() != d + 1 or rho.shape[0] != 1 or u.shape[0] != d:
+        raise ValueError(f"need rho [1, ...] and u [{d}, ...] of rank {d + 1}, got {list(rho.shape)} {list(u.shape)}")
+    rho = rho.to(device=u.device, dtype=u.dtype).contiguous()
+    u = u.contiguous()
+    for a in range(d):
+        if rho.shape[a + 1] not in (1, res[a]) or u.shape[a + 1] not in (1, res[a]):
+            raise ValueError("rho / u do not broadcast to the resolution")
+    lat = lattice_of(stencil, res, u.dtype)
+    rs = (C.c_int64 * 3)(*[rho.stride(a + 1) if rho.shape[a + 1] > 1 else 0 for a in range(d)], *([0] * (3 - d)))
+    us = (C.c_int64 * 4)(u.stride(0), *[u.stride(a + 1) if u.shape[a + 1] > 1 else 0 for a in range(d)],
+                         *([0] * (3 - d)))
+    f = torch.empty([stencil.q, *res], dtype=u.dtype, device=u.device)
+    with torch.cuda.device(u.device):
+        check(lib().lbm_equilibrium(C.byref(lat), rho.data_ptr(), rs, u.data_ptr(), us, f.data_ptr(),
+                                    _stream_ptr(u.device)), "lbm_equilibrium")
+    return f
 
 
 _scratch = {}

@@ -216,7 +216,7 @@ def test_ctypes_struct_layout_matches_header():
     assert ctypes.sizeof(native.LbmOp) == 104
     assert ctypes.sizeof(native.LbmLattice) == 24
     assert ctypes.sizeof(native.LbmHalo) == 12 * 8
-    assert ctypes.sizeof(native.LbmStepDesc) == 24 + 16 + 8 * 104 + 16 + 96
+    assert ctypes.sizeof(native.LbmStepDesc) == 24 + 16 + 8 * 104 + 16 + 16 + 96
 
 
 def test_descriptor_validation_without_gpu():
