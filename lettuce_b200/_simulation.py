@@ -94,12 +94,16 @@ class Simulation:
         labels = list(range(len(self.pre_boundaries))) + \
             list(range(self.collision_index + 1, self.collision_index + 1 + len(self.post_boundaries)))
         for label, boundary in zip(labels, boundaries):
-            ncm = boundary.make_no_collision_mask(shape[1:], context=ctx)
+            ncm, nsm = self._boundary_masks(boundary, shape)
             if ncm is not None:
                 self.no_collision_mask[ncm.to(device=ctx.device, dtype=torch.bool)] = label
-            nsm = boundary.make_no_streaming_mask(shape, context=ctx)
             if nsm is not None:
                 self.no_streaming_mask |= nsm.to(device=ctx.device, dtype=torch.uint8)
+
+    def _boundary_masks(self, boundary, shape):
+        """(no_collision_mask, no_streaming_mask) of one boundary; either may be None"""
+        return (boundary.make_no_collision_mask(shape[1:], context=self.context),
+                boundary.make_no_streaming_mask(shape, context=self.context))
 
     @property
     def units(self):

@@ -264,6 +264,8 @@ class Engine:
             if direction is None:       # the reference keeps only index lists (equilibrium_outlet_p.py:36-49)
                 direction = [0 if isinstance(ix, slice) else (1 if ix == -1 else -1) for ix in op.index]
             o.axis, o.side = _direction_axis_side(direction)
+            if getattr(op, "_slab_disabled", False):
+                o.side = 0          # the plane belongs to another rank's slab (lettuce_b200/slab.py)
             if kind == OP_OUTLET_P:
                 o.p0 = float(op.rho_outlet)
 
@@ -295,7 +297,10 @@ class Engine:
               "lbm_pack_masks")
         self.desc.labels = self.labels.data_ptr()
         self.desc.frozen = self.frozen.data_ptr()
-        # compact list of the nodes the sparse general-nodes kernel has to visit
+        self._list_general_nodes()
+
+    def _list_general_nodes(self):
+        """compact list of the nodes the sparse general-nodes kernel has to visit"""
         count = torch.zeros((), dtype=torch.int64, device=self.device)
         stream = _stream_ptr(self.device)
         check(self.lib.lbm_list_general_nodes(C.byref(self.lat), self.labels.data_ptr(), None, 0, count.data_ptr(),

@@ -19,10 +19,10 @@ import torch.distributed as dist
 
 from . import native
 from ._simulation import Simulation, StreamingStrategy
-from .ext.flows import TaylorGreenVortex
+from .ext.flows import Obstacle, TaylorGreenVortex
 from .ext.reporter import Observable
 
-__all__ = ["SlabDecomposition", "SlabTaylorGreenVortex", "SlabSimulation", "SlabEngine",
+__all__ = ["SlabDecomposition", "SlabTaylorGreenVortex", "SlabObstacle", "SlabSimulation", "SlabEngine",
            "GlobalSum", "GlobalMax", "make_tgv_slab_simulation"]
 
 
@@ -103,6 +103,36 @@ class SlabTaylorGreenVortex(TaylorGreenVortex):
         self._f_next = None
 
 
+class SlabObstacle(Obstacle):
+    """The rank-local slab of a global `Obstacle` flow.  `grid` holds the GLOBAL physical coordinates of
+    the local nodes, so masks written in terms of coordinates (inlet `x == 0`, solids) come out right on
+    every rank; `mask` has the local slab's shape.  Subclass and override `post_boundaries` exactly as
+    with `Obstacle`."""
+
+    def __init__(self, context, global_resolution, reynolds_number, mach_number, domain_length_x,
+                 decomposition: SlabDecomposition, char_length=1, char_velocity=1, stencil=None, equilibrium=None):
+        self.decomposition = decomposition
+        self.global_resolution = [int(r) for r in global_resolution]
+        assert decomposition.nx_global == self.global_resolution[0]
+        local = [decomposition.nx_local] + self.global_resolution[1:]
+        self._global_char_length_lu = self.global_resolution[0] / domain_length_x * char_length
+        Obstacle.__init__(self, context, local, reynolds_number, mach_number,
+                          domain_length_x * decomposition.nx_local / self.global_resolution[0],
+                          char_length, char_velocity, stencil, equilibrium)
+
+    @property
+    def grid(self):
+        dec = self.decomposition
+        starts = [dec.x0] + [0] * (len(self.resolution) - 1)
+        axes = [self.units.convert_length_to_pu(torch.arange(s, s + n)) for s, n in zip(starts, self.resolution)]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    @property
+    def global_extent_pu(self):
+        """largest physical coordinate per axis of the GLOBAL lattice (what `grid[i].max()` is on one GPU)"""
+        return [self.units.convert_length_to_pu(torch.arange(n - 1, n))[0] for n in self.global_resolution]
+
+
 class _RawCuda:
     """exposes a raw device allocation to torch through __cuda_array_interface__"""
 
@@ -162,8 +192,40 @@ class SlabEngine(native.Engine):
         self._peers = {}
         self.lo = self._map_peer(self.dec.lo, everyone)
         self.hi = self._map_peer(self.dec.hi, everyone)
+        if self.labels is not None and self.dec.world > 1:
+            self._stitch_masks(simulation)
         if self.dec.world > 1:
             dist.barrier(group=group)       # every rank has filled its buffer and mapped its neighbours
+
+    def _stitch_masks(self, simulation):
+        """Make the packed masks consistent across the cuts.  `lbm_pack_masks` treated the slab as periodic
+        in x; here the two cut planes get (a) the neighbours' frozen-slot words, which the general scatter
+        consults before storing into the neighbour's plane, and (b) the "general" bit wherever a population
+        leaving through the cut would land in a frozen slot of the neighbour."""
+        dec, dev = self.dec, self.device
+        st = self.flow.stencil
+        res = [int(r) for r in self.flow.f.shape[1:]]
+        plane_shape = res[1:]
+        fro = self.frozen.view(res)
+        mine = torch.stack([fro[0], fro[-1]]).contiguous()                    # [2, *plane]
+        planes = [torch.empty_like(mine) for _ in range(dec.world)]
+        dist.all_gather(planes, mine, group=self.group)
+        self.frozen_lo = planes[dec.lo][1].contiguous()                       # lo neighbour's LAST plane
+        self.frozen_hi = planes[dec.hi][0].contiguous()                       # hi neighbour's FIRST plane
+        self.desc.halo.frozen_lo = self.frozen_lo.data_ptr()
+        self.desc.halo.frozen_hi = self.frozen_hi.data_ptr()
+        lab = self.labels.view(res)
+        dims = tuple(range(len(plane_shape)))
+        for side, nb_frozen, ex in ((0, self.frozen_lo, -1), (-1, self.frozen_hi, 1)):
+            hit = torch.zeros(plane_shape, dtype=torch.bool, device=dev)
+            for q, e in enumerate(st.e):
+                if e[0] != ex:
+                    continue
+                # node (y,z) streams population q into (y+e_y, z+e_z) of the neighbour plane
+                dest_frozen = ((nb_frozen >> q) & 1).bool()
+                hit |= torch.roll(dest_frozen, shifts=tuple(-int(c) for c in e[1:]), dims=dims)
+            lab[side] |= (hit.to(torch.uint8) * 128)
+        self._list_general_nodes()
 
     def _map_peer(self, rank, everyone):
         if rank in self._peers:
@@ -228,17 +290,40 @@ class SlabEngine(native.Engine):
             b.free()
 
 
+def _owns_outlet_plane(boundary, dec: SlabDecomposition) -> bool:
+    """x-normal outlet planes exist on one rank only: the last rank for +x, the first for -x"""
+    direction = getattr(boundary, "direction", None)
+    if direction is None or int(direction[0]) == 0:
+        return True
+    return dec.rank == (dec.world - 1 if int(direction[0]) > 0 else 0)
+
+
 class SlabSimulation(Simulation):
-    """`Simulation` whose flow is one x-slab of a larger lattice.  Boundaries are not supported on
-    slabs yet (periodic flows only)."""
+    """`Simulation` whose flow is one x-slab of a larger lattice.
+
+    Boundaries are built from the flow's `pre_/post_boundaries` like on one GPU, with local masks; an outlet
+    whose plane is normal to x is active only on the rank that owns that global plane (its transformer entry
+    stays in the list on every rank so that labels mean the same everywhere)."""
 
     def __init__(self, flow, collision, reporter, streaming_strategy=StreamingStrategy.POST_STREAMING,
                  decomposition: Optional[SlabDecomposition] = None, group=None):
-        super().__init__(flow, collision, reporter, streaming_strategy)
-        if len(self.transformer) > 1:
-            raise NotImplementedError("boundaries on multi-GPU slabs are not implemented yet")
         self.decomposition = decomposition or flow.decomposition
+        super().__init__(flow, collision, reporter, streaming_strategy)
         self._b200_engine = SlabEngine(self, self.decomposition, group)
+
+    def _build_masks(self):
+        dec = self.decomposition
+        for b in self.pre_boundaries + self.post_boundaries:
+            b._slab_disabled = not _owns_outlet_plane(b, dec)
+            if not b._slab_disabled and getattr(b, "direction", None) is not None and int(b.direction[0]) != 0:
+                if dec.nx_local < 2:
+                    raise ValueError("the rank owning an x-normal outlet needs at least two planes")
+        super()._build_masks()
+
+    def _boundary_masks(self, boundary, shape):
+        if getattr(boundary, "_slab_disabled", False):
+            return None, None
+        return super()._boundary_masks(boundary, shape)
 
     def close(self):
         self._b200_engine.close()

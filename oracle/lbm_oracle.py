@@ -420,6 +420,46 @@ def step(st, f, collision, pre=(), post=(), ncm=None, nsm=None, strategy="POST_S
     return f
 
 
+def step_parallel(st, f, collision, strategy="POST_STREAMING", pool=None, chunks=8):
+    """`step` for flows WITHOUT boundaries on several host cores: the node-local collide phase is split
+    into x-chunks and the per-population rolls are spread over the thread pool `pool` (NumPy releases the
+    GIL inside its loops).  Used by bench.py's CPU baseline so that the port uses all host threads, as the
+    reference's torch path does through OpenMP."""
+    if pool is None:
+        return step(st, f, collision, strategy=strategy)
+    pre_s, post_s = STRATEGIES[strategy]
+    d = st["d"]
+    args = {k: v for k, v in collision.items() if k != "kind"}
+    coll = COLLISIONS[collision["kind"]]
+
+    def stream_all(g):
+        out = np.empty_like(g)
+        out[0] = g[0]
+
+        def one(i):
+            out[i] = np.roll(g[i], shift=tuple(int(c) for c in st["e"][i]), axis=tuple(range(d)))
+        list(pool.map(one, range(1, st["q"])))
+        return out
+
+    def collide_all(g):
+        out = np.empty_like(g)
+        edges = np.linspace(0, g.shape[1], chunks + 1).astype(int)
+
+        def one(k):
+            a, b = edges[k], edges[k + 1]
+            if b > a:
+                out[:, a:b] = coll(st, g[:, a:b], **args)
+        list(pool.map(one, range(chunks)))
+        return out
+
+    if pre_s:
+        f = stream_all(f)
+    f = collide_all(f)
+    if post_s:
+        f = stream_all(f)
+    return f
+
+
 def run(st, f, nsteps, collision, pre=(), post=(), strategy="POST_STREAMING"):
     """`Simulation.__call__` without reporters (lettuce/_simulation.py:311-323)."""
     res = f.shape[1:]

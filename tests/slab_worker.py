@@ -65,6 +65,60 @@ def gpu_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev):
     return bool(flag.item())
 
 
+def _eq_out_boundaries(self):
+    x = self.grid[0]
+    return [lt.EquilibriumBoundaryPU(flow=self, context=self.context, mask=torch.abs(x) < 1e-6,
+                                     velocity=self.units.characteristic_velocity_pu * self._unit_vector()),
+            lt.EquilibriumOutletP(direction=self._unit_vector().tolist(), flow=self, rho_outlet=1.0),
+            lt.BounceBackBoundary(self.mask)]
+
+
+class ObstacleEqOut(lt.Obstacle):
+    post_boundaries = property(_eq_out_boundaries)
+
+
+class SlabObstacleEqOut(slab.SlabObstacle):
+    post_boundaries = property(_eq_out_boundaries)
+
+
+def _solid(flow, extent):
+    g = flow.grid
+    c = [0.25 * extent[0]] + [0.5 * e for e in extent[1:]]
+    return sum((gi - ci) ** 2 for gi, ci in zip(g, c)) < 0.5 ** 2
+
+
+def gpu_obstacle_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev, stock=False):
+    """inlet + outlet + bounce-back obstacle flow on slabs vs the same flow on one GPU, bit for bit"""
+    ctx = lt.Context(dev, dtype=dtype)
+    dec = slab.SlabDecomposition(res[0], world, rank)
+    D = res[1] / 8
+    cls_slab, cls_one = (slab.SlabObstacle, lt.Obstacle) if stock else (SlabObstacleEqOut, ObstacleEqOut)
+    flow = cls_slab(ctx, res, 100, 0.05, res[0] / D, dec, stencil=stencil_cls())
+    flow.mask = _solid(flow, flow.global_extent_pu)
+    flow.initialize()
+    make = {"bgk": lambda f: lt.BGKCollision(f.units.relaxation_parameter_lu),
+            "trt": lambda f: lt.TRTCollision(f.units.relaxation_parameter_lu), "kbc": lambda f: lt.KBCCollision()}[coll]
+    sim = slab.SlabSimulation(flow, make(flow), [], strategy, dec)
+    sim(1); sim(2); sim(steps - 3)
+    got = gather_slabs(flow.f, dec, dev)
+    ok = True
+    if rank == 0:
+        one = cls_one(ctx, res, 100, 0.05, res[0] / D, stencil=stencil_cls())
+        one.mask = _solid(one, [gi.max() for gi in one.grid])
+        one.initialize()
+        ref = lt.Simulation(one, make(one), [], strategy)
+        ref(steps)
+        same = torch.equal(one.f, got)
+        diff = float((one.f - got).abs().max())
+        print(f"[slab-obstacle] {stencil_cls.__name__} {res} {coll} {strategy.name} {dtype} world={world} "
+              f"stock={stock}: bit-exact={same} maxdiff={diff:.1e}", flush=True)
+        ok = same
+    sim.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    return bool(flag.item())
+
+
 def gpu_main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -79,6 +133,13 @@ def gpu_main():
              (lt.D2Q9, [50, 32], "kbc", S.POST_STREAMING, torch.float32, 10),
              (lt.D3Q19, [world * 2, 16, 32], "bgk", S.POST_STREAMING, torch.float32, 7)]
     ok = all([gpu_case(*c, rank, world, dev) for c in cases])
+    ocases = [(lt.D2Q9, [64, 32], "bgk", S.POST_STREAMING, torch.float64, 12, False),
+              (lt.D2Q9, [64, 32], "bgk", S.PRE_STREAMING, torch.float32, 12, False),
+              (lt.D3Q27, [32, 16, 16], "trt", S.POST_STREAMING, torch.float32, 9, False),
+              (lt.D3Q19, [24, 16, 24], "bgk", S.DOUBLE_STREAMING, torch.float64, 8, False),
+              (lt.D2Q9, [48, 24], "bgk", S.POST_STREAMING, torch.float64, 10, True),
+              (lt.D3Q19, [world * 2, 16, 16], "bgk", S.POST_STREAMING, torch.float32, 6, False)]
+    ok = all([gpu_obstacle_case(*c[:6], rank, world, dev, stock=c[6]) for c in ocases]) and ok
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

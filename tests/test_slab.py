@@ -64,3 +64,4 @@ def test_slab_cuda_path_matches_single_gpu_bit_exact():
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stderr[-4000:]
     assert "bit-exact=False" not in r.stdout and "bit-exact=True" in r.stdout
+    assert r.stdout.count("[slab-obstacle]") >= 6
