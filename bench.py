@@ -35,6 +35,10 @@ if ROOT not in sys.path:
 
 Q, BYTES_PER_NODE = 19, 2 * 19 * 4       # D3Q19 fp32: every population read once and written once
 RE, MA = 1600.0, 0.05
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed
+# `ncu --set full` captures (profiles/r1_step_d3q19_bgk_{pre,post}_256.csv); algorithmic = 2.550e9
+NCU_DRAM_BYTES_PER_LAUNCH = {(256, "PRE_STREAMING"): 1.275083e9 + 1.225110e9,
+                             (256, "POST_STREAMING"): 1.276738e9 + 1.226840e9}
 
 
 def measured_hbm_peak():
@@ -265,7 +269,9 @@ def gpu_main(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, n, args.strategy),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((n, args.strategy)),
+                         "traffic_unit": "bytes per launch (ncu, profiles/r1_step_d3q19_bgk_*_256.csv)",
+                         "algorithmic_bytes_per_launch": nodes_local * BYTES_PER_NODE, "peak_source": peak_src,
                          "kernel": native.engine_of(sim).variant_name if world == 1 else "slab",
                          "bytes_per_node": BYTES_PER_NODE},
             "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e}

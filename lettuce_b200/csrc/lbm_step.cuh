@@ -278,23 +278,27 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
         if (p.labels[(int64_t)x * p.n1 * p.n2 + row] != p.collision_index) return;
     }
 
-    // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
+    // Neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243).  Addresses are
+    // split into a block-uniform part (plane pointer + q * stride, computed on the uniform datapath) and a
+    // 32-bit in-plane index per thread (row offset + column, nine combinations), so one access costs one
+    // IMAD.WIDE instead of a chain of 64-bit integer operations.
     const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
     const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
+    const int rowm = ym * p.n2, row0 = y * p.n2, rowp = yp * p.n2;
 
     R f[Q];
     if (PULL) {
         const Plane<R, const R> pl[3] = {in_plane(p, x + 1), in_plane(p, x), in_plane(p, x - 1)};  // index e0+1 -> x - e0
         ForQ<Q>::run([&]<int q>() {
             constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            const int ys = e1 == 0 ? y : (e1 == 1 ? ym : yp);
+            const int rs = e1 == 0 ? row0 : (e1 == 1 ? rowm : rowp);
             const int zs = e2 == 0 ? z : (e2 == 1 ? zm : zp);
-            const auto &s = pl[e0 + 1];
-            f[q] = __ldg(s.p + (q * s.qs + (int64_t)ys * p.n2 + zs));
+            const R *qb = pl[e0 + 1].p + q * pl[e0 + 1].qs;   // block-uniform
+            f[q] = __ldg(qb + (rs + zs));
         });
     } else {
-        const R *src = p.in + (int64_t)x * p.n1 * p.n2 + row;
-        ForQ<Q>::run([&]<int q>() { f[q] = __ldg(src + q * p.N); });
+        const R *src = p.in + (int64_t)x * p.n1 * p.n2;
+        ForQ<Q>::run([&]<int q>() { f[q] = __ldg(src + q * p.N + (row0 + z)); });
     }
 
     Collide<S, R, COLL>::apply(f, p.ca, p.cb);
@@ -303,14 +307,14 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
         const Plane<R, R> pl[3] = {out_plane(p, x - 1), out_plane(p, x), out_plane(p, x + 1)};  // index e0+1 -> x + e0
         ForQ<Q>::run([&]<int q>() {
             constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            const int yd = e1 == 0 ? y : (e1 == 1 ? yp : ym);
+            const int rd = e1 == 0 ? row0 : (e1 == 1 ? rowp : rowm);
             const int zd = e2 == 0 ? z : (e2 == 1 ? zp : zm);
-            const auto &d = pl[e0 + 1];
-            d.p[q * d.qs + (int64_t)yd * p.n2 + zd] = f[q];
+            R *qb = pl[e0 + 1].p + q * pl[e0 + 1].qs;         // block-uniform
+            qb[rd + zd] = f[q];
         });
     } else {
-        R *dst = p.out + (int64_t)x * p.n1 * p.n2 + row;
-        ForQ<Q>::run([&]<int q>() { dst[q * p.N] = f[q]; });
+        R *dst = p.out + (int64_t)x * p.n1 * p.n2;
+        ForQ<Q>::run([&]<int q>() { (dst + q * p.N)[row0 + z] = f[q]; });
     }
 }
 
@@ -392,6 +396,8 @@ __global__ void __launch_bounds__(256) step_multi_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------
 template <class S, class R, int COLL, bool PULL, bool PUSH>
 __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constant__ StepParams<R> p) {
+    // let the bulk kernel (launched with programmatic stream serialization) start right away
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_general) return;
     const int n = p.general_nodes[i];

@@ -13,16 +13,11 @@ namespace lbm {
 
 namespace {
 
-// nodes per thread: small stencils need more loads in flight per thread (measured on B200:
-// D2Q9 fp32 at 4096x1024 runs at 0.72 of the HBM roofline with 1 node per thread)
-template <class S, class R>
-constexpr int nodes_per_thread() {
-    return S::Q == 9 ? (sizeof(R) == 4 ? 4 : 2) : 1;
-}
-
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
-int launch_scalar(const StepParams<R> &p, cudaStream_t stream) {
-    constexpr int NPT = nodes_per_thread<S, R>();
+// Nodes per thread for the small stencil.  Measured on B200 (C4, 4096x1024 fp32, PRE): 1 node per thread
+// 65.8 GLUPS, 4 nodes per thread 55.5 GLUPS -- more loads in flight per thread do not pay, occupancy does.
+// desc->variant = 2 or 4 selects the multi-node kernel for experiments; 0 / 1 = one node per thread.
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED, int NPT>
+int launch_bulk(const StepParams<R> &p, cudaStream_t stream) {
     // threadIdx.x runs along the contiguous axis; fill the block up to 256 threads with rows.
     int tz = 32;
     while (tz * NPT < p.n2 && tz < 256) tz <<= 1;
@@ -30,52 +25,84 @@ int launch_scalar(const StepParams<R> &p, cudaStream_t stream) {
     while (ty > 1 && ty / 2 >= p.n1) ty >>= 1;
     dim3 block(tz, ty, 1);
     dim3 grid((p.n2 + tz * NPT - 1) / (tz * NPT), (p.n1 + ty - 1) / ty, p.n0);
-    if constexpr (NPT == 1) step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED><<<grid, block, 0, stream>>>(p);
-    else step_multi_kernel<S, R, COLL, PULL, PUSH, MASKED, NPT><<<grid, block, 0, stream>>>(p);
-    ++g_launch_count;
+    void (*bulk)(const StepParams<R>) = nullptr;
+    if constexpr (NPT == 1) bulk = step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED>;
+    else bulk = step_multi_kernel<S, R, COLL, PULL, PUSH, MASKED, NPT>;
     if (MASKED && p.n_general > 0) {
+        // The sparse kernel is a chain of dependent loads on a handful of CTAs (~10 us at 15 k nodes); it
+        // and the bulk kernel write disjoint slots, so the bulk kernel is launched with programmatic
+        // dependent launch right behind it and overlaps it completely (the sparse kernel releases its
+        // dependents in its first instruction; the bulk kernel never waits on it).  The next launch on the
+        // stream is an ordinary one and waits for both.
         general_nodes_kernel<S, R, COLL, PULL, PUSH><<<(p.n_general + 127) / 128, 128, 0, stream>>>(p);
         ++g_launch_count;
+        int e = (int)cudaGetLastError();
+        if (e) return e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        e = (int)cudaLaunchKernelEx(&cfg, bulk, p);
+        ++g_launch_count;
+        return e;
     }
+    bulk<<<grid, block, 0, stream>>>(p);
+    ++g_launch_count;
     return (int)cudaGetLastError();
 }
 
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
+int launch_scalar(const StepParams<R> &p, int variant, cudaStream_t stream) {
+    if constexpr (S::Q == 9) {
+        if (variant == 2) return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 2>(p, stream);
+        if (variant == 4) return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 4>(p, stream);
+    }
+    return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 1>(p, stream);
+}
+
 template <class S, class R, int COLL, bool MASKED>
-int by_streaming(const StepParams<R> &p, int streaming, cudaStream_t stream) {
+int by_streaming(const StepParams<R> &p, int streaming, int variant, cudaStream_t stream) {
     switch (streaming) {
-        case LBM_NO_STREAMING: return launch_scalar<S, R, COLL, false, false, MASKED>(p, stream);
-        case LBM_POST_STREAMING: return launch_scalar<S, R, COLL, false, true, MASKED>(p, stream);
-        case LBM_PRE_STREAMING: return launch_scalar<S, R, COLL, true, false, MASKED>(p, stream);
-        case LBM_DOUBLE_STREAMING: return launch_scalar<S, R, COLL, true, true, MASKED>(p, stream);
+        case LBM_NO_STREAMING: return launch_scalar<S, R, COLL, false, false, MASKED>(p, variant, stream);
+        case LBM_POST_STREAMING: return launch_scalar<S, R, COLL, false, true, MASKED>(p, variant, stream);
+        case LBM_PRE_STREAMING: return launch_scalar<S, R, COLL, true, false, MASKED>(p, variant, stream);
+        case LBM_DOUBLE_STREAMING: return launch_scalar<S, R, COLL, true, true, MASKED>(p, variant, stream);
     }
     return LBM_ERR_BAD_ARGUMENT;
 }
 
 template <class S, class R, int COLL>
-int by_mask(const StepParams<R> &p, int streaming, bool masked, cudaStream_t stream) {
-    return masked ? by_streaming<S, R, COLL, true>(p, streaming, stream)
-                  : by_streaming<S, R, COLL, false>(p, streaming, stream);
+int by_mask(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream) {
+    return masked ? by_streaming<S, R, COLL, true>(p, streaming, variant, stream)
+                  : by_streaming<S, R, COLL, false>(p, streaming, variant, stream);
 }
 
 }  // namespace
 
 template <class S, class R>
 int launch_step(const StepParams<R> &p, int coll, int streaming, bool masked, int variant, cudaStream_t stream) {
-    (void)variant;
     switch (coll) {
-        case LBM_OP_NO_COLLISION: return by_mask<S, R, LBM_OP_NO_COLLISION>(p, streaming, masked, stream);
-        case LBM_OP_BGK: return by_mask<S, R, LBM_OP_BGK>(p, streaming, masked, stream);
-        case LBM_OP_TRT: return by_mask<S, R, LBM_OP_TRT>(p, streaming, masked, stream);
+        case LBM_OP_NO_COLLISION: return by_mask<S, R, LBM_OP_NO_COLLISION>(p, streaming, masked, variant, stream);
+        case LBM_OP_BGK: return by_mask<S, R, LBM_OP_BGK>(p, streaming, masked, variant, stream);
+        case LBM_OP_TRT: return by_mask<S, R, LBM_OP_TRT>(p, streaming, masked, variant, stream);
         case LBM_OP_KBC:
             // KBC exists for D2Q9 and D3Q27 only (kbc_collision.py:101,116)
             if constexpr (S::ID == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
-            else return by_mask<S, R, LBM_OP_KBC>(p, streaming, masked, stream);
+            else return by_mask<S, R, LBM_OP_KBC>(p, streaming, masked, variant, stream);
     }
     return LBM_ERR_BAD_ARGUMENT;
 }
 
 template <class S, class R>
-const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int) {
+const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int variant) {
+    if (S::Q == 9 && (variant == 2 || variant == 4))
+        return masked ? "multi_masked+general_nodes" : "multi";
     return masked ? "scalar_masked+general_nodes" : "scalar";
 }
 

@@ -338,6 +338,40 @@ def test_obstacle_matches_live_oracle(stencil, res, coll, strategy, dtype):
     assert err < TOL[dtype], (stencil, coll, strategy, err)
 
 
+# ------------------------------------------------------------------ ragged / degenerate lattices
+@pytest.mark.parametrize("stencil,res", [("D2Q9", [1, 1]), ("D2Q9", [2, 3]), ("D2Q9", [37, 1]), ("D2Q9", [3, 259]),
+                                         ("D3Q19", [1, 1, 1]), ("D3Q19", [2, 2, 2]), ("D3Q19", [5, 7, 3]),
+                                         ("D3Q27", [3, 1, 33]), ("D3Q27", [1, 9, 65]), ("D3Q19", [7, 3, 300])])
+@pytest.mark.parametrize("strategy", ["POST_STREAMING", "PRE_STREAMING", "DOUBLE_STREAMING"])
+def test_ragged_lattices_match_oracle(stencil, res, strategy):
+    """extents of 1 and 2 (every neighbour is the node itself or the same neighbour twice), extents that are
+    no multiple of the warp or block size, rows longer than one block"""
+    ctx = cuda_ctx(torch.float64)
+    st = lo.stencil(stencil)
+    rng = np.random.default_rng(3)
+    f0 = st["w"].reshape((-1,) + (1,) * st["d"]) * (1.0 + 0.1 * (rng.random((st["q"], *res)) - 0.5))
+    flow = RandomFlow(ctx, res, 50.0, 0.1, stencil=STENCILS[stencil]())
+    set_f(flow, f0)
+    tau = flow.units.relaxation_parameter_lu
+    sim = lt.Simulation(flow, lt.TRTCollision(tau, 0.9), [], STRATS[strategy])
+    sim(5)
+    ref = lo.run(st, f0, 5, dict(kind="trt", tau=tau, tau_minus=0.9), strategy=strategy)
+    assert max_rel(get_f(flow), ref) < 1e-12
+
+
+def test_d2q9_multi_node_variants_match(monkeypatch):
+    """the 2- and 4-nodes-per-thread kernels (desc.variant) give the same bits as the default kernel"""
+    ctx = cuda_ctx(torch.float32)
+    results = []
+    for variant in ("0", "2", "4"):
+        monkeypatch.setenv("LBM_B200_VARIANT", variant)
+        flow = make_obstacle(ObstacleEqOut, ctx, [96, 200], lt.D2Q9())
+        sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+        sim(7)
+        results.append(flow.f.clone())
+    assert torch.equal(results[0], results[1]) and torch.equal(results[0], results[2])
+
+
 # ------------------------------------------------------------------ size-independent properties at BASELINE sizes
 def test_streaming_round_trip_is_bit_exact_at_full_size():
     """Pure streaming is a permutation: after lcm(resolution) steps every population is back
