@@ -184,7 +184,8 @@ typedef enum lbm_reduction {
     LBM_SUM_F_MASKED = 4,/* sum over q and nodes of f*mask, mask uint8 [nx,ny,nz] (observable_reporter.py:157) */
     LBM_ENSTROPHY = 5    /* sum of |curl u|^2 with 6th-order periodic differences, lattice units,
                             dx = 1 (observable_reporter.py:45-68, util/utility.py:56-58,88-98);
-                            needs d_u from lbm_moments */
+                            needs d_u from lbm_moments; an optional uint8 node mask restricts the sum
+                            (used for slabs extended by the stencil radius) */
 } lbm_reduction;
 
 /* Bytes of scratch lbm_reduce needs for this lattice. */

@@ -210,7 +210,14 @@ def initialize_f_neq(flow: Flow) -> torch.Tensor:
     u = torch.tensordot(st.e.t().contiguous(), f, dims=1) / rho
     grad_u = torch.stack([_gradient6(u[a]) for a in range(d)])
     pi1 = flow.units.relaxation_parameter_lu * rho * grad_u / st.cs ** 2
+    del grad_u
     eye = torch.eye(d, device=f.device) * flow.stencil.cs ** 2
     Q = torch.einsum("ia,ib->iab", st.e, st.e) - eye
-    fneq = st.w.reshape([-1] + [1] * d) * torch.einsum("ab...,iab->i...", pi1, Q)
-    return flow.equilibrium(flow, rho, u) - fneq
+    fneq = torch.einsum("ab...,iab->i...", pi1, Q)
+    del pi1
+    fneq.mul_(st.w.reshape([-1] + [1] * d))
+    if f.is_cuda and type(flow.equilibrium) is QuadraticEquilibrium:
+        feq = native.equilibrium_field(flow.stencil, rho, u, f.shape[1:])     # no full-size temporaries
+    else:
+        feq = flow.equilibrium(flow, rho, u)
+    return feq.sub_(fneq)

@@ -167,11 +167,13 @@ LBM_D R d6(const R *__restrict__ a, int64_t base, int i, int n, int64_t stride) 
 
 // sum |curl u|^2, u given as [d][n0*n1*n2] in USER component order
 template <class R, int D>
-__global__ void enstrophy_kernel(const R *__restrict__ u, int n0, int n1, int n2, double *partials) {
+__global__ void enstrophy_kernel(const R *__restrict__ u, int n0, int n1, int n2, const uint8_t *__restrict__ mask,
+                                 double *partials) {
     const int64_t N = (int64_t)n0 * n1 * n2;
     const int64_t s0 = (int64_t)n1 * n2, s1 = n2, s2 = 1;
     double acc = 0.0;
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[n]) continue;  // e.g. the halo planes of a slab extended for the stencil radius
         const int z = (int)(n % n2);
         const int y = (int)((n / n2) % n1);
         const int x = (int)(n / s0);
@@ -234,7 +236,7 @@ int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, in
             population_sum_kernel<R, 2><<<g, kReduceThreads, 0, st>>>(in, S::Q, n0, n1, n2, S::D, mask, partials);
             break;
         case LBM_ENSTROPHY:
-            enstrophy_kernel<R, S::D><<<g, kReduceThreads, 0, st>>>(in, n0, n1, n2, partials);
+            enstrophy_kernel<R, S::D><<<g, kReduceThreads, 0, st>>>(in, n0, n1, n2, mask, partials);
             break;
         default: return LBM_ERR_BAD_ARGUMENT;
     }

@@ -23,7 +23,7 @@ from .ext.flows import Obstacle, TaylorGreenVortex
 from .ext.reporter import Observable
 
 __all__ = ["SlabDecomposition", "SlabTaylorGreenVortex", "SlabObstacle", "SlabSimulation", "SlabEngine",
-           "GlobalSum", "GlobalMax", "make_tgv_slab_simulation"]
+           "GlobalSum", "GlobalMax", "SlabEnstrophy", "make_tgv_slab_simulation"]
 
 
 class SlabDecomposition:
@@ -352,6 +352,44 @@ class GlobalSum(_GlobalReduce):
 class GlobalMax(_GlobalReduce):
     """max of a rank-local observable (maximum velocity) over all slabs"""
     op = dist.ReduceOp.MAX
+
+
+class SlabEnstrophy(Observable):
+    """Global enstrophy of a slab-decomposed periodic flow (observable_reporter.py:45-68).  The 6th-order
+    stencil reaches three planes across each cut, so the velocity field -- not the populations -- of three
+    boundary planes is exchanged with both neighbours (a real exchange step: NCCL send/recv), the curl is
+    evaluated on the extended slab and summed over the owned planes only, then all-reduced."""
+    _HALO = 3
+
+    def __init__(self, flow, decomposition: SlabDecomposition = None, group=None):
+        super().__init__(flow)
+        self.dec = decomposition or flow.decomposition
+        self.group = group
+
+    def __call__(self, f=None):
+        f = self.flow.f if f is None else f
+        units, st, dec, h = self.flow.units, self.flow.stencil, self.dec, self._HALO
+        _, u = native.moments(st, f, want_rho=False)
+        if dec.world > 1:
+            if dec.nx_local < h:
+                raise ValueError(f"slabs must be at least {h} planes thick for the enstrophy stencil")
+            first, last = u[:, :h].contiguous(), u[:, -h:].contiguous()
+            from_lo, from_hi = torch.empty_like(last), torch.empty_like(first)
+            # order matters when both neighbours are the same rank (world 2): sends and receives pair up in order
+            ops = [dist.P2POp(dist.isend, last, dec.hi, self.group), dist.P2POp(dist.isend, first, dec.lo, self.group),
+                   dist.P2POp(dist.irecv, from_lo, dec.lo, self.group), dist.P2POp(dist.irecv, from_hi, dec.hi, self.group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            ext = torch.cat([from_lo, u, from_hi], dim=1).contiguous()
+            mask = torch.zeros(ext.shape[1:], dtype=torch.uint8, device=ext.device)
+            mask[h:-h] = 1
+            w2 = native.reduce(st, native.ENSTROPHY, ext, mask)
+            dist.all_reduce(w2, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            w2 = native.reduce(st, native.ENSTROPHY, u)
+        dx = units.convert_length_to_pu(1.0)
+        scale = units.convert_velocity_to_pu(1.0) / dx
+        return w2 * scale ** 2 * dx ** st.d
 
 
 def make_tgv_slab_simulation(context, global_resolution, reynolds_number, mach_number, stencil, strategy,

@@ -3,6 +3,7 @@ for DESIGN.md / profiles).  Prints one JSON line per case.
 
     python scripts/bench_configs.py [c1 c2 c3 c4 c5 ...] [--small]
 """
+import gc
 import json
 import os
 import sys
@@ -56,6 +57,7 @@ def timed(sim, steps, warmup):
 
 
 def report(name, flow, sim, steps=50, warmup=5, **extra):
+    gc.collect()
     torch.cuda.empty_cache()
     ms, launches = timed(sim, steps, warmup)
     n = 1
@@ -93,6 +95,7 @@ def main():
                     sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], strat)
                     report(f"C2 TGV3D D3Q19 BGK {n}^3 fp32", flow, sim)
                     del flow, sim
+                    gc.collect(); torch.cuda.empty_cache()
         elif case == "c3":
             for n in ((256,) if small else (256, 512)):
                 for strat in (S.PRE_STREAMING, S.POST_STREAMING):
@@ -101,6 +104,7 @@ def main():
                     sim = lt.Simulation(flow, lt.KBCCollision(), [], strat)
                     report(f"C3 TGV3D D3Q27 KBC {n}^3 fp32", flow, sim, steps=30)
                     del flow, sim
+                    gc.collect(); torch.cuda.empty_cache()
         elif case == "c4":
             for dt_ in (f32, f64):
                 for strat in (S.POST_STREAMING, S.PRE_STREAMING):
