@@ -1,0 +1,215 @@
+"""Property tests of the CUDA operators, modelled on the reference's own unit tests
+(tests/collision/*.py, tests/test_equilibrium.py, tests/boundary/*.py) but run through the B200 engine."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_rel
+
+pytestmark = pytest.mark.gpu
+
+lt = pytest.importorskip("lettuce_b200")
+from oracle import lbm_oracle as lo  # noqa: E402
+
+STENCILS = {"D2Q9": lt.D2Q9, "D3Q19": lt.D3Q19, "D3Q27": lt.D3Q27}
+COLLISIONS = ["bgk", "trt", "kbc"]
+
+
+def ctx(dtype=torch.float64):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return lt.Context("cuda", dtype=dtype)
+
+
+class TestFlow(lt.ExtFlow):
+    """uniform u = 1.01, p = 0.01 (pu): the reference's TestFlow (tests/conftest.py:195-232)"""
+    __test__ = False
+    boundary_factory = None
+
+    def make_resolution(self, resolution, stencil=None):
+        return resolution
+
+    def make_units(self, reynolds_number, mach_number, resolution):
+        return lt.UnitConversion(reynolds_number, mach_number, characteristic_length_lu=resolution[0])
+
+    def initial_pu(self):
+        return 0.01 * np.ones([1] + self.resolution), 1.01 * np.ones([self.stencil.d] + self.resolution)
+
+    @property
+    def post_boundaries(self):
+        return self.boundary_factory(self) if self.boundary_factory else []
+
+
+def random_flow(stencil, res, dtype=torch.float64, seed=1, amplitude=0.2, cls=TestFlow, re=100.0, ma=0.1):
+    flow = cls(ctx(dtype), res, re, ma, stencil=STENCILS[stencil]())
+    st = lo.stencil(stencil)
+    rng = np.random.default_rng(seed)
+    f0 = st["w"].reshape((-1,) + (1,) * st["d"]) * (1.0 + amplitude * (rng.random((st["q"], *res)) - 0.5))
+    flow.f = flow.context.convert_to_tensor(f0).contiguous()
+    return flow, st, f0
+
+
+def collide_once(flow, coll, tau):
+    c = {"bgk": lambda: lt.BGKCollision(tau), "trt": lambda: lt.TRTCollision(tau), "kbc": lambda: lt.KBCCollision(),
+         "none": lambda: lt.NoCollision()}[coll]()
+    lt.Simulation(flow, c, [], lt.StreamingStrategy.NO_STREAMING)(1)
+    return flow.f.cpu().numpy()
+
+
+@pytest.mark.parametrize("stencil", list(STENCILS))
+@pytest.mark.parametrize("coll", COLLISIONS)
+def test_collision_conserves_mass_and_momentum(stencil, coll):
+    """tests/collision/test_collision_conserves_{mass,momentum}.py"""
+    if coll == "kbc" and stencil == "D3Q19":
+        pytest.skip("KBC exists for D2Q9 and D3Q27 only")
+    flow, st, f0 = random_flow(stencil, [7] * STENCILS[stencil]().d)
+    f1 = collide_once(flow, coll, 0.6 if coll != "kbc" else flow.units.relaxation_parameter_lu)
+    assert np.max(np.abs(lo.rho(f1) - lo.rho(f0))) < 1e-14
+    assert np.max(np.abs(lo.j(st, f1) - lo.j(st, f0))) < 1e-14
+    assert np.max(np.abs(f1 - f0)) > 1e-6          # the operator did act
+
+
+@pytest.mark.parametrize("stencil", list(STENCILS))
+@pytest.mark.parametrize("coll", COLLISIONS)
+def test_collision_relaxes_shear_moments(stencil, coll):
+    """tests/collision/test_collision_relaxes_shear_moments.py, on a NON-equilibrium state: every second
+    moment relaxes towards its equilibrium value at rate 1/tau (BGK, TRT's even part, KBC's shear part)"""
+    if coll == "kbc" and stencil == "D3Q19":
+        pytest.skip("KBC exists for D2Q9 and D3Q27 only")
+    flow, st, f0 = random_flow(stencil, [6] * STENCILS[stencil]().d)
+    tau = 0.6 if coll != "kbc" else flow.units.relaxation_parameter_lu
+    f1 = collide_once(flow, coll, tau)
+    e = st["e"].astype(float)
+    shear = lambda f: np.einsum("q...,qa,qb->ab...", f, e, e)
+    feq = lo.equilibrium(st, lo.rho(f0), lo.u(st, f0))
+    expect = shear(f0) - (1.0 / tau) * (shear(f0) - shear(feq))
+    assert np.max(np.abs(shear(f1) - expect)) < 1e-13
+
+
+@pytest.mark.parametrize("stencil", list(STENCILS))
+def test_equilibrium_conserves_mass_and_momentum(stencil):
+    """tests/test_equilibrium.py:4-39 on the device-side equilibrium kernel (lbm_equilibrium)"""
+    c = ctx()
+    s = STENCILS[stencil]()
+    res = [5, 6, 7][:s.d]
+    rng = np.random.default_rng(2)
+    rho = c.convert_to_tensor(1.0 + 0.1 * rng.random([1, *res]))
+    u = c.convert_to_tensor(0.05 * rng.standard_normal([s.d, *res]))
+    f = lt.native.equilibrium_field(s, rho, u, res)
+    r, v = lt.native.moments(s, f)
+    assert max_rel(r.cpu().numpy(), rho.cpu().numpy()) < 1e-14
+    assert np.max(np.abs(v.cpu().numpy() - u.cpu().numpy())) < 1e-15
+    st = lo.stencil(stencil)
+    assert max_rel(f.cpu().numpy(), lo.equilibrium(st, rho.cpu().numpy()[0], u.cpu().numpy())) < 1e-14
+
+
+def test_kbc_increases_pseudo_entropy_over_bgk():
+    """tests/collision/test_collision_optimizes_pseudo_entropy.py: same seeded random populations"""
+    for stencil in ("D2Q9", "D3Q27"):
+        d = STENCILS[stencil]().d
+        np.random.seed(1)
+        f0 = np.random.random([STENCILS[stencil]().q] + [3] * d)
+        st = lo.stencil(stencil)
+        outs = {}
+        for coll in ("kbc", "bgk"):
+            flow = TestFlow(ctx(), [3] * d, 100.0, 0.1, stencil=STENCILS[stencil]())
+            flow.f = flow.context.convert_to_tensor(f0).contiguous()
+            tau = flow.units.relaxation_parameter_lu     # KBC takes tau from the units (kbc_collision.py:97-99)
+            outs[coll] = collide_once(flow, coll, tau)
+        feq = lo.equilibrium(st, lo.rho(f0), lo.u(st, f0))
+        entropy = lambda f: lo.rho(f) - (f * f / feq).sum(axis=0)      # Flow.pseudo_entropy_local, _flow.py:222-228
+        assert (entropy(outs["bgk"]) < entropy(outs["kbc"])).all()
+
+
+@pytest.mark.parametrize("stencil", list(STENCILS))
+def test_bounce_back_everywhere_and_nowhere(stencil):
+    """tests/boundary/test_bounceback_bc.py:6-36"""
+    d = STENCILS[stencil]().d
+    for everywhere in (True, False):
+        class F(TestFlow):
+            boundary_factory = staticmethod(
+                lambda self: [lt.BounceBackBoundary(torch.full(self.resolution, everywhere, dtype=torch.bool))])
+        flow, st, f0 = random_flow(stencil, [5] * d, cls=F)
+        f1 = collide_once(flow, "none", 1.0)
+        assert np.array_equal(f1, f0[st["opposite"]] if everywhere else f0)
+
+
+@pytest.mark.parametrize("stencil", list(STENCILS))
+@pytest.mark.parametrize("sign", [1, -1])
+def test_equilibrium_outlet_p_plane(stencil, sign):
+    """tests/boundary/test_equilibrium_bc_outlet_p.py:6-31: the outlet plane equals feq(rho_outlet, u of the
+    neighbour plane); here exactly (the reference accepts rel 1e-2), for both ends of the last axis"""
+    d = STENCILS[stencil]().d
+    direction = [0] * (d - 1) + [sign]
+
+    class F(TestFlow):
+        boundary_factory = staticmethod(lambda self: [lt.EquilibriumOutletP(direction, self, rho_outlet=1.2)])
+
+    flow = F(ctx(), [8] * d, 1.0, 0.1, stencil=STENCILS[stencil]())
+    f0 = flow.f.cpu().numpy()
+    f1 = collide_once(flow, "none", 1.0)
+    st = lo.stencil(stencil)
+    u_lu = np.full([d] + [8] * (d - 1), flow.units.convert_velocity_to_lu(1.01))
+    expect = lo.equilibrium(st, 1.2, u_lu)
+    plane = -1 if sign > 0 else 0
+    assert max_rel(f1[..., plane], expect) < 1e-13
+    keep = [i for i in range(8) if i != plane % 8]
+    assert np.array_equal(f1[..., keep], f0[..., keep])       # NoCollision elsewhere
+
+
+def test_anti_bounce_back_outlet_formula():
+    """tests/boundary/test_antibounceback_outlet_bc.py: textbook formula (Krueger et al., p. 195) on the plane"""
+    class F(TestFlow):
+        boundary_factory = staticmethod(lambda self: [lt.AntiBounceBackOutlet([1, 0], self)])
+
+    flow, st, f0 = random_flow("D2Q9", [6, 7], cls=F, amplitude=0.05)
+    f1 = collide_once(flow, "none", 1.0)
+    u = lo.u(st, f0)
+    u_w = u[:, -1] + 0.5 * (u[:, -1] - u[:, -2])
+    rho_w = lo.rho(f0)[-1]
+    expect = f0.copy()
+    for q in np.flatnonzero(st["e"][:, 0] == 1):
+        eu = st["e"][q] @ u_w
+        expect[st["opposite"][q], -1] = (-f0[q, -1] + st["w"][q] * rho_w *
+                                         (2 + eu ** 2 / lo.CS2 ** 2 - (u_w ** 2).sum(axis=0) / lo.CS2))
+    assert max_rel(f1, expect) < 1e-13
+
+
+def test_masks_nonempty_for_obstacle():
+    """tests/boundary/test_bc_masks.py:4-19"""
+    c = ctx(torch.float32)
+    flow = lt.Obstacle(c, [32, 16], 100, 0.05, domain_length_x=16, stencil=lt.D2Q9())
+    m = torch.zeros([32, 16], dtype=torch.bool); m[10:14, 6:10] = True
+    flow.mask = m
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+    assert sim.no_collision_mask.any() and sim.no_streaming_mask.any()
+    sim(2)
+    assert torch.isfinite(flow.f).all()
+
+
+def test_reporters_change_slowly():
+    """tests/reporter/test_generic_reporters.py:4-25: observables move < 5 % over two steps"""
+    c = ctx(torch.float32)
+    flow = lt.TaylorGreenVortex(c, [32] * 3, 1600.0, 0.05, stencil=lt.D3Q27())
+    reps = [lt.ObservableReporter(o(flow), interval=1, out=None)
+            for o in (lt.IncompressibleKineticEnergy, lt.Enstrophy, lt.MaximumVelocity, lt.Mass)]
+    lt.Simulation(flow, lt.KBCCollision(), reps)(2)
+    for r in reps:
+        vals = np.array([row[2] for row in r.out])
+        assert len(vals) == 3 and np.all(np.abs(vals / vals[0] - 1) < 0.05)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """tests/test_checkpoint.py: dump, keep stepping, load restores the dumped state"""
+    c = ctx(torch.float64)
+    flow = lt.TaylorGreenVortex(c, [16, 16], 10.0, 0.05, stencil=lt.D2Q9())
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+    sim(3)
+    saved = flow.f.clone()
+    flow.dump(tmp_path / "f.pkl")
+    sim(3)
+    assert not torch.equal(flow.f, saved)
+    flow.load(tmp_path / "f.pkl")
+    assert torch.equal(flow.f, saved)
+    sim(1)                                  # f_next is re-allocated lazily after load
+    assert torch.isfinite(flow.f).all()
