@@ -62,7 +62,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -206,8 +206,15 @@ def gpu_main(args):
         stepper(args.steps)
         stop.record()
         barrier()
+        launches = native.launch_count() - launches0
+        # the timed region is only tens of milliseconds: keep the same kernel running (untimed) for
+        # about half a second so that the 50 ms clock samples are taken under this load
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            stepper(20 if args.steps >= 20 else 2 * ((args.steps + 1) // 2))
+            torch.cuda.synchronize(dev)
+        barrier()
     ms = start.elapsed_time(stop)
-    launches = native.launch_count() - launches0
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

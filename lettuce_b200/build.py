@@ -3,8 +3,8 @@
 No per-configuration JIT (the reference generates and compiles one extension per
 (stencil, strategy, operator list), lettuce/cuda_native/_generator.py:99-127):
 every (stencil, dtype, collision, streaming, masked) variant is template-instantiated
-once and selected at run time from the descriptor.  The six (stencil, dtype) pairs
-are separate translation units and compile in parallel.
+once and selected at run time from the descriptor.  The 22 (stencil, dtype, collision)
+triples are separate translation units and compile in parallel.
 
     python -m lettuce_b200.build [--force] [--verbose]
 """
@@ -34,10 +34,14 @@ def _units():
     units = [("lbm_api", os.path.join(CSRC, "lbm_api.cu"), []),
              ("lbm_moments", os.path.join(CSRC, "lbm_moments.cu"), []),
              ("lbm_slab", os.path.join(CSRC, "lbm_slab.cu"), [])]
-    for s in STENCILS:
-        for r in REALS:
-            units.append((f"lbm_step_{s}_{r}", os.path.join(CSRC, "lbm_step_inst.cu"),
-                          [f"-DLBM_INST_STENCIL={s}", f"-DLBM_INST_REAL={r}"]))
+    # heaviest units first so the pool's tail is short
+    for c, cname in ((3, "kbc"), (2, "trt"), (1, "bgk"), (0, "none")):
+        for s in reversed(STENCILS):
+            if cname == "kbc" and s == "D3Q19":
+                continue            # KBC exists for D2Q9 and D3Q27 only
+            for r in reversed(REALS):
+                units.append((f"lbm_step_{s}_{r}_{cname}", os.path.join(CSRC, "lbm_step_inst.cu"),
+                              [f"-DLBM_INST_STENCIL={s}", f"-DLBM_INST_REAL={r}", f"-DLBM_INST_COLL={c}"]))
     return units
 
 

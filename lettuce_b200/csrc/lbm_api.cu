@@ -21,6 +21,27 @@ template <class S, class R>
 int launch_equilibrium(const R *rho, const int64_t *rs, const R *u, const int64_t *us, int n0, int n1, int n2, R *f,
                        cudaStream_t stream);
 
+// collision dispatch over the separately compiled (stencil, dtype, collision) units
+template <class S, class R>
+static int launch_step(const StepParams<R> &p, int coll, int streaming, bool masked, int variant, cudaStream_t stream) {
+    switch (coll) {
+        case LBM_OP_NO_COLLISION: return launch_step_coll<S, R, LBM_OP_NO_COLLISION>(p, streaming, masked, variant, stream);
+        case LBM_OP_BGK: return launch_step_coll<S, R, LBM_OP_BGK>(p, streaming, masked, variant, stream);
+        case LBM_OP_TRT: return launch_step_coll<S, R, LBM_OP_TRT>(p, streaming, masked, variant, stream);
+        case LBM_OP_KBC:
+            // KBC exists for D2Q9 and D3Q27 only (kbc_collision.py:101,116)
+            if constexpr (S::ID == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
+            else return launch_step_coll<S, R, LBM_OP_KBC>(p, streaming, masked, variant, stream);
+    }
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+template <class S, class R>
+static const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int variant) {
+    if (S::Q == 9 && (variant == 2 || variant == 4)) return masked ? "multi_masked+general_nodes" : "multi";
+    return masked ? "scalar_masked+general_nodes" : "scalar";
+}
+
 static int cuda_fail(int e) {
     if (e <= 0) return e;  // already an lbm_status
     snprintf(g_cuda_error, sizeof g_cuda_error, "%s: %s", cudaGetErrorName((cudaError_t)e),

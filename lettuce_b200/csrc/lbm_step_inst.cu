@@ -1,5 +1,5 @@
-// lbm_step_inst.cu -- instantiates the step kernels for ONE (stencil, dtype) pair.
-// Compile with -DLBM_INST_STENCIL=D3Q19 -DLBM_INST_REAL=float (see build.py).
+// lbm_step_inst.cu -- instantiates the step kernels for ONE (stencil, dtype, collision) triple.
+// Compile with -DLBM_INST_STENCIL=D3Q19 -DLBM_INST_REAL=float -DLBM_INST_COLL=1 (see build.py).
 #include "lbm_launch.cuh"
 
 #ifndef LBM_INST_STENCIL
@@ -7,6 +7,9 @@
 #endif
 #ifndef LBM_INST_REAL
 #error "define LBM_INST_REAL (float | double)"
+#endif
+#ifndef LBM_INST_COLL
+#error "define LBM_INST_COLL (lbm_op_kind collision value 0..3)"
 #endif
 
 namespace lbm {
@@ -85,30 +88,12 @@ int by_mask(const StepParams<R> &p, int streaming, bool masked, int variant, cud
 
 }  // namespace
 
-template <class S, class R>
-int launch_step(const StepParams<R> &p, int coll, int streaming, bool masked, int variant, cudaStream_t stream) {
-    switch (coll) {
-        case LBM_OP_NO_COLLISION: return by_mask<S, R, LBM_OP_NO_COLLISION>(p, streaming, masked, variant, stream);
-        case LBM_OP_BGK: return by_mask<S, R, LBM_OP_BGK>(p, streaming, masked, variant, stream);
-        case LBM_OP_TRT: return by_mask<S, R, LBM_OP_TRT>(p, streaming, masked, variant, stream);
-        case LBM_OP_KBC:
-            // KBC exists for D2Q9 and D3Q27 only (kbc_collision.py:101,116)
-            if constexpr (S::ID == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
-            else return by_mask<S, R, LBM_OP_KBC>(p, streaming, masked, variant, stream);
-    }
-    return LBM_ERR_BAD_ARGUMENT;
+template <class S, class R, int COLL>
+int launch_step_coll(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream) {
+    return by_mask<S, R, COLL>(p, streaming, masked, variant, stream);
 }
 
-template <class S, class R>
-const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int variant) {
-    if (S::Q == 9 && (variant == 2 || variant == 4))
-        return masked ? "multi_masked+general_nodes" : "multi";
-    return masked ? "scalar_masked+general_nodes" : "scalar";
-}
-
-template int launch_step<LBM_INST_STENCIL, LBM_INST_REAL>(const StepParams<LBM_INST_REAL> &, int, int, bool, int,
-                                                          cudaStream_t);
-template const char *step_variant_name<LBM_INST_STENCIL, LBM_INST_REAL>(const StepParams<LBM_INST_REAL> &, int, int,
-                                                                        bool, int);
+template int launch_step_coll<LBM_INST_STENCIL, LBM_INST_REAL, LBM_INST_COLL>(const StepParams<LBM_INST_REAL> &, int,
+                                                                              bool, int, cudaStream_t);
 
 }  // namespace lbm

@@ -41,7 +41,7 @@ def gpu_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev):
     make = {"bgk": lambda f: lt.BGKCollision(f.units.relaxation_parameter_lu), "kbc": lambda f: lt.KBCCollision(),
             "trt": lambda f: lt.TRTCollision(f.units.relaxation_parameter_lu)}[coll]
     energy = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=steps, out=None)
-    enst = lt.ObservableReporter(slab.SlabEnstrophy(flow), interval=steps, out=None) if dec.nx_local >= 3 else None
+    enst = lt.ObservableReporter(slab.SlabEnstrophy(flow), interval=steps, out=None) if min(dec.sizes) >= 3 else None
     umax = lt.ObservableReporter(slab.GlobalMax(lt.MaximumVelocity(flow)), interval=steps, out=None)
     sim = slab.SlabSimulation(flow, make(flow), [r for r in (energy, enst, umax) if r is not None], strategy, dec)
     f0 = gather_slabs(flow.f, dec, dev)

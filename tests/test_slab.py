@@ -57,7 +57,7 @@ def test_slab_cuda_path_matches_single_gpu_bit_exact():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    world = 2 if n < 4 else 4
+    world = 2 if n < 4 else (4 if n < 8 else 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tests", "slab_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
