@@ -234,14 +234,17 @@ typedef struct lbm_slab {
     /* peer-mapped addresses where this rank publishes the number of steps it has completed: slot 1 of
      * the lo neighbour's counter pair and slot 0 of the hi neighbour's */
     uint64_t *signal_lo, *signal_hi;
-    /* this rank's own counter pair (in lbm_ipc_alloc memory): [0] written by lo, [1] written by hi */
+    /* this rank's own counter block (in lbm_ipc_alloc memory, at least 4 words): [0] written by lo,
+     * [1] written by hi, [2],[3] scratch of the in-kernel lock step */
     const uint64_t *wait_slots;
     uint64_t epoch;                /* steps completed before this call; identical on all ranks */
 } lbm_slab;
 
-/* n lock-stepped time steps on an x-slab.  After every step the rank publishes its progress to both
- * neighbours and waits (on the device, inside a 1-thread kernel) until both have completed the same
- * step, which orders the peer reads/writes of consecutive steps.  desc->halo's population pointers
+/* n lock-stepped time steps on an x-slab.  Ranks publish the number of steps they have completed to both
+ * neighbours and never run a boundary plane of step k+1 before both neighbours have completed step k,
+ * which orders the peer reads/writes of consecutive steps.  Unmasked slabs do this INSIDE the step kernel
+ * (boundary-plane CTAs are scheduled first, wait for the neighbour's counter, and the last of them
+ * publishes this rank's counter; interior CTAs never wait); masked slabs use a 1-thread kernel per step.  desc->halo's population pointers
  * are ignored (they are derived from `slab`); its label/frozen pointers are used as given. */
 int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
                     void *stream);

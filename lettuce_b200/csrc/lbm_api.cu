@@ -50,6 +50,7 @@ static int cuda_fail(int e) {
 }
 
 int cuda_fail_public(int e) { return cuda_fail(e); }
+int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream);
 
 struct Dims {
     int n0, n1, n2, d, q;
@@ -164,9 +165,11 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
 }
 
 template <class S, class R>
-static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, cudaStream_t st) {
+static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, const SlabSync *sync,
+                      cudaStream_t st) {
     StepParams<R> p;
     fill_params<S, R>(d, dm, f_in, f_out, p);
+    if (sync) p.sync = *sync;
     const bool masked = d->n_ops > 1;
     return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, d->variant, st));
 }
@@ -281,6 +284,14 @@ const char *lbm_last_cuda_error(void) { return g_cuda_error; }
 int64_t lbm_launch_count(void) { return g_launch_count; }
 
 int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream) {
+    return step_with_sync(desc, d_f_in, d_f_out, nullptr, stream);
+}
+
+}  // extern "C"
+
+namespace lbm {
+// lbm_step plus the optional in-kernel slab lock step (used by lbm_slab_step_n)
+int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream) {
     Dims dm;
     int rc = validate_desc(desc, dm);
     if (rc) return rc;
@@ -289,9 +300,12 @@ int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void 
     const char *a = (const char *)d_f_in, *b = (const char *)d_f_out;
     if (a < b + bytes && b < a + bytes) return LBM_ERR_ALIASING;
     LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype,
-                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, (cudaStream_t)stream)));
+                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, sync, (cudaStream_t)stream)));
     return LBM_ERR_BAD_ARGUMENT;
 }
+}  // namespace lbm
+
+extern "C" {
 
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream) {
     if (n < 0) return LBM_ERR_BAD_ARGUMENT;

@@ -9,6 +9,7 @@
 namespace lbm {
 
 int cuda_fail_public(int e);
+int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream);
 
 // One thread: publish `epoch` to both neighbours, then wait until both neighbours have published it.
 // Everything this rank's step kernel wrote (also into peer memory) is complete when this kernel starts
@@ -24,6 +25,21 @@ __global__ void peer_signal_wait_kernel(unsigned long long *sig_lo, unsigned lon
     const long long t0 = clock64();
     while (w[0] < epoch || w[1] < epoch) {
         // a neighbour that never arrives (crashed rank) must not hang the GPU: ~20 s at 2 GHz, then fault
+        if (clock64() - t0 > 40000000000LL) __trap();
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// Wait only: used once at the end of a batch of in-kernel-synchronised steps, so that when the batch has
+// completed on this rank's stream the neighbours have also finished the last step's boundary planes --
+// their pushes into this rank's planes have landed and their pulls from them are done -- before a
+// reporter reads, or the caller overwrites, the populations.
+__global__ void peer_wait_kernel(const unsigned long long *wait_slots, unsigned long long epoch) {
+    if (threadIdx.x != 0) return;
+    const volatile unsigned long long *w = wait_slots;
+    const long long t0 = clock64();
+    while (w[0] < epoch || w[1] < epoch) {
         if (clock64() - t0 > 40000000000LL) __trap();
         __nanosleep(200);
     }
@@ -84,6 +100,15 @@ int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a
     char *lo_in = (char *)slab->lo_a, *lo_out = (char *)slab->lo_b;
     char *hi_in = (char *)slab->hi_a, *hi_out = (char *)slab->hi_b;
     unsigned long long epoch = slab->epoch;
+    // Unmasked slabs thick enough for separate lo / hi boundary planes synchronise inside the step kernel
+    // (step_sync_kernel); everything else uses the one-thread signal/wait kernel after each step.
+    const int w = (desc->streaming == LBM_DOUBLE_STREAMING) ? 2 : 1;
+    const bool fused = desc->n_ops == 1 && desc->lat.nx >= 2 * w;
+    unsigned long long *counters = (unsigned long long *)slab->wait_slots;   // [0],[1] peers; [2],[3] scratch
+    if (fused) {
+        const int e = (int)cudaMemsetAsync(counters + 2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream);
+        if (e) return cuda_fail_public(e);
+    }
     for (int64_t k = 0; k < n; ++k) {
         // x = -1 is the LAST plane of the lo neighbour, x = nx is the FIRST plane of the hi neighbour
         d.halo.in_lo = lo_in + (size_t)(slab->lo_nx - 1) * plane * es;
@@ -92,18 +117,40 @@ int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a
         d.halo.in_hi = hi_in;
         d.halo.out_hi = hi_out;
         d.halo.in_hi_qstride = d.halo.out_hi_qstride = (int64_t)slab->hi_nx * plane;
-        const int rc = lbm_step(&d, a, b, stream);
-        if (rc) return rc;
-        ++epoch;
-        peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)slab->signal_lo,
-                                                                    (unsigned long long *)slab->signal_hi,
-                                                                    (const unsigned long long *)slab->wait_slots, epoch);
-        ++g_launch_count;
-        const int e = (int)cudaGetLastError();
-        if (e) return cuda_fail_public(e);
+        if (fused) {
+            SlabSync sync;
+            sync.sig_lo = (unsigned long long *)slab->signal_lo;
+            sync.sig_hi = (unsigned long long *)slab->signal_hi;
+            sync.wait = counters;
+            sync.done = counters + 2;
+            sync.wait_value = epoch;          // neighbours have completed the previous step
+            sync.signal_value = epoch + 1;
+            sync.ctas_per_side = 0;           // filled in by the launcher
+            sync.on = 1;
+            const int rc = step_with_sync(&d, a, b, &sync, stream);
+            if (rc) return rc;
+            ++epoch;
+        } else {
+            const int rc = lbm_step(&d, a, b, stream);
+            if (rc) return rc;
+            ++epoch;
+            peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)slab->signal_lo,
+                                                                        (unsigned long long *)slab->signal_hi,
+                                                                        (const unsigned long long *)slab->wait_slots,
+                                                                        epoch);
+            ++g_launch_count;
+            const int e = (int)cudaGetLastError();
+            if (e) return cuda_fail_public(e);
+        }
         void *t = a; a = b; b = t;
         char *c = lo_in; lo_in = lo_out; lo_out = c;
         c = hi_in; hi_in = hi_out; hi_out = c;
+    }
+    if (fused && n > 0) {
+        peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long *)slab->wait_slots, epoch);
+        ++g_launch_count;
+        const int e = (int)cudaGetLastError();
+        if (e) return cuda_fail_public(e);
     }
     return LBM_OK;
 }

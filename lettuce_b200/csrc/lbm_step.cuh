@@ -25,6 +25,18 @@ struct OpDev {
     int64_t u_stride[4];         // component, internal axes 0..2
 };
 
+// In-kernel lock step of neighbouring slabs (multi-GPU, unmasked runs): boundary-plane CTAs wait for the
+// neighbour's progress counter before they touch peer memory and publish this rank's counter when the
+// last of them has finished -- no separate synchronisation kernel, interior CTAs never wait.
+struct SlabSync {
+    unsigned long long *sig_lo, *sig_hi;   // peer-mapped: neighbour's wait slot for this rank
+    const unsigned long long *wait;        // local: [0] written by lo neighbour, [1] by hi neighbour
+    unsigned long long *done;              // local: [0],[1] finished boundary CTAs per side (zeroed per call)
+    unsigned long long wait_value, signal_value;
+    unsigned int ctas_per_side;
+    int on;
+};
+
 template <class R>
 struct StepParams {
     const R *in;
@@ -41,6 +53,7 @@ struct StepParams {
     int n_general;
     int n_ops, collision_index;
     R ca, cb;  // scalars of the collision entry
+    SlabSync sync;
     OpDev<R> ops[LBM_MAX_OPS];
 };
 
@@ -262,26 +275,13 @@ constexpr int min_blocks_per_sm() {
     return (sizeof(R) == 4 && COLL == LBM_OP_KBC && S::Q == 27) ? 3 : 0;  // 0 = no constraint
 }
 
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
-__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
-    step_scalar_kernel(const __grid_constant__ StepParams<R> p) {
+// one node: gather, collide, scatter.  Addresses are split into a block-uniform part (plane pointer +
+// q * stride) and a 32-bit in-plane index per thread (row offset + column, nine combinations), so one
+// access costs one IMAD.WIDE instead of a chain of 64-bit integer operations.
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+LBM_D void node_update(const StepParams<R> &p, int x, int y, int z) {
     constexpr int Q = S::Q;
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
-    if (z >= p.n2 || y >= p.n1) return;
-    const int64_t row = (int64_t)y * p.n2 + z;
-
-    if (MASKED) {
-        // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
-        // bit 7 and are left to general_nodes_kernel; every output slot still has exactly one writer.
-        if (p.labels[(int64_t)x * p.n1 * p.n2 + row] != p.collision_index) return;
-    }
-
-    // Neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243).  Addresses are
-    // split into a block-uniform part (plane pointer + q * stride, computed on the uniform datapath) and a
-    // 32-bit in-plane index per thread (row offset + column, nine combinations), so one access costs one
-    // IMAD.WIDE instead of a chain of 64-bit integer operations.
+    // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
     const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
     const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
     const int rowm = ym * p.n2, row0 = y * p.n2, rowp = yp * p.n2;
@@ -315,6 +315,61 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
     } else {
         R *dst = p.out + (int64_t)x * p.n1 * p.n2;
         ForQ<Q>::run([&]<int q>() { (dst + q * p.N)[row0 + z] = f[q]; });
+    }
+}
+
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
+__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
+    step_scalar_kernel(const __grid_constant__ StepParams<R> p) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.z;
+    if (z >= p.n2 || y >= p.n1) return;
+    if (MASKED) {
+        // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
+        // bit 7 and are left to general_nodes_kernel; every output slot still has exactly one writer.
+        if (p.labels[(int64_t)x * p.n1 * p.n2 + (int64_t)y * p.n2 + z] != p.collision_index) return;
+    }
+    node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+}
+
+// Slab variant of the bulk kernel (unmasked, multi-GPU): identical arithmetic, plus the in-kernel lock
+// step.  W boundary planes per side take part (2 when the step both pulls and pushes, because plane 1
+// then reads slots the neighbour pushed into plane 0 and pushes into plane 0 itself); their CTAs are
+// scheduled FIRST so that the progress counters go out early and the neighbour's next step never stalls.
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
+    step_sync_kernel(const __grid_constant__ StepParams<R> p) {
+    constexpr int W = (PULL && PUSH) ? 2 : 1;
+    const int zb = blockIdx.z;
+    const int x = zb < W ? zb : (zb < 2 * W ? p.n0 - 2 * W + zb : zb - W);   // host guarantees n0 >= 2 W
+    const bool lo = x < W, hi = x >= p.n0 - W;
+    const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+    if (lo || hi) {
+        if (leader) {
+            const volatile unsigned long long *w = p.sync.wait + (lo ? 0 : 1);
+            const long long t0 = clock64();
+            while (*w < p.sync.wait_value) {
+                if (clock64() - t0 > 40000000000LL) __trap();   // a dead neighbour must not hang the GPU
+                __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (z < p.n2 && y < p.n1) node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+    if (lo || hi) {
+        __threadfence_system();   // this thread's loads from / stores to the neighbour are performed
+        __syncthreads();
+        if (leader) {
+            const unsigned long long old = atomicAdd(p.sync.done + (lo ? 0 : 1), 1ULL);
+            if ((old + 1) % p.sync.ctas_per_side == 0) {
+                __threadfence_system();
+                *(volatile unsigned long long *)(lo ? p.sync.sig_lo : p.sync.sig_hi) = p.sync.signal_value;
+            }
+        }
     }
 }
 

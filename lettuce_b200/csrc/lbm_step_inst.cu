@@ -31,6 +31,16 @@ int launch_bulk(const StepParams<R> &p, cudaStream_t stream) {
     void (*bulk)(const StepParams<R>) = nullptr;
     if constexpr (NPT == 1) bulk = step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED>;
     else bulk = step_multi_kernel<S, R, COLL, PULL, PUSH, MASKED, NPT>;
+    if constexpr (!MASKED && NPT == 1) {
+        if (p.sync.on) {       // multi-GPU slab with in-kernel lock step (lbm_slab_step_n)
+            StepParams<R> ps = p;
+            ps.sync.ctas_per_side = grid.x * grid.y * ((PULL && PUSH) ? 2 : 1);
+            step_sync_kernel<S, R, COLL, PULL, PUSH><<<grid, block, 0, stream>>>(ps);
+            ++g_launch_count;
+            return (int)cudaGetLastError();
+        }
+    }
+    if (p.sync.on) return LBM_ERR_UNSUPPORTED;
     if (MASKED && p.n_general > 0) {
         // The sparse kernel is a chain of dependent loads on a handful of CTAs (~10 us at 15 k nodes); it
         // and the bulk kernel write disjoint slots, so the bulk kernel is launched with programmatic
@@ -63,6 +73,7 @@ int launch_bulk(const StepParams<R> &p, cudaStream_t stream) {
 template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
 int launch_scalar(const StepParams<R> &p, int variant, cudaStream_t stream) {
     if constexpr (S::Q == 9) {
+        if (p.sync.on) variant = 0;
         if (variant == 2) return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 2>(p, stream);
         if (variant == 4) return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 4>(p, stream);
     }

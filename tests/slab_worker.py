@@ -147,8 +147,11 @@ def gpu_main():
               (lt.D2Q9, [48, 24], "bgk", S.POST_STREAMING, torch.float64, 10, True),
               (lt.D3Q19, [world * 2, 16, 16], "bgk", S.POST_STREAMING, torch.float32, 6, False)]
     ok = all([gpu_obstacle_case(*c[:6], rank, world, dev, stock=c[6]) for c in ocases]) and ok
+    print(f"[slab-worker] rank {rank}: all cases done, ok={ok}", flush=True)
+    torch.cuda.synchronize(dev)
     dist.barrier()
     dist.destroy_process_group()
+    print(f"[slab-worker] rank {rank}: process group destroyed", flush=True)
     if not ok:
         sys.exit(1)
 
@@ -198,4 +201,12 @@ def cpu_worker(rank, world, port, results):
 
 
 if __name__ == "__main__":
-    gpu_main()
+    import faulthandler
+    import traceback
+    faulthandler.enable()
+    try:
+        gpu_main()
+    except BaseException:
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise
