@@ -70,6 +70,8 @@ typedef enum lbm_op_kind {
     LBM_OP_BGK = 1,          /* ext/_collision/bgk_collision.py:17-22 (force = None); p0 = tau */
     LBM_OP_TRT = 2,          /* ext/_collision/trt_collision.py:16-27; p0 = tau_plus, p1 = tau_minus */
     LBM_OP_KBC = 3,          /* ext/_collision/kbc_collision.py:96-160; p0 = tau (units.relaxation_parameter_lu) */
+    LBM_OP_REGULARIZED = 4,  /* ext/_collision/regularized_collision.py:17-43; p0 = tau (units.relaxation_parameter_lu) */
+    LBM_OP_SMAGORINSKY = 5,  /* ext/_collision/smagorinsky_collision.py:22-40 (force = None); p0 = tau, p1 = constant */
     LBM_OP_BOUNCE_BACK = 16, /* ext/_boundary/bounce_back_boundary.py:10-32 */
     LBM_OP_EQUILIBRIUM = 17, /* ext/_boundary/equilibrium_boundary_pu.py:79-84, values already in lattice units */
     LBM_OP_OUTLET_P = 18,    /* ext/_boundary/equilibrium_outlet_p.py:63-73; p0 = rho_outlet */

@@ -32,6 +32,8 @@ static int launch_step(const StepParams<R> &p, int coll, int streaming, bool mas
             // KBC exists for D2Q9 and D3Q27 only (kbc_collision.py:101,116)
             if constexpr (S::ID == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
             else return launch_step_coll<S, R, LBM_OP_KBC>(p, streaming, masked, variant, stream);
+        case LBM_OP_REGULARIZED: return launch_step_coll<S, R, LBM_OP_REGULARIZED>(p, streaming, masked, variant, stream);
+        case LBM_OP_SMAGORINSKY: return launch_step_coll<S, R, LBM_OP_SMAGORINSKY>(p, streaming, masked, variant, stream);
     }
     return LBM_ERR_BAD_ARGUMENT;
 }
@@ -73,7 +75,7 @@ static int lattice_dims(const lbm_lattice *lat, Dims &dm) {
     return LBM_OK;
 }
 
-static bool is_collision(int kind) { return kind >= LBM_OP_NO_COLLISION && kind <= LBM_OP_KBC; }
+static bool is_collision(int kind) { return kind >= LBM_OP_NO_COLLISION && kind <= LBM_OP_SMAGORINSKY; }
 static bool is_outlet(int kind) { return kind == LBM_OP_OUTLET_P || kind == LBM_OP_ANTI_BOUNCE_BACK; }
 
 static int validate_desc(const lbm_step_desc *d, Dims &dm) {

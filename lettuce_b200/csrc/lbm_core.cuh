@@ -341,6 +341,90 @@ struct Collide<S, R, LBM_OP_KBC> {
     }
 };
 
+// raw second moments P_ab = sum_q g_q e_qa e_qb of (f - feq), with f <- f - feq done in place
+template <class S, class R>
+struct NonEqMoments {
+    R P00 = 0, P11 = 0, P22 = 0, P01 = 0, P02 = 0, P12 = 0;
+    LBM_D void accumulate(const R (&g)[S::Q]) {
+        ForQ<S::Q>::run([&]<int q>() {
+            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
+            if constexpr (e0 != 0) P00 += g[q];
+            if constexpr (e1 != 0) P11 += g[q];
+            if constexpr (e2 != 0) P22 += g[q];
+            if constexpr (e0 * e1 == 1) P01 += g[q];
+            if constexpr (e0 * e1 == -1) P01 -= g[q];
+            if constexpr (e0 * e2 == 1) P02 += g[q];
+            if constexpr (e0 * e2 == -1) P02 -= g[q];
+            if constexpr (e1 * e2 == 1) P12 += g[q];
+            if constexpr (e1 * e2 == -1) P12 -= g[q];
+        });
+    }
+};
+
+// Regularized LBM (Latt & Chopard 2006): f = feq + (1 - 1/tau) w_q (Q_q : Pi_neq) / (2 cs^4),
+// Q_q = e_q e_q - cs^2 I  (lettuce/ext/_collision/regularized_collision.py:17-43).  a = 1 - 1/tau.
+template <class S, class R>
+struct Collide<S, R, LBM_OP_REGULARIZED> {
+    LBM_D static void apply(R (&f)[S::Q], R a, R) {
+        R rho, j[3];
+        moments<S, R>(f, rho, j);
+        const R inv_rho = R(1) / rho;
+        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
+        Equilibrium<S, R> eq(rho, u);
+        R feq[S::Q];
+        ForQ<S::Q>::run([&]<int q>() {
+            feq[q] = eq.template get<q>();
+            f[q] -= feq[q];
+        });
+        NonEqMoments<S, R> m;
+        m.accumulate(f);
+        const R trace = (m.P00 + m.P11 + m.P22) * R(kCs2);
+        const R scale = a * R(1.0 / (2.0 * kCs2 * kCs2));
+        ForQ<S::Q>::run([&]<int q>() {
+            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
+            R qpi = -trace;
+            if constexpr (e0 != 0) qpi += m.P00;
+            if constexpr (e1 != 0) qpi += m.P11;
+            if constexpr (e2 != 0) qpi += m.P22;
+            if constexpr (e0 * e1 != 0) qpi += R(2 * e0 * e1) * m.P01;
+            if constexpr (e0 * e2 != 0) qpi += R(2 * e0 * e2) * m.P02;
+            if constexpr (e1 * e2 != 0) qpi += R(2 * e1 * e2) * m.P12;
+            f[q] = feq[q] + scale * (R(S::w(q)) * qpi);
+        });
+    }
+};
+
+// Smagorinsky LES on BGK (lettuce/ext/_collision/smagorinsky_collision.py:22-40, force = None): strain from the
+// non-equilibrium second moments, two fixed-point iterations for tau_eff, then BGK with tau_eff.
+// a = tau, b = smagorinsky constant.
+template <class S, class R>
+struct Collide<S, R, LBM_OP_SMAGORINSKY> {
+    LBM_D static void apply(R (&f)[S::Q], R tau, R constant) {
+        R rho, j[3];
+        moments<S, R>(f, rho, j);
+        const R inv_rho = R(1) / rho;
+        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
+        Equilibrium<S, R> eq(rho, u);
+        R fn[S::Q];
+        ForQ<S::Q>::run([&]<int q>() { fn[q] = f[q] - eq.template get<q>(); });
+        NonEqMoments<S, R> m;
+        m.accumulate(fn);
+        // S_shear = Pi_neq / (2 rho cs^2); sum over ALL a,b of S_ab^2 (off-diagonals count twice)
+        const R k = R(1) / (R(2.0 * kCs2) * rho);
+        const R ss0 = k * k * (m.P00 * m.P00 + m.P11 * m.P11 + m.P22 * m.P22 +
+                               R(2) * (m.P01 * m.P01 + m.P02 * m.P02 + m.P12 * m.P12));
+        const R nu = (tau - R(0.5)) / R(3);
+        R tau_eff = tau;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const R ss = ss0 / (tau_eff * tau_eff);
+            tau_eff = (nu + constant * constant * ss) * R(3) + R(0.5);
+        }
+        const R inv_tau = R(1) / tau_eff;
+        ForQ<S::Q>::run([&]<int q>() { f[q] = f[q] - inv_tau * fn[q]; });
+    }
+};
+
 // parameters handed to Collide::apply for a given collision kind
 template <class R>
 LBM_HD void collision_scalars(int kind, double p0, double p1, R &a, R &b) {
@@ -348,6 +432,8 @@ LBM_HD void collision_scalars(int kind, double p0, double p1, R &a, R &b) {
     if (kind == LBM_OP_BGK) a = R(1.0 / p0);
     if (kind == LBM_OP_TRT) { a = R(1.0 / (2.0 * p0)); b = R(1.0 / (2.0 * p1)); }
     if (kind == LBM_OP_KBC) a = R(1.0 / (2.0 * p0));
+    if (kind == LBM_OP_REGULARIZED) a = R(1.0 - 1.0 / p0);
+    if (kind == LBM_OP_SMAGORINSKY) { a = R(p0); b = R(p1); }
 }
 
 }  // namespace lbm

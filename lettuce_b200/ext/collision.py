@@ -7,7 +7,8 @@ from __future__ import annotations
 
 from .._simulation import Collision
 
-__all__ = ["NoCollision", "BGKCollision", "TRTCollision", "KBCCollision"]
+__all__ = ["NoCollision", "BGKCollision", "TRTCollision", "KBCCollision", "RegularizedCollision",
+           "SmagorinskyCollision"]
 
 
 class NoCollision(Collision):
@@ -43,3 +44,23 @@ class KBCCollision(Collision):
     def __init__(self, tau: float = None):
         self.tau = tau
         self.beta = None
+
+
+class RegularizedCollision(Collision):
+    """regularized LBM of Latt & Chopard (lettuce/ext/_collision/regularized_collision.py:9-43).  Like KBC,
+    the reference ignores the constructor argument and takes tau from the flow's units on first use."""
+
+    def __init__(self, tau: float = None):
+        self.tau = tau
+
+
+class SmagorinskyCollision(Collision):
+    """Smagorinsky LES model on BGK (lettuce/ext/_collision/smagorinsky_collision.py:9-40)"""
+
+    def __init__(self, tau, smagorinsky_constant=0.17, force=None):
+        if force is not None:
+            raise NotImplementedError("forcing (Guo / ShanChen) is outside the B200 hot path (SURVEY.md 8f)")
+        self.force = None
+        self.tau = tau
+        self.iterations = 2
+        self.constant = smagorinsky_constant

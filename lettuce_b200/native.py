@@ -25,7 +25,7 @@ LBM_MAX_OPS = 8
 # enums of include/lbm_b200.h
 D2Q9, D3Q19, D3Q27 = 0, 1, 2
 F32, F64 = 0, 1
-OP_NO_COLLISION, OP_BGK, OP_TRT, OP_KBC = 0, 1, 2, 3
+OP_NO_COLLISION, OP_BGK, OP_TRT, OP_KBC, OP_REGULARIZED, OP_SMAGORINSKY = 0, 1, 2, 3, 4, 5
 OP_BOUNCE_BACK, OP_EQUILIBRIUM, OP_OUTLET_P, OP_ANTI_BOUNCE_BACK = 16, 17, 18, 19
 SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED, ENSTROPHY = range(6)
 
@@ -141,7 +141,8 @@ def launch_count() -> int:
 # --------------------------------------------------------------------------
 _STENCIL_IDS = {"D2Q9": D2Q9, "D3Q19": D3Q19, "D3Q27": D3Q27}
 _KIND_BY_NAME = {"NoCollision": OP_NO_COLLISION, "BGKCollision": OP_BGK, "TRTCollision": OP_TRT,
-                 "KBCCollision": OP_KBC, "BounceBackBoundary": OP_BOUNCE_BACK,
+                 "KBCCollision": OP_KBC, "RegularizedCollision": OP_REGULARIZED,
+                 "SmagorinskyCollision": OP_SMAGORINSKY, "BounceBackBoundary": OP_BOUNCE_BACK,
                  "EquilibriumBoundaryPU": OP_EQUILIBRIUM, "EquilibriumOutletP": OP_OUTLET_P,
                  "AntiBounceBackOutlet": OP_ANTI_BOUNCE_BACK}
 
@@ -240,11 +241,15 @@ class Engine:
         flow, units = self.flow, self.flow.units
         if kind == OP_BGK and getattr(op, "force", None) is not None:
             raise NotImplementedError("BGKCollision with a force term has no B200 kernel")
+        if kind in (OP_BGK, OP_SMAGORINSKY) and getattr(op, "force", None) is not None:
+            raise NotImplementedError("collisions with a force term have no B200 kernel")
         if kind == OP_KBC:
             # the reference replaces tau by the flow's relaxation parameter on first call
             # (lettuce/ext/_collision/kbc_collision.py:97-99); mirror that state change
             op.tau = units.relaxation_parameter_lu
             op.beta = 1.0 / (2 * op.tau)
+        if kind == OP_REGULARIZED:
+            op.tau = units.relaxation_parameter_lu      # regularized_collision.py:19, same quirk
         if kind == OP_EQUILIBRIUM:
             rho = units.convert_pressure_pu_to_density_lu(op.pressure)
             u = units.convert_velocity_to_lu(op.velocity)
@@ -278,8 +283,10 @@ class Engine:
                 o.p0 = float(op.tau)
             elif o.kind == OP_TRT:
                 o.p0, o.p1 = float(op.tau_plus), float(op.tau_minus)
-            elif o.kind == OP_KBC:
+            elif o.kind in (OP_KBC, OP_REGULARIZED):
                 o.p0 = float(op.tau)
+            elif o.kind == OP_SMAGORINSKY:
+                o.p0, o.p1 = float(op.tau), float(op.constant)
 
     def _pack_masks(self):
         sim = self.simulation

@@ -243,7 +243,43 @@ def collide_kbc(st, f, tau, **_):
     return f - beta * (2.0 * ds + gamma * dh)
 
 
-COLLISIONS = {"none": collide_none, "bgk": collide_bgk, "trt": collide_trt, "kbc": collide_kbc}
+def _second_moments(st, g):
+    """Pi_ab = sum_q g_q e_qa e_qb (Flow.shear_tensor, lettuce/_flow.py:230-237)"""
+    e = st["e"].astype(g.dtype)
+    return np.einsum("q...,qa,qb->ab...", g, e, e)
+
+
+def collide_regularized(st, f, tau, **_):
+    """Regularized LBM of Latt & Chopard (lettuce/ext/_collision/regularized_collision.py:17-43):
+    f = feq + (1 - 1/tau) w_q Q_q:Pi_neq / (2 cs^4).  `tau` must be units.relaxation_parameter_lu
+    (the reference overwrites the constructor argument with it, regularized_collision.py:19)."""
+    d = st["d"]
+    feq = equilibrium(st, rho(f), u(st, f))
+    pi = _second_moments(st, f - feq)
+    e = st["e"].astype(f.dtype)
+    Q = np.einsum("qa,qb->qab", e, e) - np.eye(d, dtype=f.dtype) * CS2
+    w = st["w"].astype(f.dtype).reshape((-1,) + (1,) * d)
+    fi1 = w * np.einsum("qab,ab...->q...", Q, pi) / (2 * CS2 ** 2)
+    return feq + (1.0 - 1.0 / tau) * fi1
+
+
+def collide_smagorinsky(st, f, tau, constant=0.17, **_):
+    """Smagorinsky LES on top of BGK (lettuce/ext/_collision/smagorinsky_collision.py:22-40), no force:
+    two fixed-point iterations for the effective relaxation time, then BGK with it."""
+    r = rho(f)
+    feq = equilibrium(st, r, u(st, f))
+    s_shear = _second_moments(st, f - feq) / (2.0 * r * CS2)
+    tau_eff = tau
+    nu = (tau - 0.5) / 3.0
+    for _ in range(2):
+        s = s_shear / tau_eff
+        ss = (s * s).sum(axis=(0, 1))
+        tau_eff = (nu + constant ** 2 * ss) * 3.0 + 0.5
+    return f - 1.0 / tau_eff * (f - feq)
+
+
+COLLISIONS = {"none": collide_none, "bgk": collide_bgk, "trt": collide_trt, "kbc": collide_kbc,
+              "regularized": collide_regularized, "smagorinsky": collide_smagorinsky}
 
 
 # --------------------------------------------------------------------------

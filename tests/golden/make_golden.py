@@ -56,7 +56,9 @@ def save(name, **arrays):
 def make_collision(kind, flow, tau_minus=1.0):
     tau = flow.units.relaxation_parameter_lu
     return {"bgk": lambda: lt.BGKCollision(tau), "trt": lambda: lt.TRTCollision(tau, tau_minus),
-            "kbc": lambda: lt.KBCCollision(), "none": lambda: lt.NoCollision()}[kind]()
+            "kbc": lambda: lt.KBCCollision(), "none": lambda: lt.NoCollision(),
+            "regularized": lambda: lt.RegularizedCollision(),
+            "smagorinsky": lambda: lt.SmagorinskyCollision(tau, 0.17)}[kind]()
 
 
 # ---------------------------------------------------------------- TGV cases
@@ -161,7 +163,7 @@ def random_collision_case():
         f0 = w * (1.0 + 0.2 * (rng.random((flow.stencil.q, *res)) - 0.5))
         out[f"{stencil}_f0"] = f0
         out[f"{stencil}_tau"] = np.float64(flow.units.relaxation_parameter_lu)
-        for coll in ("bgk", "trt", "kbc"):
+        for coll in ("bgk", "trt", "kbc", "regularized", "smagorinsky"):
             if coll == "kbc" and stencil == "D3Q19":
                 continue
             flow.f = ctx.convert_to_tensor(f0)
@@ -256,6 +258,12 @@ if __name__ == "__main__":
     tgv_case("tgv3d_d3q19_trt", "D3Q19", [8, 8, 12], 400.0, 0.05, "trt", 6, ["POST_STREAMING"])
     tgv_case("tgv3d_d3q19_bgk_fp32", "D3Q19", [12, 12, 12], 1600.0, 0.05, "bgk", 10, ["POST_STREAMING"],
              dtype=torch.float32)
+    tgv_case("tgv3d_d3q19_regularized", "D3Q19", [10, 8, 12], 1600.0, 0.05, "regularized", 8,
+             ["POST_STREAMING", "PRE_STREAMING"])
+    tgv_case("tgv3d_d3q27_smagorinsky", "D3Q27", [8, 10, 12], 1600.0, 0.05, "smagorinsky", 8,
+             ["POST_STREAMING", "PRE_STREAMING"])
+    tgv_case("tgv2d_d2q9_smagorinsky", "D2Q9", [20, 16], 3000.0, 0.1, "smagorinsky", 8, ["POST_STREAMING"])
+    tgv_case("tgv2d_d2q9_regularized", "D2Q9", [20, 16], 3000.0, 0.1, "regularized", 8, ["POST_STREAMING"])
     obstacle_case("cylinder_d2q9_bgk", ObstacleEqOut, "D2Q9", [64, 16], "bgk", 30, all4)
     obstacle_case("sphere_d3q27_trt", ObstacleEqOut, "D3Q27", [32, 16, 16], "trt", 10,
                   ["POST_STREAMING", "PRE_STREAMING"])

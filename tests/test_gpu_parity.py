@@ -30,7 +30,9 @@ def cuda_ctx(dtype):
 def make_collision(kind, flow, tau_minus=1.0):
     tau = flow.units.relaxation_parameter_lu
     return {"bgk": lambda: lt.BGKCollision(tau), "trt": lambda: lt.TRTCollision(tau, tau_minus),
-            "kbc": lambda: lt.KBCCollision(), "none": lambda: lt.NoCollision()}[kind]()
+            "kbc": lambda: lt.KBCCollision(), "none": lambda: lt.NoCollision(),
+            "regularized": lambda: lt.RegularizedCollision(),
+            "smagorinsky": lambda: lt.SmagorinskyCollision(tau, 0.17)}[kind]()
 
 
 def set_f(flow, f0):
@@ -43,7 +45,8 @@ def get_f(flow):
 
 # ------------------------------------------------------------------ TGV golden vectors
 TGV = ["tgv2d_d2q9_bgk", "tgv3d_d3q19_bgk", "tgv3d_d3q27_kbc", "tgv2d_d2q9_kbc", "tgv3d_d3q27_trt",
-       "tgv3d_d3q19_trt"]
+       "tgv3d_d3q19_trt", "tgv3d_d3q19_regularized", "tgv3d_d3q27_smagorinsky", "tgv2d_d2q9_smagorinsky",
+       "tgv2d_d2q9_regularized"]
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -162,7 +165,7 @@ def test_single_collision_on_random_populations(dtype):
     g = load_golden("random_collisions")
     ctx = cuda_ctx(dtype)
     for stencil, res in (("D2Q9", [6, 5]), ("D3Q19", [4, 5, 6]), ("D3Q27", [4, 5, 6])):
-        for coll in ("bgk", "trt", "kbc"):
+        for coll in ("bgk", "trt", "kbc", "regularized", "smagorinsky"):
             if coll == "kbc" and stencil == "D3Q19":
                 continue
             flow = RandomFlow(ctx, res, 50.0, 0.1, stencil=STENCILS[stencil]())
@@ -280,7 +283,8 @@ def test_equilibrium_boundary_broadcast_shapes():
 
 
 # ------------------------------------------------------------------ live oracle at larger sizes, all strategies
-CASES = [("D2Q9", [48, 40], "bgk", 1.0), ("D2Q9", [48, 40], "kbc", 800.0), ("D2Q9", [33, 47], "trt", 100.0),
+CASES = [("D3Q19", [20, 12, 28], "regularized", 1600.0), ("D3Q27", [12, 20, 24], "smagorinsky", 1600.0),
+         ("D2Q9", [48, 40], "bgk", 1.0), ("D2Q9", [48, 40], "kbc", 800.0), ("D2Q9", [33, 47], "trt", 100.0),
          ("D3Q19", [24, 20, 36], "bgk", 1600.0), ("D3Q19", [17, 19, 23], "trt", 400.0),
          ("D3Q27", [20, 24, 28], "kbc", 1600.0), ("D3Q27", [16, 16, 40], "bgk", 1600.0)]
 
@@ -301,6 +305,8 @@ def test_tgv_matches_live_oracle(stencil, res, coll, re, strategy, dtype):
     sim = lt.Simulation(flow, make_collision(coll, flow), [], STRATS[strategy])
     sim(steps)
     cdesc = dict(kind=coll, tau=flow.units.relaxation_parameter_lu)
+    if coll == "smagorinsky":
+        cdesc["constant"] = 0.17
     ref = lo.run(st, f0, steps, cdesc, strategy=strategy)
     err = max_rel(get_f(flow), ref)
     tol = TOL[dtype]

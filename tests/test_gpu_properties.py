@@ -12,7 +12,7 @@ lt = pytest.importorskip("lettuce_b200")
 from oracle import lbm_oracle as lo  # noqa: E402
 
 STENCILS = {"D2Q9": lt.D2Q9, "D3Q19": lt.D3Q19, "D3Q27": lt.D3Q27}
-COLLISIONS = ["bgk", "trt", "kbc"]
+COLLISIONS = ["bgk", "trt", "kbc", "regularized", "smagorinsky"]
 
 
 def ctx(dtype=torch.float64):
@@ -51,6 +51,7 @@ def random_flow(stencil, res, dtype=torch.float64, seed=1, amplitude=0.2, cls=Te
 
 def collide_once(flow, coll, tau):
     c = {"bgk": lambda: lt.BGKCollision(tau), "trt": lambda: lt.TRTCollision(tau), "kbc": lambda: lt.KBCCollision(),
+         "regularized": lambda: lt.RegularizedCollision(), "smagorinsky": lambda: lt.SmagorinskyCollision(tau),
          "none": lambda: lt.NoCollision()}[coll]()
     lt.Simulation(flow, c, [], lt.StreamingStrategy.NO_STREAMING)(1)
     return flow.f.cpu().numpy()
@@ -63,7 +64,7 @@ def test_collision_conserves_mass_and_momentum(stencil, coll):
     if coll == "kbc" and stencil == "D3Q19":
         pytest.skip("KBC exists for D2Q9 and D3Q27 only")
     flow, st, f0 = random_flow(stencil, [7] * STENCILS[stencil]().d)
-    f1 = collide_once(flow, coll, 0.6 if coll != "kbc" else flow.units.relaxation_parameter_lu)
+    f1 = collide_once(flow, coll, 0.6 if coll not in ("kbc", "regularized") else flow.units.relaxation_parameter_lu)
     assert np.max(np.abs(lo.rho(f1) - lo.rho(f0))) < 1e-14
     assert np.max(np.abs(lo.j(st, f1) - lo.j(st, f0))) < 1e-14
     assert np.max(np.abs(f1 - f0)) > 1e-6          # the operator did act
@@ -76,8 +77,10 @@ def test_collision_relaxes_shear_moments(stencil, coll):
     moment relaxes towards its equilibrium value at rate 1/tau (BGK, TRT's even part, KBC's shear part)"""
     if coll == "kbc" and stencil == "D3Q19":
         pytest.skip("KBC exists for D2Q9 and D3Q27 only")
+    if coll == "smagorinsky":
+        pytest.skip("relaxes with the local effective tau, not the prescribed one")
     flow, st, f0 = random_flow(stencil, [6] * STENCILS[stencil]().d)
-    tau = 0.6 if coll != "kbc" else flow.units.relaxation_parameter_lu
+    tau = 0.6 if coll not in ("kbc", "regularized") else flow.units.relaxation_parameter_lu
     f1 = collide_once(flow, coll, tau)
     e = st["e"].astype(float)
     shear = lambda f: np.einsum("q...,qa,qb->ab...", f, e, e)

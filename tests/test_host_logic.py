@@ -155,11 +155,13 @@ def test_no_cpu_path():
 
 
 def test_unsupported_operators_raise():
-    class Smagorinsky(lt.Collision):
+    class MRTCollision(lt.Collision):
         pass
 
     with pytest.raises(NotImplementedError):
-        native.op_kind(Smagorinsky())
+        native.op_kind(MRTCollision())
+    with pytest.raises(NotImplementedError):
+        lt.SmagorinskyCollision(0.6, force=object())
     with pytest.raises(NotImplementedError):
         lt.BGKCollision(0.6, force=object())
     assert native.op_kind(lt.KBCCollision()) == native.OP_KBC
@@ -168,7 +170,7 @@ def test_unsupported_operators_raise():
         pass
 
     assert native.op_kind(MyBB(None)) == native.OP_BOUNCE_BACK
-    assert MyBB(None).native_available() and not Smagorinsky().native_available()
+    assert MyBB(None).native_available() and not MRTCollision().native_available()
 
 
 def test_streaming_strategy_bits():
