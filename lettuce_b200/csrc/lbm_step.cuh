@@ -272,7 +272,10 @@ template <class S, class R, int COLL>
 constexpr int min_blocks_per_sm() {
     // fp32 KBC on D3Q27: cap at 85 registers (3 CTAs of 256 threads); the push variant otherwise
     // hoists 27 store addresses into 108 registers.
-    return (sizeof(R) == 4 && COLL == LBM_OP_KBC && S::Q == 27) ? 3 : 0;  // 0 = no constraint
+#ifndef LBM_KBC_MIN_BLOCKS
+#define LBM_KBC_MIN_BLOCKS 3
+#endif
+    return (sizeof(R) == 4 && COLL == LBM_OP_KBC && S::Q == 27) ? LBM_KBC_MIN_BLOCKS : 0;  // 0 = no constraint
 }
 
 // one node: gather, collide, scatter.  Addresses are split into a block-uniform part (plane pointer +

@@ -19,7 +19,7 @@ from typing import List, Optional
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "liblbm_b200.so")
+LIB_PATH = os.environ.get("LBM_B200_LIB", os.path.join(_PKG, "liblbm_b200.so"))   # override for A/B experiments
 
 LBM_MAX_OPS = 8
 # enums of include/lbm_b200.h
