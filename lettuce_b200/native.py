@@ -205,12 +205,15 @@ class Engine:
     """Everything `invoke` needs for one Simulation: the packed descriptor, the
     label / frozen-slot fields and the boundary parameter tensors it borrows."""
 
-    def __init__(self, simulation):
+    def __init__(self, simulation, dry: bool = False):
+        """`dry=True` only translates the simulation into the descriptor (no CUDA tensors required, no
+        mask packing): used to check the duck-typed translation against the reference's own classes."""
         self.lib = lib()
         flow = simulation.flow
         self.flow = flow
         self.simulation = simulation
-        _require_cuda(flow.f, "flow.f")
+        if not dry:
+            _require_cuda(flow.f, "flow.f")
         self.device = flow.f.device
         self.lat = lattice_of(flow.stencil, flow.f.shape[1:], flow.f.dtype)
         transformer = list(simulation.transformer)
@@ -229,6 +232,9 @@ class Engine:
         self.refresh_parameters()
         self.labels: Optional[torch.Tensor] = None
         self.frozen: Optional[torch.Tensor] = None
+        if dry:
+            self.variant_name = "dry"
+            return
         if len(transformer) > 1:
             self._pack_masks()
         self.variant_name = self.lib.lbm_step_variant_name(C.byref(self.desc)).decode()
@@ -344,6 +350,20 @@ class Engine:
                 check(self.lib.lbm_step_n(C.byref(self.desc), f.data_ptr(), g.data_ptr(), n, stream), "lbm_step_n")
         if n % 2 == 1:
             flow.f, flow.f_next = g, f
+
+
+def describe(simulation):
+    """The transformer list of `simulation` as the engine would see it: a list of dicts with the native op
+    kind and its parameters.  Works on CPU simulations and on the reference's own `lettuce.Simulation`."""
+    eng = Engine(simulation, dry=True)
+    out = []
+    for i in range(eng.desc.n_ops):
+        o = eng.desc.ops[i]
+        out.append(dict(kind=int(o.kind), axis=int(o.axis), side=int(o.side), p0=float(o.p0), p1=float(o.p1),
+                        rho_stride=list(o.rho_stride), u_stride=list(o.u_stride)))
+    return dict(stencil=int(eng.desc.lat.stencil), dtype=int(eng.desc.lat.dtype),
+                resolution=[int(eng.desc.lat.nx), int(eng.desc.lat.ny), int(eng.desc.lat.nz)],
+                streaming=int(eng.desc.streaming), collision_index=int(eng.desc.collision_index), ops=out)
 
 
 def engine_of(simulation) -> Engine:
