@@ -16,7 +16,7 @@ from .. import native
 from .._simulation import Reporter
 
 __all__ = ["Observable", "ObservableReporter", "MaximumVelocity", "IncompressibleKineticEnergy",
-           "Enstrophy", "Mass"]
+           "Enstrophy", "Mass", "FailureReporterBase", "NaNReporter", "HighMaReporter"]
 
 
 class Observable(ABC):
@@ -101,3 +101,82 @@ class ObservableReporter(Reporter):
             self.out.append(entry)
         else:
             print(*entry, file=self.out)
+
+
+class FailureReporterBase(Reporter):
+    """Detects a failing simulation every `interval` steps and aborts a `BreakableSimulation` by pushing
+    `flow.i` past any step target (lettuce/ext/_reporter/failure_reporter.py:12-56).  The test itself is one
+    reduction on the engine; the list of the `k` worst locations is only assembled after a failure.  A log
+    file is written when `outdir` is given (VTK output is outside the hot path)."""
+    batchable = True
+    name = "Failure"
+
+    def __init__(self, interval: int, k: int = 100, outdir: Optional[str] = None):
+        super().__init__(interval)
+        self.k = k
+        self.outdir = outdir
+        self.failed_iteration = None
+        self.results = None
+
+    def __call__(self, simulation):
+        if simulation.flow.i % self.interval != 0 or not self.is_failed(simulation):
+            return
+        self.results = self.get_results(simulation)
+        self.failed_iteration = simulation.flow.i
+        if self.outdir is not None:
+            import os
+            os.makedirs(self.outdir, exist_ok=True)
+            with open(os.path.join(self.outdir, f"{self.name}_reporter.log"), "w") as fh:
+                fh.write(f"{self.name} detected at iteration {simulation.flow.i}\n")
+                for pos, val in self.results:
+                    fh.write(f"{pos} {val}\n")
+        print(f"(!) ABORT MESSAGE: {self.name}Reporter detected {self.name} (reporter-interval = {self.interval}) "
+              f"at iteration {simulation.flow.i}.")
+        simulation.flow.i = int(simulation.flow.i + 1e10)
+
+    def _top(self, mask: torch.Tensor, values: torch.Tensor):
+        bad = values[mask]
+        coords = torch.nonzero(mask)
+        n = min(self.k, bad.numel())
+        idx = torch.arange(n, device=values.device) if torch.isnan(bad).any() else torch.topk(bad, k=n).indices
+        return [(list(map(int, c)), float(v)) for c, v in zip(coords[idx].cpu().numpy(), bad[idx].cpu().numpy())]
+
+    @abstractmethod
+    def is_failed(self, simulation) -> bool:
+        ...
+
+    @abstractmethod
+    def get_results(self, simulation):
+        ...
+
+
+class NaNReporter(FailureReporterBase):
+    """aborts when any population is NaN (failure_reporter.py:131-153).  NaN propagates through the sum of
+    all populations, so the test is the engine's SUM_F reduction."""
+    name = "NaN"
+
+    def is_failed(self, simulation) -> bool:
+        total = native.reduce(simulation.flow.stencil, native.SUM_F, simulation.flow.f)
+        return bool(torch.isnan(total).cpu())
+
+    def get_results(self, simulation):
+        return self._top(torch.isnan(simulation.flow.f), simulation.flow.f)
+
+
+class HighMaReporter(FailureReporterBase):
+    """aborts when the local Mach number |u|/cs exceeds `threshold` anywhere (failure_reporter.py:156-184)"""
+    name = "HighMa"
+
+    def __init__(self, interval: int, threshold: float = 0.3, k: int = 100, outdir: Optional[str] = None):
+        super().__init__(interval, k, outdir)
+        self.threshold = threshold
+
+    def is_failed(self, simulation) -> bool:
+        flow = simulation.flow
+        umax = native.reduce(flow.stencil, native.MAX_U, flow.f)
+        return bool((umax / flow.stencil.cs > self.threshold).cpu()) or bool(torch.isnan(umax).cpu())
+
+    def get_results(self, simulation):
+        flow = simulation.flow
+        ma = torch.norm(flow.u(), dim=0) / flow.stencil.cs
+        return self._top(ma > self.threshold, ma)

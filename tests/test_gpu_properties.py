@@ -216,3 +216,33 @@ def test_checkpoint_round_trip(tmp_path):
     assert torch.equal(flow.f, saved)
     sim(1)                                  # f_next is re-allocated lazily after load
     assert torch.isfinite(flow.f).all()
+
+
+def test_high_ma_reporter_aborts_at_the_reference_iteration(tmp_path):
+    """tests/reporter/test_high_ma_reporter.py:5-17: the stock obstacle at Ma 0.2 exceeds Ma 0.3 locally at
+    iteration 13 (same iteration on the reference's torch path in fp32 and fp64)"""
+    for dtype in (torch.float32, torch.float64):
+        c = ctx(dtype)
+        flow = lt.Obstacle(context=c, resolution=[16, 16], reynolds_number=10, mach_number=0.2, domain_length_x=16,
+                           stencil=lt.D2Q9())
+        g = flow.grid
+        flow.mask = ((2 < g[0]) & (g[0] < 10) & (2 < g[1]) & (g[1] < 10))
+        reporter = lt.HighMaReporter(1, outdir=str(tmp_path))
+        sim = lt.BreakableSimulation(flow, lt.BGKCollision(tau=flow.units.relaxation_parameter_lu), [reporter])
+        sim(100)
+        assert flow.i > 100 and reporter.failed_iteration == 13
+        assert (tmp_path / "HighMa_reporter.log").is_file() and len(reporter.results) > 0
+
+
+def test_nan_reporter_aborts(tmp_path):
+    """tests/reporter/test_nan_reporter.py: a NaN planted in the populations stops a BreakableSimulation"""
+    c = ctx(torch.float32)
+    flow = lt.TaylorGreenVortex(c, [16, 16], 10.0, 0.05, stencil=lt.D2Q9())
+    reporter = lt.NaNReporter(2, outdir=str(tmp_path))
+    sim = lt.BreakableSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [reporter])
+    sim(4)
+    assert reporter.failed_iteration is None and flow.i == 4
+    flow.f[3, 5, 7] = float("nan")
+    sim(50)
+    assert reporter.failed_iteration == 4 and flow.i > 50
+    assert reporter.results[0][0] == [3, 5, 7]
