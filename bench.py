@@ -222,6 +222,7 @@ def gpu_main(args):
     mlups = args.steps * nodes_total / 1e6 / (ms * 1e-3)
     assert torch.isfinite(flow.f).all()
 
+    kernel_name = native.engine_of(sim).variant_name if world == 1 else "step_sync (slab, in-kernel lock step)"
     # ---- e2e: HOST populations in, HOST populations out, every step's kinetic energy read back
     e2e = None
     f_host = torch.empty(flow.f.shape, dtype=torch.float32).pin_memory()
@@ -268,6 +269,11 @@ def gpu_main(args):
            "h2d_bytes_per_step": fbytes * world / args.steps, "d2h_bytes_per_step": fbytes * world / args.steps + 8,
            "note": how + "; transfers amortised over K steps"}
 
+    if world > 1:
+        # orderly teardown on every rank: unmap the neighbours' buffers, then leave the process group together
+        sim.close()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_hbm_peak()
@@ -281,14 +287,12 @@ def gpu_main(args):
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((n, args.strategy)),
                          "traffic_unit": "bytes per launch (ncu, profiles/r1_step_d3q19_bgk_*_256.csv)",
                          "algorithmic_bytes_per_launch": nodes_local * BYTES_PER_NODE, "peak_source": peak_src,
-                         "kernel": native.engine_of(sim).variant_name if world == 1 else "slab",
+                         "kernel": kernel_name,
                          "bytes_per_node": BYTES_PER_NODE},
             "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_arm(steps=3, warmup=1, budget_s=20.0)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
