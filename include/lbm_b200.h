@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LBM_ABI_VERSION 1
+#define LBM_ABI_VERSION 2
 #define LBM_MAX_OPS 8 /* transformer list length: pre_boundaries + collision + post_boundaries */
 
 typedef enum lbm_status {
@@ -72,6 +72,9 @@ typedef enum lbm_op_kind {
     LBM_OP_KBC = 3,          /* ext/_collision/kbc_collision.py:96-160; p0 = tau (units.relaxation_parameter_lu) */
     LBM_OP_REGULARIZED = 4,  /* ext/_collision/regularized_collision.py:17-43; p0 = tau (units.relaxation_parameter_lu) */
     LBM_OP_SMAGORINSKY = 5,  /* ext/_collision/smagorinsky_collision.py:22-40 (force = None); p0 = tau, p1 = constant */
+    LBM_OP_BGK_FORCED = 6,   /* BGK with a body force (bgk_collision.py:17-22 with ext/_force/guo.py or shan_chen.py):
+                                p0 = tau, force[] = acceleration in lattice units, ueq_scale = 0.5 (Guo) or tau
+                                (ShanChen), source_scale = 1 - 1/(2 tau_force) (Guo) or 0 (ShanChen) */
     LBM_OP_BOUNCE_BACK = 16, /* ext/_boundary/bounce_back_boundary.py:10-32 */
     LBM_OP_EQUILIBRIUM = 17, /* ext/_boundary/equilibrium_boundary_pu.py:79-84, values already in lattice units */
     LBM_OP_OUTLET_P = 18,    /* ext/_boundary/equilibrium_outlet_p.py:63-73; p0 = rho_outlet */
@@ -95,6 +98,10 @@ typedef struct lbm_op {
     const void *u;
     int64_t rho_stride[3];
     int64_t u_stride[4]; /* component, x, y, z */
+    /* LBM_OP_BGK_FORCED: u_eq = u + ueq_scale * force / rho enters the equilibrium, and the source term
+     * source_scale * w_q [ (e_q - u_eq)/cs^2 + (e_q.u_eq) e_q/cs^4 ] . force is added after relaxation */
+    double force[3];
+    double ueq_scale, source_scale;
 } lbm_op;
 
 /* Geometry of the slab of lattice this call works on. */

@@ -149,9 +149,15 @@ class Flow(ABC):
 
     def u(self, f: Optional[torch.Tensor] = None, rho=None, acceleration=None) -> torch.Tensor:
         """velocity [d, *res] (lettuce/_flow.py:178-193)"""
-        if acceleration is not None:
-            raise NotImplementedError("force-corrected velocity: forcing is outside the B200 hot path")
-        return native.moments(self.stencil, self.f if f is None else f, want_rho=False)[1]
+        if acceleration is None:
+            return native.moments(self.stencil, self.f if f is None else f, want_rho=False)[1]
+        # with a forcing scheme the physical velocity averages pre- and post-collision momentum
+        rho_, v = native.moments(self.stencil, self.f if f is None else f)
+        rho_ = rho_ if rho is None else rho
+        acceleration = self.context.convert_to_tensor(acceleration)
+        if acceleration.dim() == 1:
+            acceleration = acceleration.reshape([-1] + [1] * self.stencil.d)
+        return v + acceleration / (2 * rho_)
 
     def j(self, f: Optional[torch.Tensor] = None) -> torch.Tensor:
         """momentum [d, *res] (lettuce/_flow.py:173-176)"""

@@ -3,7 +3,7 @@
 No per-configuration JIT (the reference generates and compiles one extension per
 (stencil, strategy, operator list), lettuce/cuda_native/_generator.py:99-127):
 every (stencil, dtype, collision, streaming, masked) variant is template-instantiated
-once and selected at run time from the descriptor.  The 34 (stencil, dtype, collision)
+once and selected at run time from the descriptor.  The 40 (stencil, dtype, collision)
 triples are separate translation units and compile in parallel.
 
     python -m lettuce_b200.build [--force] [--verbose]
@@ -35,7 +35,8 @@ def _units():
              ("lbm_moments", os.path.join(CSRC, "lbm_moments.cu"), []),
              ("lbm_slab", os.path.join(CSRC, "lbm_slab.cu"), [])]
     # heaviest units first so the pool's tail is short
-    for c, cname in ((3, "kbc"), (5, "smagorinsky"), (4, "regularized"), (2, "trt"), (1, "bgk"), (0, "none")):
+    for c, cname in ((3, "kbc"), (5, "smagorinsky"), (4, "regularized"), (6, "bgk_forced"), (2, "trt"), (1, "bgk"),
+                     (0, "none")):
         for s in reversed(STENCILS):
             if cname == "kbc" and s == "D3Q19":
                 continue            # KBC exists for D2Q9 and D3Q27 only

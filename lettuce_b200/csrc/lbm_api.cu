@@ -34,6 +34,7 @@ static int launch_step(const StepParams<R> &p, int coll, int streaming, bool mas
             else return launch_step_coll<S, R, LBM_OP_KBC>(p, streaming, masked, variant, stream);
         case LBM_OP_REGULARIZED: return launch_step_coll<S, R, LBM_OP_REGULARIZED>(p, streaming, masked, variant, stream);
         case LBM_OP_SMAGORINSKY: return launch_step_coll<S, R, LBM_OP_SMAGORINSKY>(p, streaming, masked, variant, stream);
+        case LBM_OP_BGK_FORCED: return launch_step_coll<S, R, LBM_OP_BGK_FORCED>(p, streaming, masked, variant, stream);
     }
     return LBM_ERR_BAD_ARGUMENT;
 }
@@ -75,7 +76,7 @@ static int lattice_dims(const lbm_lattice *lat, Dims &dm) {
     return LBM_OK;
 }
 
-static bool is_collision(int kind) { return kind >= LBM_OP_NO_COLLISION && kind <= LBM_OP_SMAGORINSKY; }
+static bool is_collision(int kind) { return kind >= LBM_OP_NO_COLLISION && kind <= LBM_OP_BGK_FORCED; }
 static bool is_outlet(int kind) { return kind == LBM_OP_OUTLET_P || kind == LBM_OP_ANTI_BOUNCE_BACK; }
 
 static int validate_desc(const lbm_step_desc *d, Dims &dm) {
@@ -146,6 +147,10 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
     p.collision_index = d->collision_index;
     const lbm_op &c = d->ops[d->collision_index];
     collision_scalars<R>(c.kind, c.p0, c.p1, p.ca, p.cb);
+    for (int a = 0; a < 3; ++a) p.force.a[a] = R(0);
+    for (int c2 = 0; c2 < S::D; ++c2) p.force.a[S::axis_of(c2)] = (R)c.force[c2];
+    p.force.ueq_scale = (R)c.ueq_scale;
+    p.force.src_scale = (R)c.source_scale;
     for (int i = 0; i < d->n_ops; ++i) {
         const lbm_op &o = d->ops[i];
         OpDev<R> &t = p.ops[i];

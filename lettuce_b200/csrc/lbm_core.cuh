@@ -425,11 +425,42 @@ struct Collide<S, R, LBM_OP_SMAGORINSKY> {
     }
 };
 
+// BGK with a body force (lettuce/ext/_collision/bgk_collision.py:17-22 with Guo, ext/_force/guo.py:16-38,
+// or ShanChen, ext/_force/shan_chen.py:13-26): the equilibrium is evaluated at u + ueq_scale a / rho and the
+// source term  src_scale w_q [ (e_q - u)/cs^2 + (e_q.u) e_q / cs^4 ] . a  is added after relaxation.
+template <class R>
+struct ForceArgs {
+    R a[3];  // acceleration, internal axes
+    R ueq_scale, src_scale;
+};
+
+template <class S, class R>
+LBM_D void collide_bgk_forced(R (&f)[S::Q], R inv_tau, const ForceArgs<R> &fa) {
+    R rho, j[3];
+    moments<S, R>(f, rho, j);
+    const R inv_rho = R(1) / rho;
+    const R k = fa.ueq_scale * inv_rho;
+    const R u[3] = {j[0] * inv_rho + k * fa.a[0], j[1] * inv_rho + k * fa.a[1], j[2] * inv_rho + k * fa.a[2]};
+    Equilibrium<S, R> eq(rho, u);
+    const R ua = u[0] * fa.a[0] + u[1] * fa.a[1] + u[2] * fa.a[2];
+    ForQ<S::Q>::run([&]<int q>() {
+        R eu = R(0), ea = R(0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (S::e(q, c) == 1) { eu += u[c]; ea += fa.a[c]; }
+            if (S::e(q, c) == -1) { eu -= u[c]; ea -= fa.a[c]; }
+        }
+        // (e - u).a / cs^2 + (e.u)(e.a) / cs^4
+        const R src = (ea - ua) * R(1.0 / kCs2) + eu * ea * R(1.0 / (kCs2 * kCs2));
+        f[q] = f[q] - inv_tau * (f[q] - eq.template get<q>()) + fa.src_scale * (R(S::w(q)) * src);
+    });
+}
+
 // parameters handed to Collide::apply for a given collision kind
 template <class R>
 LBM_HD void collision_scalars(int kind, double p0, double p1, R &a, R &b) {
     a = R(0); b = R(0);
-    if (kind == LBM_OP_BGK) a = R(1.0 / p0);
+    if (kind == LBM_OP_BGK || kind == LBM_OP_BGK_FORCED) a = R(1.0 / p0);
     if (kind == LBM_OP_TRT) { a = R(1.0 / (2.0 * p0)); b = R(1.0 / (2.0 * p1)); }
     if (kind == LBM_OP_KBC) a = R(1.0 / (2.0 * p0));
     if (kind == LBM_OP_REGULARIZED) a = R(1.0 - 1.0 / p0);

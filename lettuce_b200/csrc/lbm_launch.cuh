@@ -1,6 +1,6 @@
 // lbm_launch.cuh -- declaration of the per-(stencil, dtype, collision) step launchers.  Each
 // triple is compiled in its own translation unit (lbm_step_inst.cu with -DLBM_INST_STENCIL /
-// -DLBM_INST_REAL / -DLBM_INST_COLL) so the 34 units build in parallel.
+// -DLBM_INST_REAL / -DLBM_INST_COLL) so the 40 units build in parallel.
 #pragma once
 #include "lbm_step.cuh"
 

@@ -53,6 +53,7 @@ struct StepParams {
     int n_general;
     int n_ops, collision_index;
     R ca, cb;  // scalars of the collision entry
+    ForceArgs<R> force;  // LBM_OP_BGK_FORCED only
     SlabSync sync;
     OpDev<R> ops[LBM_MAX_OPS];
 };
@@ -90,6 +91,13 @@ LBM_D const uint8_t *label_plane(const StepParams<R> &p, int x) {
 }
 
 LBM_D int wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+// the collision entry of the transformer list applied to one node
+template <class S, class R, int COLL>
+LBM_D void collide_node(const StepParams<R> &p, R (&f)[S::Q]) {
+    if constexpr (COLL == LBM_OP_BGK_FORCED) collide_bgk_forced<S, R>(f, p.ca, p.force);
+    else Collide<S, R, COLL>::apply(f, p.ca, p.cb);
+}
 
 // ---------------------------------------------------------------------------
 // general path pieces
@@ -146,7 +154,7 @@ LBM_D void apply_local_op(const StepParams<R> &p, int i, int label, int x, int y
     if (label != i) return;
     const OpDev<R> &op = p.ops[i];
     if (i == p.collision_index) {
-        Collide<S, R, COLL>::apply(f, p.ca, p.cb);
+        collide_node<S, R, COLL>(p, f);
     } else if (op.kind == LBM_OP_BOUNCE_BACK) {
         bounce_back<S, R>(f);
     } else if (op.kind == LBM_OP_EQUILIBRIUM) {
@@ -304,7 +312,7 @@ LBM_D void node_update(const StepParams<R> &p, int x, int y, int z) {
         ForQ<Q>::run([&]<int q>() { f[q] = __ldg(src + q * p.N + (row0 + z)); });
     }
 
-    Collide<S, R, COLL>::apply(f, p.ca, p.cb);
+    collide_node<S, R, COLL>(p, f);
 
     if (PUSH) {
         const Plane<R, R> pl[3] = {out_plane(p, x - 1), out_plane(p, x), out_plane(p, x + 1)};  // index e0+1 -> x + e0
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(256) step_multi_kernel(const __grid_constant__
 
 #pragma unroll
     for (int k = 0; k < NPT; ++k)
-        if (active[k]) Collide<S, R, COLL>::apply(f[k], p.ca, p.cb);
+        if (active[k]) collide_node<S, R, COLL>(p, f[k]);
 
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {

@@ -9,7 +9,7 @@
 #error "define LBM_INST_REAL (float | double)"
 #endif
 #ifndef LBM_INST_COLL
-#error "define LBM_INST_COLL (lbm_op_kind collision value 0..5)"
+#error "define LBM_INST_COLL (lbm_op_kind collision value 0..6)"
 #endif
 
 namespace lbm {

@@ -8,7 +8,7 @@ from __future__ import annotations
 from .._simulation import Collision
 
 __all__ = ["NoCollision", "BGKCollision", "TRTCollision", "KBCCollision", "RegularizedCollision",
-           "SmagorinskyCollision"]
+           "SmagorinskyCollision", "Force", "Guo", "ShanChen"]
 
 
 class NoCollision(Collision):
@@ -20,10 +20,8 @@ class BGKCollision(Collision):
     before every launch, like the reference's generated call passes 1/tau per step."""
 
     def __init__(self, tau, force=None):
-        if force is not None:
-            raise NotImplementedError("forcing (Guo / ShanChen) is outside the B200 hot path (SURVEY.md 8f)")
         self.tau = tau
-        self.force = None
+        self.force = force          # None, Guo or ShanChen: the forced variant is its own kernel
 
 
 class TRTCollision(Collision):
@@ -59,8 +57,40 @@ class SmagorinskyCollision(Collision):
 
     def __init__(self, tau, smagorinsky_constant=0.17, force=None):
         if force is not None:
-            raise NotImplementedError("forcing (Guo / ShanChen) is outside the B200 hot path (SURVEY.md 8f)")
+            raise NotImplementedError("SmagorinskyCollision with a force term has no B200 kernel")
         self.force = None
         self.tau = tau
         self.iterations = 2
         self.constant = smagorinsky_constant
+
+
+class Force:
+    """Body force acting through BGKCollision(tau, force=...) (lettuce/ext/_force/_force.py).  Parameter
+    holder: `acceleration` in lattice units, one component per dimension."""
+
+    def __init__(self, flow, tau, acceleration):
+        self.flow = flow
+        self.tau = tau
+        self.acceleration = flow.context.convert_to_tensor(acceleration)
+
+    @property
+    def ueq_scaling_factor(self):
+        raise NotImplementedError
+
+
+class Guo(Force):
+    """Guo forcing: equilibrium velocity shifted by a/(2 rho), source term
+    (1 - 1/(2 tau)) w_q [(e_q - u)/cs^2 + (e_q.u) e_q/cs^4] . a  (lettuce/ext/_force/guo.py:9-38)"""
+
+    @property
+    def ueq_scaling_factor(self):
+        return 0.5
+
+
+class ShanChen(Force):
+    """Shan-Chen forcing: equilibrium velocity shifted by tau a / rho, no source term
+    (lettuce/ext/_force/shan_chen.py:9-26)"""
+
+    @property
+    def ueq_scaling_factor(self):
+        return self.tau * 1

@@ -14,7 +14,7 @@ from .._stencil import D2Q9, D3Q19
 from .._unit import UnitConversion
 from .boundary import AntiBounceBackOutlet, BounceBackBoundary, EquilibriumBoundaryPU
 
-__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle"]
+__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D"]
 
 
 class ExtFlow(Flow):
@@ -157,3 +157,57 @@ class Obstacle(ExtFlow):
 
     def _unit_vector(self, i=0):
         return torch.eye(self.stencil.d)[i]
+
+
+class PoiseuilleFlow2D(ExtFlow):
+    """Force-driven channel flow between two bounce-back walls (rows y = 0 and y = ny-1), periodic in x
+    (lettuce/ext/_flows/poiseuille.py:18-97).  `acceleration` (physical units) drives it through a forcing
+    scheme: BGKCollision(tau, force=Guo(flow, tau, flow.units.convert_acceleration_to_lu(flow.acceleration)))."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None,
+                 initialize_with_zeros=True):
+        self.stencil = D2Q9() if stencil is None else (stencil() if callable(stencil) else stencil)
+        self.initialize_with_zeros = initialize_with_zeros
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, self.stencil, equilibrium)
+
+    def make_resolution(self, resolution, stencil=None):
+        if isinstance(resolution, int):
+            return [resolution] * self.stencil.d
+        assert len(resolution) == self.stencil.d
+        return list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution):
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0] - 1, characteristic_length_pu=1,
+                              characteristic_velocity_pu=1)
+
+    @property
+    def grid(self):
+        axes = [torch.linspace(0, 1, steps=n, device=self.context.device, dtype=self.context.dtype)
+                for n in self.resolution]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    @property
+    def acceleration(self):
+        return self.context.convert_to_tensor([0.001, 0])
+
+    def analytic_solution(self, t=0):
+        """parabolic profile with the walls half a lattice spacing inside the boundary rows"""
+        h = 0.5 / self.resolution[0]
+        x, y = self.grid
+        ux = self.acceleration[0] / (2 * 1 * self.units.viscosity_pu) * ((y - h) * (1 - h - y))
+        u = torch.stack([ux, torch.zeros_like(ux)], dim=0)
+        p = y * 0 + self.units.convert_density_lu_to_pressure_pu(1)
+        return p, u
+
+    def initial_pu(self):
+        if not self.initialize_with_zeros:
+            return self.analytic_solution()
+        zeros = self.context.zero_tensor(self.resolution)
+        return zeros[None, ...], torch.stack([zeros, zeros], dim=0)
+
+    @property
+    def post_boundaries(self):
+        mask = self.context.zero_tensor(self.resolution, dtype=torch.bool)
+        mask[:, [0, -1]] = True
+        return [BounceBackBoundary(mask=mask)]

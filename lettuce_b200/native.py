@@ -25,7 +25,7 @@ LBM_MAX_OPS = 8
 # enums of include/lbm_b200.h
 D2Q9, D3Q19, D3Q27 = 0, 1, 2
 F32, F64 = 0, 1
-OP_NO_COLLISION, OP_BGK, OP_TRT, OP_KBC, OP_REGULARIZED, OP_SMAGORINSKY = 0, 1, 2, 3, 4, 5
+OP_NO_COLLISION, OP_BGK, OP_TRT, OP_KBC, OP_REGULARIZED, OP_SMAGORINSKY, OP_BGK_FORCED = 0, 1, 2, 3, 4, 5, 6
 OP_BOUNCE_BACK, OP_EQUILIBRIUM, OP_OUTLET_P, OP_ANTI_BOUNCE_BACK = 16, 17, 18, 19
 SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED, ENSTROPHY = range(6)
 
@@ -34,7 +34,8 @@ class LbmOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("axis", C.c_int32), ("side", C.c_int32), ("_pad", C.c_int32),
                 ("p0", C.c_double), ("p1", C.c_double),
                 ("rho", C.c_void_p), ("u", C.c_void_p),
-                ("rho_stride", C.c_int64 * 3), ("u_stride", C.c_int64 * 4)]
+                ("rho_stride", C.c_int64 * 3), ("u_stride", C.c_int64 * 4),
+                ("force", C.c_double * 3), ("ueq_scale", C.c_double), ("source_scale", C.c_double)]
 
 
 class LbmLattice(C.Structure):
@@ -147,11 +148,25 @@ _KIND_BY_NAME = {"NoCollision": OP_NO_COLLISION, "BGKCollision": OP_BGK, "TRTCol
                  "AntiBounceBackOutlet": OP_ANTI_BOUNCE_BACK}
 
 
+_FORCES = ("Guo", "ShanChen")
+
+
+def force_kind(force) -> str:
+    for cls in type(force).__mro__:
+        if cls.__name__ in _FORCES:
+            return cls.__name__
+    raise NotImplementedError(f"force {type(force).__name__} has no B200 kernel (supported: {_FORCES})")
+
+
 def op_kind(op) -> int:
     """Native kind of a collision / boundary object; most-derived class name wins."""
     for cls in type(op).__mro__:
         if cls.__name__ in _KIND_BY_NAME:
-            return _KIND_BY_NAME[cls.__name__]
+            kind = _KIND_BY_NAME[cls.__name__]
+            if kind == OP_BGK and getattr(op, "force", None) is not None:
+                force_kind(op.force)
+                return OP_BGK_FORCED
+            return kind
     raise NotImplementedError(
         f"{type(op).__name__} has no B200 kernel (supported: {sorted(_KIND_BY_NAME)}); "
         f"lettuce_b200 does not fall back to torch")
@@ -245,10 +260,8 @@ class Engine:
         kind = op_kind(op)
         o.kind = kind
         flow, units = self.flow, self.flow.units
-        if kind == OP_BGK and getattr(op, "force", None) is not None:
-            raise NotImplementedError("BGKCollision with a force term has no B200 kernel")
-        if kind in (OP_BGK, OP_SMAGORINSKY) and getattr(op, "force", None) is not None:
-            raise NotImplementedError("collisions with a force term have no B200 kernel")
+        if kind == OP_SMAGORINSKY and getattr(op, "force", None) is not None:
+            raise NotImplementedError("SmagorinskyCollision with a force term has no B200 kernel")
         if kind == OP_KBC:
             # the reference replaces tau by the flow's relaxation parameter on first call
             # (lettuce/ext/_collision/kbc_collision.py:97-99); mirror that state change
@@ -287,6 +300,18 @@ class Engine:
             o = self.desc.ops[i]
             if o.kind == OP_BGK:
                 o.p0 = float(op.tau)
+            elif o.kind == OP_BGK_FORCED:
+                # Guo: u_eq = a/(2 rho), source (1 - 1/(2 tau_force)) ... ; ShanChen: u_eq = tau a / rho, no source
+                # (lettuce/ext/_force/guo.py:16-38, shan_chen.py:13-26)
+                force = op.force
+                o.p0 = float(op.tau)
+                acc = [float(a) for a in torch.as_tensor(force.acceleration).flatten().tolist()]
+                if len(acc) != self.flow.stencil.d:
+                    raise ValueError(f"acceleration must have {self.flow.stencil.d} components, got {len(acc)}")
+                for a in range(3):
+                    o.force[a] = acc[a] if a < len(acc) else 0.0
+                o.ueq_scale = float(force.ueq_scaling_factor)
+                o.source_scale = (1.0 - 1.0 / (2.0 * float(force.tau))) if force_kind(force) == "Guo" else 0.0
             elif o.kind == OP_TRT:
                 o.p0, o.p1 = float(op.tau_plus), float(op.tau_minus)
             elif o.kind in (OP_KBC, OP_REGULARIZED):

@@ -170,6 +170,28 @@ def collide_bgk(st, f, tau, **_):
     return f - (1.0 / tau) * (f - feq)
 
 
+def collide_bgk_forced(st, f, tau, acceleration, scheme="guo", tau_force=None, **_):
+    """BGK with a body force (lettuce/ext/_collision/bgk_collision.py:17-22).  Guo (ext/_force/guo.py:16-38):
+    u_eq = a/(2 rho), source (1 - 1/(2 tau_f)) w [(e - u)/cs^2 + (e.u) e/cs^4] . a ; ShanChen
+    (ext/_force/shan_chen.py:13-26): u_eq = tau_f a / rho, no source."""
+    tau_force = tau if tau_force is None else tau_force
+    d = st["d"]
+    a = np.asarray(acceleration, dtype=f.dtype).reshape((d,) + (1,) * d)
+    r = rho(f)
+    scale = 0.5 if scheme == "guo" else tau_force
+    uu = u(st, f) + scale * a / r
+    feq = equilibrium(st, r, uu)
+    out = f - (1.0 / tau) * (f - feq)
+    if scheme == "guo":
+        e = st["e"].astype(f.dtype)
+        emu = e.reshape((st["q"], d) + (1,) * d) - uu[None]
+        eu = np.tensordot(e, uu, axes=1)
+        eeu = e.reshape((st["q"], d) + (1,) * d) * eu[:, None]
+        term = ((emu / CS2 + eeu / CS2 ** 2) * a[None]).sum(axis=1)
+        out = out + (1 - 1 / (2 * tau_force)) * st["w"].astype(f.dtype).reshape((-1,) + (1,) * d) * term
+    return out
+
+
 def collide_trt(st, f, tau, tau_minus=1.0, **_):
     """Two relaxation times (lettuce/ext/_collision/trt_collision.py:16-27)."""
     feq = equilibrium(st, rho(f), u(st, f))
@@ -279,7 +301,8 @@ def collide_smagorinsky(st, f, tau, constant=0.17, **_):
 
 
 COLLISIONS = {"none": collide_none, "bgk": collide_bgk, "trt": collide_trt, "kbc": collide_kbc,
-              "regularized": collide_regularized, "smagorinsky": collide_smagorinsky}
+              "regularized": collide_regularized, "smagorinsky": collide_smagorinsky,
+              "bgk_forced": collide_bgk_forced}
 
 
 # --------------------------------------------------------------------------

@@ -241,6 +241,26 @@ def native_known_answers():
     save("native_known_answers", **out)
 
 
+def poiseuille_case():
+    """tests/collision/test_force.py set-up: PoiseuilleFlow2D 17^2, Re 1, Ma 0.02, BGK + Guo / ShanChen"""
+    out = {}
+    for fname, cls in (("guo", lt.Guo), ("shanchen", lt.ShanChen)):
+        ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+        flow = lt.PoiseuilleFlow2D(context=ctx, resolution=17, reynolds_number=1, mach_number=0.02,
+                                   initialize_with_zeros=True)
+        acc = flow.units.convert_acceleration_to_lu(flow.acceleration)
+        tau = flow.units.relaxation_parameter_lu
+        sim = lt.Simulation(flow, lt.BGKCollision(tau, force=cls(flow=flow, tau=tau, acceleration=acc)), [])
+        out["f0"] = npy(flow.f)
+        out["tau"] = np.float64(tau)
+        out["acceleration_lu"] = npy(acc)
+        out["ncm"] = npy(sim.no_collision_mask)
+        sim(40)
+        out[f"f_{fname}_40"] = npy(flow.f)
+        out[f"u_{fname}_40"] = npy(flow.u(acceleration=acc))
+    save("poiseuille2d_forced", **out)
+
+
 def stock_obstacle_case():
     """Stock lt.Obstacle (AntiBounceBackOutlet default, lettuce/ext/_flows/obstacle.py:107-122)."""
     obstacle_case("obstacle2d_abb_bgk", lt.Obstacle, "D2Q9", [48, 16], "bgk", 20, ["POST_STREAMING"])
@@ -270,5 +290,6 @@ if __name__ == "__main__":
     obstacle_case("sphere_d3q19_bgk", ObstacleEqOut, "D3Q19", [32, 16, 16], "bgk", 10, ["POST_STREAMING"])
     obstacle_case("cylinder_d2q9_kbc", ObstacleEqOut, "D2Q9", [64, 16], "kbc", 20, ["POST_STREAMING"])
     stock_obstacle_case()
+    poiseuille_case()
     random_collision_case()
     native_known_answers()

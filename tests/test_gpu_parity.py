@@ -344,6 +344,45 @@ def test_obstacle_matches_live_oracle(stencil, res, coll, strategy, dtype):
     assert err < TOL[dtype], (stencil, coll, strategy, err)
 
 
+# ------------------------------------------------------------------ body forces (Guo, ShanChen)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("scheme", ["guo", "shanchen"])
+def test_forced_poiseuille_matches_reference_golden(scheme, dtype):
+    g = load_golden("poiseuille2d_forced")
+    ctx = cuda_ctx(dtype)
+    flow = lt.PoiseuilleFlow2D(ctx, 17, reynolds_number=1, mach_number=0.02)
+    acc = flow.units.convert_acceleration_to_lu(flow.acceleration)
+    tau = flow.units.relaxation_parameter_lu
+    assert tau == pytest.approx(float(g["tau"]), rel=1e-14)
+    assert np.allclose(acc.cpu().numpy(), g["acceleration_lu"], rtol=1e-6 if dtype == torch.float32 else 1e-14)
+    set_f(flow, g["f0"])
+    force = (lt.Guo if scheme == "guo" else lt.ShanChen)(flow=flow, tau=tau, acceleration=acc)
+    sim = lt.Simulation(flow, lt.BGKCollision(tau, force=force), [])
+    assert np.array_equal(sim.no_collision_mask.cpu().numpy(), g["ncm"])
+    sim(40)
+    assert max_rel(get_f(flow), g[f"f_{scheme}_40"]) < TOL[dtype]
+    u = flow.u(acceleration=acc).cpu().numpy()
+    assert np.max(np.abs(u - g[f"u_{scheme}_40"])) < (1e-15 if dtype == torch.float64 else 1e-7)
+
+
+@pytest.mark.parametrize("Force", ["Guo", "ShanChen"])
+def test_forced_poiseuille_reaches_analytic_profile(Force):
+    """tests/collision/test_force.py: after 1000 steps the velocity matches the parabola within 1 %"""
+    ctx = cuda_ctx(torch.float64)
+    flow = lt.PoiseuilleFlow2D(ctx, 17, reynolds_number=1, mach_number=0.02, initialize_with_zeros=True)
+    acc = flow.units.convert_acceleration_to_lu(flow.acceleration)
+    tau = flow.units.relaxation_parameter_lu
+    sim = lt.Simulation(flow, lt.BGKCollision(tau, force=getattr(lt, Force)(flow=flow, tau=tau, acceleration=acc)), [])
+    sim(1000)
+    u_sim = flow.units.convert_velocity_to_pu(flow.u(acceleration=acc))
+    _, u_ref = flow.analytic_solution()
+    fluid = sim.no_collision_mask == 0
+    for dim in range(2):
+        a, b = u_sim[dim][fluid].cpu().numpy(), u_ref[dim][fluid].cpu().numpy()
+        assert a.max() == pytest.approx(b.max(), rel=0.01)
+        assert np.max(np.abs(a - b)) < 0.01 * float(u_ref[0].max())
+
+
 # ------------------------------------------------------------------ ragged / degenerate lattices
 @pytest.mark.parametrize("stencil,res", [("D2Q9", [1, 1]), ("D2Q9", [2, 3]), ("D2Q9", [37, 1]), ("D2Q9", [3, 259]),
                                          ("D3Q19", [1, 1, 1]), ("D3Q19", [2, 2, 2]), ("D3Q19", [5, 7, 3]),

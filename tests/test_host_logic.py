@@ -163,7 +163,11 @@ def test_unsupported_operators_raise():
     with pytest.raises(NotImplementedError):
         lt.SmagorinskyCollision(0.6, force=object())
     with pytest.raises(NotImplementedError):
-        lt.BGKCollision(0.6, force=object())
+        native.op_kind(lt.BGKCollision(0.6, force=object()))          # unknown forcing scheme
+    flow = lt.PoiseuilleFlow2D(cpu(), 9, 1.0, 0.02)
+    assert native.op_kind(lt.BGKCollision(0.6, force=lt.Guo(flow, 0.6, [1e-5, 0]))) == native.OP_BGK_FORCED
+    d = native.describe(lt.Simulation(flow, lt.BGKCollision(0.6, force=lt.ShanChen(flow, 0.7, [1e-5, 0])), []))
+    assert d["ops"][0]["kind"] == native.OP_BGK_FORCED and d["ops"][1]["kind"] == native.OP_BOUNCE_BACK
     assert native.op_kind(lt.KBCCollision()) == native.OP_KBC
 
     class MyBB(lt.BounceBackBoundary):
@@ -209,16 +213,16 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(L, sym), f"{sym} declared in include/lbm_b200.h but not exported"
     assert set(native.EXPORTS) == declared
-    assert L.lbm_abi_version() == 1
+    assert L.lbm_abi_version() == 2
     assert b"unsupported" in L.lbm_status_string(-2)
 
 
 def test_ctypes_struct_layout_matches_header():
     """sizes computed from the C declaration: lbm_op = 4*4 + 2*8 + 2*8 + 3*8 + 4*8 = 104 bytes"""
-    assert ctypes.sizeof(native.LbmOp) == 104
+    assert ctypes.sizeof(native.LbmOp) == 104 + 5 * 8
     assert ctypes.sizeof(native.LbmLattice) == 24
     assert ctypes.sizeof(native.LbmHalo) == 12 * 8
-    assert ctypes.sizeof(native.LbmStepDesc) == 24 + 16 + 8 * 104 + 16 + 16 + 96
+    assert ctypes.sizeof(native.LbmStepDesc) == 24 + 16 + 8 * 144 + 16 + 16 + 96
 
 
 def test_descriptor_validation_without_gpu():
