@@ -1,14 +1,19 @@
-"""`python -m lettuce_b200.cli benchmark` -- the measurement harness of the reference's console script
-(`lettuce benchmark`, lettuce/cli.py:57-131) on the B200 engine: build a flow, BGK with tau from the
-units, run `steps` time steps, print MLUPS.  Same option names and defaults (precision double,
-PRE_STREAMING); only the flows and stencils of the hot-path scope are offered."""
+"""`python -m lettuce_b200.cli {benchmark,convergence}` -- the two commands of the reference's console script
+(lettuce/cli.py:57-186) on the B200 engine.  `benchmark`: build a flow, BGK with tau from the units, run
+`steps` time steps, print MLUPS (same option names and defaults: precision double, PRE_STREAMING; only the
+flows and stencils of the hot-path scope are offered).  `convergence`: Taylor-Green 2-D in diffusive scaling,
+checks second-order convergence of the velocity and first-order of the pressure."""
 from __future__ import annotations
 
 import click
 import torch
 
-from . import (BGKCollision, Context, D2Q9, D3Q19, D3Q27, Simulation, StreamingStrategy, TaylorGreenVortex,
-               __version__)
+import sys
+
+import numpy as np
+
+from . import (BGKCollision, Context, D2Q9, D3Q19, D3Q27, ErrorReporter, Simulation, StreamingStrategy,
+               TaylorGreenVortex, __version__)
 
 FLOWS = {"taylor2d": (TaylorGreenVortex, D2Q9), "taylor3d": (TaylorGreenVortex, D3Q27),
          "taylor3d_d3q19": (TaylorGreenVortex, D3Q19)}
@@ -49,6 +54,41 @@ def benchmark(ctx, steps, resolution, flow, streaming_strategy):
     click.echo("Finished {} ({}, {}) for {} steps in {} bit precision with {}. MLUPS: {:10.2f}".format(
         fl.__class__.__name__, fl.stencil.__class__.__name__, ctx.obj["device"], steps,
         str(ctx.obj["dtype"]).replace("torch.float", ""), streaming_strategy, mlups))
+    return 0
+
+
+def run_convergence(context, exponents=range(4, 9), echo=print):
+    """(order_u, order_p) of the last refinement; lettuce/cli.py:134-186"""
+    echo(("{:>15} " * 6).format("resolution", "error (u)", "order (u)", "error (p)", "order (p)", "MLUPS"))
+    old_u = old_p = None
+    factor_u = factor_p = 0.0
+    for i in exponents:
+        resolution = 2 ** i
+        flow = TaylorGreenVortex(context, [resolution] * 2, reynolds_number=10000, mach_number=8 / resolution,
+                                 stencil=D2Q9())
+        reporter = ErrorReporter(flow.analytic_solution, interval=1, out=None)
+        simulation = Simulation(flow, BGKCollision(tau=flow.units.relaxation_parameter_lu), [reporter])
+        mlups = simulation(10 * resolution)
+        error_u, error_p = np.mean(np.abs(reporter.out), axis=0).tolist()
+        factor_u = 0 if old_u is None else old_u / error_u
+        factor_p = 0 if old_p is None else old_p / error_p
+        old_u, old_p = error_u, error_p
+        echo(f"{resolution:15} {error_u:15.2e} {factor_u / 2:15.2f} {error_p:15.2e} {factor_p / 2:15.2f} {mlups:15.2f}")
+    return factor_u / 2, factor_p / 2
+
+
+@main.command()
+@click.pass_context
+def convergence(ctx):
+    """Use Taylor Green 2D for convergence test in diffusive scaling."""
+    order_u, order_p = run_convergence(Context(ctx.obj["device"], ctx.obj["dtype"]), echo=click.echo)
+    tol = 1e-1
+    if not (2 - tol) < order_u < (2 + tol):
+        click.echo(f"FAILED: Velocity convergence order {order_u} is not in [1.9, 2.1]")
+        sys.exit(1)
+    if not (1 - tol) < order_p < (1 + tol):
+        click.echo(f"FAILED: Pressure convergence order {order_p} is not in [0.9, 1.1].")
+        sys.exit(1)
     return 0
 
 

@@ -152,10 +152,6 @@ LBM_D void equilibrium_all(R rho, const R (&u)[3], R (&feq)[S::Q]) {
     ForQ<S::Q>::run([&]<int q>() { feq[q] = eq.template get<q>(); });
 }
 
-struct CollisionParams {
-    double p0, p1;
-};
-
 // ---------------------------------------------------------------------------
 // collisions.  COLL is an lbm_op_kind collision value.
 // ---------------------------------------------------------------------------

@@ -1,13 +1,21 @@
 // lbm_step.cuh -- fused stream+collide kernels.
 //
-// One launch = one lettuce time step (lettuce/_simulation.py:149-166, 241-305):
-// every population is read once and written once.  PULL gathers f_q(x - e_q)
-// (stream-before-collide), PUSH scatters the post-collision value to x + e_q
-// (stream-after-collide); the four StreamingStrategy values are the four
-// (PULL, PUSH) combinations.  Boundaries are folded in through a per-node label
-// byte; nodes whose label is the plain collision label and that touch no frozen
-// slot take the register-only fast path, everything else goes through
-// `general_node`, which restates Appendix A.2 of SURVEY.md node by node.
+// One launch = one lettuce time step (lettuce/_simulation.py:149-166, 241-305): every population is
+// read once and written once.  PULL gathers f_q(x - e_q) (stream-before-collide), PUSH scatters the
+// post-collision value to x + e_q (stream-after-collide); the four StreamingStrategy values are the four
+// (PULL, PUSH) combinations.
+//
+//   step_scalar_kernel   bulk kernel, one node per thread (`node_update`); in masked runs it skips every
+//                        node whose label byte is not the plain collision label
+//   general_nodes_kernel sparse kernel over the precomputed list of those skipped nodes (boundaries,
+//                        frozen slots): `general_node` restates Appendix A.2 of SURVEY.md node by node;
+//                        launched right before the bulk kernel, which overlaps it (programmatic
+//                        dependent launch); the two kernels write disjoint slots
+//   step_sync_kernel     bulk kernel for multi-GPU slabs with the in-kernel lock step (SlabSync)
+//   step_multi_kernel    experimental 2/4-nodes-per-thread bulk kernel for D2Q9
+//
+// Planes x = -1 and x = n0 resolve to the wrapped plane of the same buffer (single GPU) or to a
+// peer-mapped plane of the neighbour rank's buffer (in_plane / out_plane).
 #pragma once
 #include "lbm_core.cuh"
 

@@ -16,7 +16,7 @@ from .. import native
 from .._simulation import Reporter
 
 __all__ = ["Observable", "ObservableReporter", "MaximumVelocity", "IncompressibleKineticEnergy",
-           "Enstrophy", "Mass", "FailureReporterBase", "NaNReporter", "HighMaReporter"]
+           "Enstrophy", "Mass", "FailureReporterBase", "NaNReporter", "HighMaReporter", "ErrorReporter"]
 
 
 class Observable(ABC):
@@ -180,3 +180,34 @@ class HighMaReporter(FailureReporterBase):
         flow = simulation.flow
         ma = torch.norm(flow.u(), dim=0) / flow.stencil.cs
         return self._top(ma > self.threshold, ma)
+
+
+class ErrorReporter(Reporter):
+    """L2 error of velocity and pressure (physical units) against an analytic solution, normalised by
+    resolution^(d/2) (lettuce/ext/_reporter/error_reporter.py:9-45).  The fields come from the engine's
+    moment kernel; the norms are two small torch reductions."""
+    batchable = True
+
+    def __init__(self, analytical_solution, interval=1, out=sys.stdout):
+        super().__init__(interval)
+        self.analytical_solution = analytical_solution
+        self.out = [] if out is None else out
+        if not isinstance(self.out, list):
+            print("#error_u         error_p", file=self.out)
+
+    def __call__(self, simulation):
+        flow = simulation.flow
+        if flow.i % self.interval != 0:
+            return
+        pref, uref = self.analytical_solution(t=simulation.units.convert_time_to_pu(flow.i))
+        pref, uref = flow.context.convert_to_tensor(pref), flow.context.convert_to_tensor(uref)
+        rho, u = native.moments(flow.stencil, flow.f)
+        p = flow.units.convert_density_lu_to_pressure_pu(rho)
+        u = flow.units.convert_velocity_to_pu(u)
+        norm = float(p.numel()) ** 0.5        # resolution^(d/2) with resolution = (#nodes)^(1/d)
+        err_u = (torch.norm(u - uref) / norm).item()
+        err_p = (torch.norm(p - pref) / norm).item()
+        if isinstance(self.out, list):
+            self.out.append([err_u, err_p])
+        else:
+            print(err_u, err_p, file=self.out)

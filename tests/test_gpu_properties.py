@@ -246,3 +246,10 @@ def test_nan_reporter_aborts(tmp_path):
     sim(50)
     assert reporter.failed_iteration == 6 and flow.i > 50      # next due step after the NaN was planted
     assert len(reporter.results) > 0 and (tmp_path / "NaN_reporter.log").is_file()
+
+
+def test_convergence_orders():
+    """`lettuce convergence` (lettuce/cli.py:134-186, run by the reference's CI): second order in u, first in p"""
+    from lettuce_b200.cli import run_convergence
+    order_u, order_p = run_convergence(ctx(torch.float64), echo=lambda *_: None)
+    assert 1.9 < order_u < 2.1 and 0.9 < order_p < 1.1
