@@ -135,6 +135,24 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
     p.out_lo_qs = h.out_lo ? h.out_lo_qstride : p.N;
     p.out_hi = h.out_hi ? (R *)h.out_hi : p.out;
     p.out_hi_qs = h.out_hi ? h.out_hi_qstride : p.N;
+    // address tables of the bulk kernel (AddrTables): entry [k][q] + (x * plane + row + column)
+    {
+        const bool pull = d->streaming & LBM_PRE_STREAMING, push = d->streaming & LBM_POST_STREAMING;
+        const int64_t last = (int64_t)(dm.n0 - 1) * plane;
+        for (int k = 0; k < 4; ++k) {
+            for (int q = 0; q < S::Q; ++q) {
+                const int e0 = S::e(q, 0);
+                const R *ld = p.in + q * p.N - (pull ? e0 * plane : 0);
+                if (pull && (k & 1) && e0 == 1) ld = p.in_lo + q * p.in_lo_qs;              // x = 0 reads plane -1
+                if (pull && (k & 2) && e0 == -1) ld = p.in_hi + q * p.in_hi_qs - last;      // x = n0-1 reads plane n0
+                p.tbl.ld[k][q] = ld;
+                R *st = p.out + q * p.N + (push ? e0 * plane : 0);
+                if (push && (k & 1) && e0 == -1) st = p.out_lo + q * p.out_lo_qs;           // x = 0 writes plane -1
+                if (push && (k & 2) && e0 == 1) st = p.out_hi + q * p.out_hi_qs - last;     // x = n0-1 writes plane n0
+                p.tbl.st[k][q] = st;
+            }
+        }
+    }
     p.labels = d->labels;
     p.frozen = d->frozen;
     p.labels_lo = h.label_lo ? h.label_lo : (d->labels ? d->labels + (dm.n0 - 1) * plane : nullptr);

@@ -129,6 +129,17 @@ struct Equilibrium {
         fq = wr * (even + odd);
         fo = wr * (even - odd);
     }
+    // feq_q + feq_opposite(q)
+    template <int q>
+    LBM_D R pair_sum() const {
+        R eu = R(0);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (S::e(q, a) == 1) eu += u[a];
+            if (S::e(q, a) == -1) eu -= u[a];
+        }
+        return (R(2.0 * S::w(q)) * rho) * (base + (eu * eu) * R(0.5 / (kCs2 * kCs2)));
+    }
 };
 
 // compile-time loop helper: body.template operator()<q>() for q in [0, Q)
@@ -217,10 +228,10 @@ LBM_D double kbc_div(double a, double b) { return a / b; }
 // Entropic KBC in the closed form of SURVEY.md Appendix A.3
 // (lettuce/ext/_collision/kbc_collision.py:22-160).  beta = 1/(2 tau).
 //
-// Register plan: only the non-equilibrium part fn = f - feq is kept (in place of f); feq is
-// re-evaluated per opposite pair where it is needed (two FMAs per pair share the even part),
-// and delta_s is one of ten scalars derived from the six second moments.  With
-// dh = fn - ds the result is  f' = feq + (1 - beta gamma) fn + beta (gamma - 2) ds.
+// Register plan: only f itself lives in registers.  Moments come from opposite-pair sums and
+// differences, feq is re-evaluated per opposite pair where it is needed (the pair shares the even
+// part; the second moments need only that part), and delta_s is one of ten scalars derived from
+// the six second moments.
 template <class S, class R>
 struct Collide<S, R, LBM_OP_KBC> {
     // shear part of population q from the precomputed moment combinations (kbc_collision.py:44-94)
@@ -249,36 +260,46 @@ struct Collide<S, R, LBM_OP_KBC> {
 
     LBM_D static void apply(R (&f)[S::Q], R beta, R) {
         constexpr int Q = S::Q;
-        R rho, j[3];
-        moments<S, R>(f, rho, j);
+        // Pass 1a: density and momentum from opposite-pair sums and differences (even moments only see
+        // f_q + f_o, odd ones only f_q - f_o).
+        R rho = f[0], j[3] = {R(0), R(0), R(0)};
+        ForQ<Q>::run([&]<int q>() {
+            constexpr int o = S::opp(q);
+            if constexpr (q != 0 && q < o) {
+                constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
+                const R d = f[q] - f[o];
+                rho += f[q] + f[o];
+                if constexpr (e0 == 1) j[0] += d;
+                if constexpr (e0 == -1) j[0] -= d;
+                if constexpr (e1 == 1) j[1] += d;
+                if constexpr (e1 == -1) j[1] -= d;
+                if constexpr (e2 == 1) j[2] += d;
+                if constexpr (e2 == -1) j[2] -= d;
+            }
+        });
         const R inv_rho = R(1) / rho;
         const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
         Equilibrium<S, R> eq(rho, u);
-        // f <- fn = f - feq
-        ForQ<Q>::run([&]<int q>() {
-            constexpr int o = S::opp(q);
-            if constexpr (q == 0) {
-                f[0] -= eq.template get<0>();
-            } else if constexpr (q < o) {
-                R eq_q, eq_o;
-                eq.template pair<q>(eq_q, eq_o);
-                f[q] -= eq_q;
-                f[o] -= eq_o;
-            }
-        });
-        // raw second moments of fn; internal axes 0,1,2 are x,y,z in 3-D and x,(unused),y in 2-D
+        // Pass 1b: raw second moments of f - feq.  They are even in e, so per opposite pair only
+        // (f_q + f_o) - (feq_q + feq_o) is needed, and feq_q + feq_o = 2 w rho (base + (e.u)^2/(2 cs^4)) costs
+        // three operations.  (Subtracting the closed-form equilibrium stress from the moments of f instead
+        // is cheaper still but loses a digit: the differences are taken between O(rho/3) numbers.)
         R P00 = 0, P11 = 0, P22 = 0, P01 = 0, P02 = 0, P12 = 0;
         ForQ<Q>::run([&]<int q>() {
-            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            if constexpr (e0 != 0) P00 += f[q];
-            if constexpr (e1 != 0) P11 += f[q];
-            if constexpr (e2 != 0) P22 += f[q];
-            if constexpr (e0 * e1 == 1) P01 += f[q];
-            if constexpr (e0 * e1 == -1) P01 -= f[q];
-            if constexpr (e0 * e2 == 1) P02 += f[q];
-            if constexpr (e0 * e2 == -1) P02 -= f[q];
-            if constexpr (e1 * e2 == 1) P12 += f[q];
-            if constexpr (e1 * e2 == -1) P12 -= f[q];
+            constexpr int o = S::opp(q);
+            if constexpr (q != 0 && q < o) {
+                constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
+                const R s = (f[q] + f[o]) - eq.template pair_sum<q>();
+                if constexpr (e0 != 0) P00 += s;
+                if constexpr (e1 != 0) P11 += s;
+                if constexpr (e2 != 0) P22 += s;
+                if constexpr (e0 * e1 == 1) P01 += s;
+                if constexpr (e0 * e1 == -1) P01 -= s;
+                if constexpr (e0 * e2 == 1) P02 += s;
+                if constexpr (e0 * e2 == -1) P02 -= s;
+                if constexpr (e1 * e2 == 1) P12 += s;
+                if constexpr (e1 * e2 == -1) P12 -= s;
+            }
         });
         R c[7];
         if constexpr (S::D == 2) {
@@ -298,20 +319,22 @@ struct Collide<S, R, LBM_OP_KBC> {
             c[5] = R(0.25) * P02;
             c[6] = R(0.25) * P01;
         }
-        // entropic stabiliser gamma = 1/beta - (2 - 1/beta) <ds|dh>/<dh|dh>, weights 1/feq
+        // Pass 2: entropic stabiliser gamma = 1/beta - (2 - 1/beta) <ds|dh>/<dh|dh>, weights 1/feq,
+        // with dh = (f - feq) - ds.  f itself stays in the registers.
         R sum_s = 0, sum_h = 0;
         ForQ<Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
             if constexpr (q == 0) {
-                const R ds = ds_of<0>(c), dh = f[0] - ds;
-                const R r = kbc_div(dh, eq.template get<0>());
+                const R fe = eq.template get<0>();
+                const R ds = ds_of<0>(c), dh = (f[0] - fe) - ds;
+                const R r = kbc_div(dh, fe);
                 sum_s += ds * r;
                 sum_h += dh * r;
             } else if constexpr (q < o) {
                 R eq_q, eq_o;
                 eq.template pair<q>(eq_q, eq_o);
                 const R ds = ds_of<q>(c);          // even in e: same for q and its opposite
-                const R dh_q = f[q] - ds, dh_o = f[o] - ds;
+                const R dh_q = (f[q] - eq_q) - ds, dh_o = (f[o] - eq_o) - ds;
                 const R r_q = kbc_div(dh_q, eq_q), r_o = kbc_div(dh_o, eq_o);
                 sum_s += ds * (r_q + r_o);
                 sum_h += dh_q * r_q + dh_o * r_o;
@@ -321,17 +344,18 @@ struct Collide<S, R, LBM_OP_KBC> {
         R gamma = inv_beta - (R(2) - inv_beta) * (sum_s / sum_h);
         // kbc_collision.py:154-157: gamma < 1e-15 -> 2 ; NaN -> 2
         if (!(gamma >= R(1e-15))) gamma = R(2);
-        const R a = R(1) - beta * gamma, b = beta * (gamma - R(2));
+        // Pass 3: f' = f - beta (2 ds + gamma dh) = a f + (1 - a) feq + b ds,  a = 1 - beta gamma, b = beta (gamma - 2)
+        const R a = R(1) - beta * gamma, na = beta * gamma, b = beta * (gamma - R(2));
         ForQ<Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
             if constexpr (q == 0) {
-                f[0] = eq.template get<0>() + (a * f[0] + b * ds_of<0>(c));
+                f[0] = a * f[0] + (na * eq.template get<0>() + b * ds_of<0>(c));
             } else if constexpr (q < o) {
                 R eq_q, eq_o;
                 eq.template pair<q>(eq_q, eq_o);
                 const R bds = b * ds_of<q>(c);
-                f[q] = eq_q + (a * f[q] + bds);
-                f[o] = eq_o + (a * f[o] + bds);
+                f[q] = a * f[q] + (na * eq_q + bds);
+                f[o] = a * f[o] + (na * eq_o + bds);
             }
         });
     }

@@ -45,6 +45,18 @@ struct SlabSync {
     int on;
 };
 
+// Per-population base pointers of the bulk kernel, built on the host (fill_params).  Entry [k][q] already
+// contains q * stride and the x-shift of population q, so that the address of a load / store is
+//     table[k][q] + (x * plane + in-plane index)
+// with k = 0 for interior planes, 1 for the first plane (its lower neighbour plane is the wrapped or
+// peer-mapped `lo` plane), 2 for the last plane (`hi`), 3 when the slab is one plane thick.
+constexpr int kQMax = 27;
+template <class R>
+struct AddrTables {
+    const R *ld[4][kQMax];
+    R *st[4][kQMax];
+};
+
 template <class R>
 struct StepParams {
     const R *in;
@@ -63,6 +75,7 @@ struct StepParams {
     R ca, cb;  // scalars of the collision entry
     ForceArgs<R> force;  // LBM_OP_BGK_FORCED only
     SlabSync sync;
+    AddrTables<R> tbl;
     OpDev<R> ops[LBM_MAX_OPS];
 };
 
@@ -73,17 +86,18 @@ struct Plane {
     int64_t qs;
 };
 
+// (branch-free selects: x is block-uniform, so these stay on the uniform datapath)
 template <class R>
 LBM_D Plane<R, const R> in_plane(const StepParams<R> &p, int x) {
-    if (x < 0) return {p.in_lo, p.in_lo_qs};
-    if (x >= p.n0) return {p.in_hi, p.in_hi_qs};
-    return {p.in + (int64_t)x * p.n1 * p.n2, p.N};
+    const bool lo = x < 0, hi = x >= p.n0;
+    const R *inner = p.in + (int64_t)(lo || hi ? 0 : x) * p.n1 * p.n2;
+    return {lo ? p.in_lo : (hi ? p.in_hi : inner), lo ? p.in_lo_qs : (hi ? p.in_hi_qs : p.N)};
 }
 template <class R>
 LBM_D Plane<R, R> out_plane(const StepParams<R> &p, int x) {
-    if (x < 0) return {p.out_lo, p.out_lo_qs};
-    if (x >= p.n0) return {p.out_hi, p.out_hi_qs};
-    return {p.out + (int64_t)x * p.n1 * p.n2, p.N};
+    const bool lo = x < 0, hi = x >= p.n0;
+    R *inner = p.out + (int64_t)(lo || hi ? 0 : x) * p.n1 * p.n2;
+    return {lo ? p.out_lo : (hi ? p.out_hi : inner), lo ? p.out_lo_qs : (hi ? p.out_hi_qs : p.N)};
 }
 template <class R>
 LBM_D const uint32_t *frozen_plane(const StepParams<R> &p, int x) {
@@ -294,47 +308,35 @@ constexpr int min_blocks_per_sm() {
     return (sizeof(R) == 4 && COLL == LBM_OP_KBC && S::Q == 27) ? LBM_KBC_MIN_BLOCKS : 0;  // 0 = no constraint
 }
 
-// one node: gather, collide, scatter.  Addresses are split into a block-uniform part (plane pointer +
-// q * stride) and a 32-bit in-plane index per thread (row offset + column, nine combinations), so one
-// access costs one IMAD.WIDE instead of a chain of 64-bit integer operations.
+// one node: gather, collide, scatter.  An address is a block-uniform table entry (AddrTables, read from the
+// constant bank) plus one 32-bit node index per thread, chosen from nine precomputed (row, column)
+// combinations: one IMAD.WIDE per access.
 template <class S, class R, int COLL, bool PULL, bool PUSH>
 LBM_D void node_update(const StepParams<R> &p, int x, int y, int z) {
     constexpr int Q = S::Q;
     // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
     const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
     const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
-    const int rowm = ym * p.n2, row0 = y * p.n2, rowp = yp * p.n2;
+    const int xoff = x * (p.n1 * p.n2);
+    const int rowm = xoff + ym * p.n2, row0 = xoff + y * p.n2, rowp = xoff + yp * p.n2;
+    const int k = (x == 0 ? 1 : 0) | (x == p.n0 - 1 ? 2 : 0);
 
     R f[Q];
-    if (PULL) {
-        const Plane<R, const R> pl[3] = {in_plane(p, x + 1), in_plane(p, x), in_plane(p, x - 1)};  // index e0+1 -> x - e0
-        ForQ<Q>::run([&]<int q>() {
-            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            const int rs = e1 == 0 ? row0 : (e1 == 1 ? rowm : rowp);
-            const int zs = e2 == 0 ? z : (e2 == 1 ? zm : zp);
-            const R *qb = pl[e0 + 1].p + q * pl[e0 + 1].qs;   // block-uniform
-            f[q] = __ldg(qb + (rs + zs));
-        });
-    } else {
-        const R *src = p.in + (int64_t)x * p.n1 * p.n2;
-        ForQ<Q>::run([&]<int q>() { f[q] = __ldg(src + q * p.N + (row0 + z)); });
-    }
+    ForQ<Q>::run([&]<int q>() {
+        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+        const int rs = (!PULL || e1 == 0) ? row0 : (e1 == 1 ? rowm : rowp);
+        const int zs = (!PULL || e2 == 0) ? z : (e2 == 1 ? zm : zp);
+        f[q] = __ldg(p.tbl.ld[k][q] + (rs + zs));
+    });
 
     collide_node<S, R, COLL>(p, f);
 
-    if (PUSH) {
-        const Plane<R, R> pl[3] = {out_plane(p, x - 1), out_plane(p, x), out_plane(p, x + 1)};  // index e0+1 -> x + e0
-        ForQ<Q>::run([&]<int q>() {
-            constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            const int rd = e1 == 0 ? row0 : (e1 == 1 ? rowp : rowm);
-            const int zd = e2 == 0 ? z : (e2 == 1 ? zp : zm);
-            R *qb = pl[e0 + 1].p + q * pl[e0 + 1].qs;         // block-uniform
-            qb[rd + zd] = f[q];
-        });
-    } else {
-        R *dst = p.out + (int64_t)x * p.n1 * p.n2;
-        ForQ<Q>::run([&]<int q>() { (dst + q * p.N)[row0 + z] = f[q]; });
-    }
+    ForQ<Q>::run([&]<int q>() {
+        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+        const int rd = (!PUSH || e1 == 0) ? row0 : (e1 == 1 ? rowp : rowm);
+        const int zd = (!PUSH || e2 == 0) ? z : (e2 == 1 ? zp : zm);
+        p.tbl.st[k][q][rd + zd] = f[q];
+    });
 }
 
 template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
