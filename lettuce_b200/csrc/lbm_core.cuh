@@ -223,7 +223,15 @@ LBM_D float kbc_div(float a, float b) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
     return a * r;
 }
-LBM_D double kbc_div(double a, double b) { return a / b; }
+// fp64: reciprocal seed (MUFU.RCP64H, ~20 bits) refined by two Newton steps to full precision; avoids the
+// IEEE division's slow-path subroutine 27 times per node.
+LBM_D double kbc_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    return a * r;
+}
 
 // Entropic KBC in the closed form of SURVEY.md Appendix A.3
 // (lettuce/ext/_collision/kbc_collision.py:22-160).  beta = 1/(2 tau).
