@@ -37,8 +37,8 @@ Q, BYTES_PER_NODE = 19, 2 * 19 * 4       # D3Q19 fp32: every population read onc
 RE, MA = 1600.0, 0.05
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed
 # `ncu --set full` captures (profiles/r1_step_d3q19_bgk_{pre,post}_256.csv); algorithmic = 2.550e9
-NCU_DRAM_BYTES_PER_LAUNCH = {(256, "PRE_STREAMING"): 1.275083e9 + 1.225110e9,
-                             (256, "POST_STREAMING"): 1.276738e9 + 1.226840e9}
+NCU_DRAM_BYTES_PER_LAUNCH = {(256, "PRE_STREAMING"): 1.275082e9 + 1.224746e9,
+                             (256, "POST_STREAMING"): 1.276132e9 + 1.225850e9}
 
 
 def measured_hbm_peak():
