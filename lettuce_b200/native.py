@@ -358,6 +358,11 @@ class Engine:
         _require_cuda(g, "flow.f_next")
         if g.shape != f.shape or g.dtype != f.dtype:
             raise RuntimeError("flow.f_next does not match flow.f")
+        lat = self.lat
+        expect = [flow.stencil.q, lat.nx, lat.ny] + ([lat.nz] if flow.stencil.d == 3 else [])
+        if list(f.shape) != expect or dtype_id(f.dtype) != lat.dtype or f.device != self.device:
+            raise RuntimeError(f"flow.f changed shape, dtype or device since the engine was built "
+                               f"({list(f.shape)} {f.dtype} {f.device}); create a new Simulation")
         return f, g
 
     def step(self, n: int = 1):
