@@ -14,7 +14,7 @@ from .._stencil import D2Q9, D3Q19
 from .._unit import UnitConversion
 from .boundary import AntiBounceBackOutlet, BounceBackBoundary, EquilibriumBoundaryPU
 
-__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D"]
+__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D", "Cavity2D", "DoublyPeriodicShear2D"]
 
 
 class ExtFlow(Flow):
@@ -211,3 +211,86 @@ class PoiseuilleFlow2D(ExtFlow):
         mask = self.context.zero_tensor(self.resolution, dtype=torch.bool)
         mask[:, [0, -1]] = True
         return [BounceBackBoundary(mask=mask)]
+
+
+def _unit_box_grid(flow):
+    """node coordinates on [0, 1) per axis (endpoint excluded), context dtype"""
+    axes = [torch.linspace(0, 1 - 1 / n, steps=n, device=flow.context.device, dtype=flow.context.dtype)
+            for n in flow.resolution]
+    return torch.meshgrid(*axes, indexing="ij")
+
+
+class Cavity2D(ExtFlow):
+    """Lid-driven cavity: bounce-back on the left, right and bottom walls, equilibrium lid moving in +x at the
+    characteristic velocity on the top row (lettuce/ext/_flows/liddrivencavity.py:14-71).  Starts at rest."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number):
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number)
+
+    def make_resolution(self, resolution, stencil=None):
+        if isinstance(resolution, int):
+            return [resolution] * 2
+        assert len(resolution) == 2, "expected 2-dimensional resolution"
+        return list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution):
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0], characteristic_length_pu=1,
+                              characteristic_velocity_pu=1)
+
+    @property
+    def grid(self):
+        return _unit_box_grid(self)
+
+    def initial_pu(self):
+        zeros = self.context.zero_tensor(self.resolution)
+        return zeros[None, ...], torch.stack([zeros, zeros])
+
+    @property
+    def post_boundaries(self):
+        walls = self.context.zero_tensor(self.resolution, dtype=torch.bool)
+        lid = self.context.zero_tensor(self.resolution, dtype=torch.bool)
+        walls[[0, -1], 1:] = True     # left and right
+        walls[:, 0] = True            # bottom
+        lid[:, -1] = True             # top (wins over the side walls in the corners: later boundary)
+        return [BounceBackBoundary(walls),
+                EquilibriumBoundaryPU(self.context, self, lid, [float(self.units.characteristic_velocity_pu), 0.0])]
+
+
+class DoublyPeriodicShear2D(ExtFlow):
+    """Two tanh shear layers with a sinusoidal cross-flow perturbation on the periodic unit square
+    (lettuce/ext/_flows/doublyshear.py:20-91)."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None,
+                 shear_layer_width=80, initial_perturbation_magnitude=0.05, initialize_fneq: bool = True):
+        self.initialize_fneq = initialize_fneq
+        self.initial_perturbation_magnitude = initial_perturbation_magnitude
+        self.shear_layer_width = shear_layer_width
+        self.stencil = D2Q9() if stencil is None else (stencil() if callable(stencil) else stencil)
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, self.stencil, equilibrium)
+
+    def make_resolution(self, resolution, stencil=None):
+        if isinstance(resolution, int):
+            return [resolution] * self.stencil.d
+        assert len(resolution) == 2, "expected 2-dimensional resolution"
+        return list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution):
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0], characteristic_length_pu=1,
+                              characteristic_velocity_pu=1)
+
+    @property
+    def grid(self):
+        return _unit_box_grid(self)
+
+    def initial_pu(self):
+        x, y = self.grid
+        w = self.shear_layer_width
+        u1 = torch.where(y > 0.5, torch.tanh(w * (y - 0.25)), torch.tanh(w * (0.75 - y)))
+        u2 = self.initial_perturbation_magnitude * torch.sin(2 * torch.pi * (x + 0.25))
+        return torch.zeros_like(u1)[None, ...], torch.stack([u1, u2])
+
+    @property
+    def post_boundaries(self):
+        return []

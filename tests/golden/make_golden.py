@@ -261,6 +261,19 @@ def poiseuille_case():
     save("poiseuille2d_forced", **out)
 
 
+def other_flows_case():
+    """DoublyPeriodicShear2D, BGK, a few steps.  (The reference's Cavity2D cannot be constructed: its
+    post_boundaries calls EquilibriumBoundaryPU without the flow argument, liddrivencavity.py:63-70.)"""
+    out = {}
+    ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+    flow = lt.DoublyPeriodicShear2D(ctx, [24, 20], reynolds_number=1000, mach_number=0.05)
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+    out["shear_f0"] = npy(flow.f)
+    sim(15)
+    out["shear_f15"] = npy(flow.f)
+    save("shear2d_bgk", **out)
+
+
 def stock_obstacle_case():
     """Stock lt.Obstacle (AntiBounceBackOutlet default, lettuce/ext/_flows/obstacle.py:107-122)."""
     obstacle_case("obstacle2d_abb_bgk", lt.Obstacle, "D2Q9", [48, 16], "bgk", 20, ["POST_STREAMING"])
@@ -291,5 +304,6 @@ if __name__ == "__main__":
     obstacle_case("cylinder_d2q9_kbc", ObstacleEqOut, "D2Q9", [64, 16], "kbc", 20, ["POST_STREAMING"])
     stock_obstacle_case()
     poiseuille_case()
+    other_flows_case()
     random_collision_case()
     native_known_answers()

@@ -357,6 +357,41 @@ def test_obstacle_matches_live_oracle(stencil, res, coll, strategy, dtype):
     assert err < TOL[dtype], (stencil, coll, strategy, err)
 
 
+# ------------------------------------------------------------------ further flows on the same kernels
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_doubly_periodic_shear_matches_reference_golden(dtype):
+    g = load_golden("shear2d_bgk")
+    ctx = cuda_ctx(dtype)
+    flow = lt.DoublyPeriodicShear2D(ctx, [24, 20], reynolds_number=1000, mach_number=0.05)
+    if dtype == torch.float64:
+        assert max_rel(get_f(flow), g["shear_f0"]) < 1e-13
+    set_f(flow, g["shear_f0"])
+    lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])(15)
+    assert max_rel(get_f(flow), g["shear_f15"]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("strategy", ["POST_STREAMING", "PRE_STREAMING"])
+def test_lid_driven_cavity_matches_oracle(strategy):
+    """bounce-back walls + equilibrium lid; the lid's label wins in the top corners (later boundary)"""
+    ctx = cuda_ctx(torch.float64)
+    res = [20, 16]
+    flow = lt.Cavity2D(ctx, res, reynolds_number=100, mach_number=0.05)
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], STRATS[strategy])
+    st = lo.stencil("D2Q9")
+    f0 = get_f(flow)
+    walls = np.zeros(res, dtype=bool); walls[[0, -1], 1:] = True; walls[:, 0] = True
+    lid = np.zeros(res, dtype=bool); lid[:, -1] = True
+    units = lo.Units(100, 0.05, characteristic_length_lu=res[0])
+    post = [lo.bounce_back(walls), lo.equilibrium_pu(lid, units.pressure_pu_to_density_lu(np.zeros((1, 1, 1))),
+                                                     units.velocity_to_lu(np.array([1.0, 0.0])).reshape(2, 1, 1))]
+    ncm, _ = lo.build_masks(st, res, [], post)
+    assert np.array_equal(sim.no_collision_mask.cpu().numpy(), ncm)
+    sim(25)
+    ref = lo.run(st, f0, 25, dict(kind="bgk", tau=units.tau), post=post, strategy=strategy)
+    assert max_rel(get_f(flow), ref) < 1e-12
+    assert float(flow.u()[0, :, -2].mean()) > 0        # the lid drags the fluid along
+
+
 # ------------------------------------------------------------------ body forces (Guo, ShanChen)
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("scheme", ["guo", "shanchen"])
