@@ -305,11 +305,15 @@ class Engine:
                 # (lettuce/ext/_force/guo.py:16-38, shan_chen.py:13-26)
                 force = op.force
                 o.p0 = float(op.tau)
-                acc = [float(a) for a in torch.as_tensor(force.acceleration).flatten().tolist()]
-                if len(acc) != self.flow.stencil.d:
-                    raise ValueError(f"acceleration must have {self.flow.stencil.d} components, got {len(acc)}")
+                a_t = force.acceleration
+                key = (id(a_t), getattr(a_t, "_version", None))
+                if getattr(self, "_acc_key", None) != key:       # reading a CUDA tensor synchronises: only when it changed
+                    acc = [float(a) for a in torch.as_tensor(a_t).flatten().tolist()]
+                    if len(acc) != self.flow.stencil.d:
+                        raise ValueError(f"acceleration must have {self.flow.stencil.d} components, got {len(acc)}")
+                    self._acc_key, self._acc = key, acc
                 for a in range(3):
-                    o.force[a] = acc[a] if a < len(acc) else 0.0
+                    o.force[a] = self._acc[a] if a < len(self._acc) else 0.0
                 o.ueq_scale = float(force.ueq_scaling_factor)
                 o.source_scale = (1.0 - 1.0 / (2.0 * float(force.tau))) if force_kind(force) == "Guo" else 0.0
             elif o.kind == OP_TRT:
