@@ -14,7 +14,7 @@ Every time step and every moment reduction runs in hand-written sm_100a CUDA ker
 """
 from ._context import *
 from ._stencil import *
-from ._unit import *
+from .units import *
 from ._flow import *
 from ._simulation import *
 from .ext import *

@@ -11,7 +11,7 @@ import torch
 
 from .._flow import Flow
 from .._stencil import D2Q9, D3Q19
-from .._unit import UnitConversion
+from ..units import UnitConversion
 from .boundary import AntiBounceBackOutlet, BounceBackBoundary, EquilibriumBoundaryPU
 
 __all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D", "Cavity2D", "DoublyPeriodicShear2D"]
