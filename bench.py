@@ -181,7 +181,7 @@ def gpu_main(args):
     n = args.size
     strategy = lt.StreamingStrategy[args.strategy]
     ctx = lt.Context(dev, dtype=torch.float32)
-    if world == 1:
+    if world == 1 and not args.slab:
         flow = lt.TaylorGreenVortex(ctx, [n] * 3, RE, MA, stencil=lt.D3Q19())
         sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], strategy)
         stepper = lambda k: native.invoke_n(sim, k)
@@ -222,7 +222,8 @@ def gpu_main(args):
     mlups = args.steps * nodes_total / 1e6 / (ms * 1e-3)
     assert torch.isfinite(flow.f).all()
 
-    kernel_name = native.engine_of(sim).variant_name if world == 1 else "step_sync (slab, in-kernel lock step)"
+    kernel_name = (native.engine_of(sim).variant_name if world == 1 and not args.slab
+                   else "step_sync (slab, in-kernel lock step)")
     # ---- e2e: HOST populations in, HOST populations out, every step's kinetic energy read back
     e2e = None
     f_host = torch.empty(flow.f.shape, dtype=torch.float32).pin_memory()
@@ -305,6 +306,9 @@ def main():
     ap.add_argument("--strategy", default="PRE_STREAMING",
                     choices=["NO_STREAMING", "PRE_STREAMING", "POST_STREAMING", "DOUBLE_STREAMING"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--slab", action="store_true",
+                    help="with --gpus 1: run the multi-GPU slab kernel (in-kernel lock step) with the rank as its own "
+                         "neighbour, e.g. to profile it under ncu")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)
