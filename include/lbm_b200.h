@@ -78,7 +78,9 @@ typedef enum lbm_op_kind {
     LBM_OP_BOUNCE_BACK = 16, /* ext/_boundary/bounce_back_boundary.py:10-32 */
     LBM_OP_EQUILIBRIUM = 17, /* ext/_boundary/equilibrium_boundary_pu.py:79-84, values already in lattice units */
     LBM_OP_OUTLET_P = 18,    /* ext/_boundary/equilibrium_outlet_p.py:63-73; p0 = rho_outlet */
-    LBM_OP_ANTI_BOUNCE_BACK = 19 /* ext/_boundary/anti_bounce_back_outlet.py:71-91 */
+    LBM_OP_ANTI_BOUNCE_BACK = 19, /* ext/_boundary/anti_bounce_back_outlet.py:71-91 */
+    LBM_OP_IDENTITY = 20     /* boundary entry that leaves its nodes untouched; used for stream-only passes (the
+                                frozen-slot rule still applies), see Engine.step in lettuce_b200/native.py */
 } lbm_op_kind;
 
 /* One entry of the transformer list (lettuce/_simulation.py:70).  Entry i acts on

@@ -91,7 +91,7 @@ static int validate_desc(const lbm_step_desc *d, Dims &dm) {
         const lbm_op &op = d->ops[i];
         if (i != d->collision_index && is_collision(op.kind)) return LBM_ERR_BAD_ARGUMENT;
         if (i != d->collision_index && op.kind != LBM_OP_BOUNCE_BACK && op.kind != LBM_OP_EQUILIBRIUM &&
-            !is_outlet(op.kind))
+            op.kind != LBM_OP_IDENTITY && !is_outlet(op.kind))
             return LBM_ERR_BAD_ARGUMENT;
         if (op.kind == LBM_OP_EQUILIBRIUM && (!op.rho || !op.u)) return LBM_ERR_BAD_ARGUMENT;
         if (is_outlet(op.kind)) {

@@ -357,6 +357,46 @@ def test_obstacle_matches_live_oracle(stencil, res, coll, strategy, dtype):
     assert err < TOL[dtype], (stencil, coll, strategy, err)
 
 
+# ------------------------------------------------------------------ long POST batches: S (C S)^(n-1) C
+@pytest.mark.parametrize("case", ["tgv_kbc", "sphere_trt", "cylinder_bgk", "stock_obstacle"])
+def test_lazy_post_batches_are_bit_identical(case, monkeypatch):
+    """n POST_STREAMING steps issued as one long batch (collide-only + pull steps + stream-only) equal the same
+    n steps issued one by one with the push kernel, bit for bit -- with boundaries, frozen slots and outlets"""
+    from lettuce_b200 import native as nv
+    ctx = cuda_ctx(torch.float32)
+
+    def build():
+        if case == "tgv_kbc":
+            flow = lt.TaylorGreenVortex(ctx, [20, 24, 28], 1600.0, 0.05, stencil=lt.D3Q27())
+            return flow, lt.KBCCollision()
+        if case == "sphere_trt":
+            flow = make_obstacle(ObstacleEqOut, ctx, [48, 24, 24], lt.D3Q27())
+            return flow, lt.TRTCollision(flow.units.relaxation_parameter_lu)
+        if case == "cylinder_bgk":
+            flow = make_obstacle(ObstacleEqOut, ctx, [96, 32], lt.D2Q9())
+            return flow, lt.BGKCollision(flow.units.relaxation_parameter_lu)
+        flow = make_obstacle(lt.Obstacle, ctx, [64, 32], lt.D2Q9())         # anti-bounce-back outlet
+        return flow, lt.BGKCollision(flow.units.relaxation_parameter_lu)
+
+    n = 21
+    flow_a, coll_a = build()
+    sim_a = lt.Simulation(flow_a, coll_a, [])
+    for _ in range(n):
+        nv.invoke(sim_a)                       # push kernel, one launch per step
+    flow_b, coll_b = build()
+    sim_b = lt.Simulation(flow_b, coll_b, [])
+    assert nv.LAZY_POST_MIN_STEPS <= n
+    launches = nv.launch_count()
+    nv.invoke_n(sim_b, n)                      # one batch: n + 1 passes
+    passes = (nv.launch_count() - launches) / (1 if case == "tgv_kbc" else 2)
+    assert passes == n + 1
+    assert torch.equal(flow_a.f, flow_b.f)
+    nv.invoke_n(sim_b, 16); nv.invoke_n(sim_b, 17)          # even and odd batch lengths
+    for _ in range(33):
+        nv.invoke(sim_a)
+    assert torch.equal(flow_a.f, flow_b.f)
+
+
 # ------------------------------------------------------------------ further flows on the same kernels
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_doubly_periodic_shear_matches_reference_golden(dtype):
