@@ -386,11 +386,14 @@ def test_lazy_post_batches_match_push_steps(case, monkeypatch):
     flow_b, coll_b = build()
     sim_b = lt.Simulation(flow_b, coll_b, [])
     monkeypatch.setattr(nv, "LAZY_POST_MIN_STEPS", 16)
+    nv.engine_of(sim_b)                        # mask packing launches happen here, outside the count
     launches = nv.launch_count()
     nv.invoke_n(sim_b, 21)                     # one batch: 22 passes
     assert (nv.launch_count() - launches) / (1 if case == "tgv_bgk" else 2) == 22
     nv.invoke_n(sim_b, 16); nv.invoke_n(sim_b, 17)          # even and odd batch lengths
-    assert max_rel(get_f(flow_b), get_f(flow_a)) < 2e-6
+    diff = max_rel(get_f(flow_b), get_f(flow_a))
+    assert diff < 2e-6
+    print(f"lazy POST vs push, {case}: max relative difference {diff:.1e}")
 
 
 # ------------------------------------------------------------------ further flows on the same kernels
