@@ -30,9 +30,10 @@ OP_BOUNCE_BACK, OP_EQUILIBRIUM, OP_OUTLET_P, OP_ANTI_BOUNCE_BACK, OP_IDENTITY = 
 NO_STREAMING, POST_STREAMING, PRE_STREAMING, DOUBLE_STREAMING = 0, 1, 2, 3
 # Opt-in (0 = off, the default): batches of at least this many POST_STREAMING steps run as collide-only +
 # (n-1) pull steps + stream-only.  Measured on B200: it pays only where the push kernel is well behind the pull
-# kernel and the batch is long (sphere D3Q27 TRT: +5 % at n = 20; D3Q19 BGK: break-even at n ~ 40), and the
-# result equals n push steps only up to rounding, because the collide code is compiled once per kernel variant
-# and nvcc's FMA contraction is not identical across them.  Off by default so that sim(n) == n x sim(1) exactly.
+# kernel and the batch is long (sphere D3Q27 TRT: +5 % at n = 20; D3Q19 BGK: break-even at n ~ 40).  The result
+# was bit-identical to n push steps in every tested case, but that rests on nvcc contracting the collide code
+# identically in three kernel variants, which nothing guarantees; off by default so that sim(n) == n x sim(1)
+# holds by construction.
 LAZY_POST_MIN_STEPS = int(os.environ.get("LBM_B200_LAZY_POST_MIN", "0"))
 SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED, ENSTROPHY = range(6)
 
@@ -389,7 +390,7 @@ class Engine:
 
         With LAZY_POST_MIN_STEPS > 0 (opt-in), long POST_STREAMING batches use the identity
         (S C)^n = S (C S)^(n-1) C: one collide-only pass, n-1 steps of the pull kernel (aligned stores) and one
-        stream-only pass; equal to n push steps up to rounding (tests/test_gpu_parity.py)."""
+        stream-only pass; observed bit-identical to n push steps (tests/test_gpu_parity.py)."""
         if n <= 0:
             return
         self.refresh_parameters()

@@ -360,9 +360,10 @@ def test_obstacle_matches_live_oracle(stencil, res, coll, strategy, dtype):
 # ------------------------------------------------------------------ long POST batches: S (C S)^(n-1) C (opt-in)
 @pytest.mark.parametrize("case", ["tgv_bgk", "sphere_trt", "cylinder_bgk", "stock_obstacle"])
 def test_lazy_post_batches_match_push_steps(case, monkeypatch):
-    """Opt-in batching of POST_STREAMING steps as collide-only + pull steps + stream-only: same result as the
-    push kernel step by step (to fp32 rounding: the collide code of different kernel variants is not guaranteed
-    to round identically), with boundaries, frozen slots and both outlet types; and off by default."""
+    """Opt-in batching of POST_STREAMING steps as collide-only + pull steps + stream-only: same bits as the push
+    kernel step by step, with boundaries, frozen slots and both outlet types (streaming only moves values and the
+    collide code rounds identically in the kernel variants involved -- observed, not guaranteed by the compiler,
+    which is why the feature is off by default)."""
     from lettuce_b200 import native as nv
     ctx = cuda_ctx(torch.float32)
     assert nv.LAZY_POST_MIN_STEPS == 0
@@ -391,9 +392,7 @@ def test_lazy_post_batches_match_push_steps(case, monkeypatch):
     nv.invoke_n(sim_b, 21)                     # one batch: 22 passes
     assert (nv.launch_count() - launches) / (1 if case == "tgv_bgk" else 2) == 22
     nv.invoke_n(sim_b, 16); nv.invoke_n(sim_b, 17)          # even and odd batch lengths
-    diff = max_rel(get_f(flow_b), get_f(flow_a))
-    assert diff < 2e-6
-    print(f"lazy POST vs push, {case}: max relative difference {diff:.1e}")
+    assert torch.equal(flow_a.f, flow_b.f)
 
 
 # ------------------------------------------------------------------ further flows on the same kernels
