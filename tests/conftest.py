@@ -13,6 +13,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no liblbm_b200.so (built artefacts are git-ignored): build it once, with nvcc
+    # cross-compiling for sm_100a; an existing library is used as is (the GPU box receives the prebuilt one)
+    from lettuce_b200 import build as _build
+    if not os.path.exists(_build.LIB):
+        _build.build()
 
 
 def load_golden(name):
