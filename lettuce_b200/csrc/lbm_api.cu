@@ -40,8 +40,7 @@ static int launch_step(const StepParams<R> &p, int coll, int streaming, bool mas
 }
 
 template <class S, class R>
-static const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int variant) {
-    if (S::Q == 9 && (variant == 2 || variant == 4)) return masked ? "multi_masked+general_nodes" : "multi";
+static const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int) {
     return masked ? "scalar_masked+general_nodes" : "scalar";
 }
 

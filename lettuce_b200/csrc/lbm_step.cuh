@@ -12,7 +12,6 @@
 //                        launched right before the bulk kernel, which overlaps it (programmatic
 //                        dependent launch); the two kernels write disjoint slots
 //   step_sync_kernel     bulk kernel for multi-GPU slabs with the in-kernel lock step (SlabSync)
-//   step_multi_kernel    experimental 2/4-nodes-per-thread bulk kernel for D2Q9
 //
 // Planes x = -1 and x = n0 resolve to the wrapped plane of the same buffer (single GPU) or to a
 // peer-mapped plane of the neighbour rank's buffer (in_plane / out_plane).
@@ -390,77 +389,6 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
                 __threadfence_system();
                 *(volatile unsigned long long *)(lo ? p.sync.sig_lo : p.sync.sig_hi) = p.sync.signal_value;
             }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// multi-node bulk kernel (small stencils): threadIdx.x runs along the contiguous axis, so every warp access is a contiguous
-// 128-byte segment (shifted by one element for e_z != 0).  A thread owns NPT nodes of one row,
-// blockDim.x apart; all their loads are issued before the first collision, which gives small
-// stencils (D2Q9: 9 loads per node) enough bytes in flight to cover HBM latency.
-// ---------------------------------------------------------------------------
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED, int NPT>
-__global__ void __launch_bounds__(256) step_multi_kernel(const __grid_constant__ StepParams<R> p) {
-    constexpr int Q = S::Q;
-    const int z0 = blockIdx.x * (blockDim.x * NPT) + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
-    if (y >= p.n1) return;
-    const int64_t rowbase = (int64_t)y * p.n2;
-
-    // neighbour rows with periodic wrap (torch.roll, _simulation.py:241-243)
-    const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
-
-    R f[NPT][Q];
-    bool active[NPT];
-#pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        const int z = z0 + k * blockDim.x;
-        active[k] = z < p.n2;
-        if (MASKED && active[k]) {
-            // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
-            // bit 7 and are left to general_nodes_kernel; every output slot still has one writer.
-            active[k] = p.labels[(int64_t)x * p.n1 * p.n2 + rowbase + z] == p.collision_index;
-        }
-        if (!active[k]) continue;
-        if (PULL) {
-            const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
-            const Plane<R, const R> pl[3] = {in_plane(p, x + 1), in_plane(p, x), in_plane(p, x - 1)};  // e0+1 -> x-e0
-            ForQ<Q>::run([&]<int q>() {
-                constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-                const int ys = e1 == 0 ? y : (e1 == 1 ? ym : yp);
-                const int zs = e2 == 0 ? z : (e2 == 1 ? zm : zp);
-                const auto &s = pl[e0 + 1];
-                f[k][q] = __ldg(s.p + (q * s.qs + (int64_t)ys * p.n2 + zs));
-            });
-        } else {
-            const R *src = p.in + (int64_t)x * p.n1 * p.n2 + rowbase + z;
-            ForQ<Q>::run([&]<int q>() { f[k][q] = __ldg(src + q * p.N); });
-        }
-    }
-
-#pragma unroll
-    for (int k = 0; k < NPT; ++k)
-        if (active[k]) collide_node<S, R, COLL>(p, f[k]);
-
-#pragma unroll
-    for (int k = 0; k < NPT; ++k) {
-        if (!active[k]) continue;
-        const int z = z0 + k * blockDim.x;
-        if (PUSH) {
-            const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
-            const Plane<R, R> pl[3] = {out_plane(p, x - 1), out_plane(p, x), out_plane(p, x + 1)};  // e0+1 -> x+e0
-            ForQ<Q>::run([&]<int q>() {
-                constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-                const int yd = e1 == 0 ? y : (e1 == 1 ? yp : ym);
-                const int zd = e2 == 0 ? z : (e2 == 1 ? zp : zm);
-                const auto &d = pl[e0 + 1];
-                d.p[q * d.qs + (int64_t)yd * p.n2 + zd] = f[k][q];
-            });
-        } else {
-            R *dst = p.out + (int64_t)x * p.n1 * p.n2 + rowbase + z;
-            ForQ<Q>::run([&]<int q>() { dst[q * p.N] = f[k][q]; });
         }
     }
 }

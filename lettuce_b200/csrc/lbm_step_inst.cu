@@ -16,22 +16,21 @@ namespace lbm {
 
 namespace {
 
-// Nodes per thread for the small stencil.  Measured on B200 (C4, 4096x1024 fp32, PRE): 1 node per thread
-// 65.8 GLUPS, 4 nodes per thread 55.5 GLUPS -- more loads in flight per thread do not pay, occupancy does.
-// desc->variant = 2 or 4 selects the multi-node kernel for experiments; 0 / 1 = one node per thread.
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED, int NPT>
-int launch_bulk(const StepParams<R> &p, cudaStream_t stream) {
+// One node per thread.  (A 2- and 4-nodes-per-thread variant for D2Q9 was measured on B200 -- C4, 4096x1024 fp32,
+// PRE: 65.8 GLUPS with one node per thread, 64.6 with two, 55.5 with four -- and removed: occupancy pays, more
+// loads in flight per thread do not.)
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
+int launch_scalar(const StepParams<R> &p, int variant, cudaStream_t stream) {
+    (void)variant;
     // threadIdx.x runs along the contiguous axis; fill the block up to 256 threads with rows.
     int tz = 32;
-    while (tz * NPT < p.n2 && tz < 256) tz <<= 1;
+    while (tz < p.n2 && tz < 256) tz <<= 1;
     int ty = 256 / tz;
     while (ty > 1 && ty / 2 >= p.n1) ty >>= 1;
     dim3 block(tz, ty, 1);
-    dim3 grid((p.n2 + tz * NPT - 1) / (tz * NPT), (p.n1 + ty - 1) / ty, p.n0);
-    void (*bulk)(const StepParams<R>) = nullptr;
-    if constexpr (NPT == 1) bulk = step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED>;
-    else bulk = step_multi_kernel<S, R, COLL, PULL, PUSH, MASKED, NPT>;
-    if constexpr (!MASKED && NPT == 1) {
+    dim3 grid((p.n2 + tz - 1) / tz, (p.n1 + ty - 1) / ty, p.n0);
+    void (*bulk)(const StepParams<R>) = step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED>;
+    if constexpr (!MASKED) {
         if (p.sync.on) {       // multi-GPU slab with in-kernel lock step (lbm_slab_step_n)
             StepParams<R> ps = p;
             ps.sync.ctas_per_side = grid.x * grid.y * ((PULL && PUSH) ? 2 : 1);
@@ -68,16 +67,6 @@ int launch_bulk(const StepParams<R> &p, cudaStream_t stream) {
     bulk<<<grid, block, 0, stream>>>(p);
     ++g_launch_count;
     return (int)cudaGetLastError();
-}
-
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
-int launch_scalar(const StepParams<R> &p, int variant, cudaStream_t stream) {
-    if constexpr (S::Q == 9) {
-        if (p.sync.on) variant = 0;
-        if (variant == 2) return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 2>(p, stream);
-        if (variant == 4) return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 4>(p, stream);
-    }
-    return launch_bulk<S, R, COLL, PULL, PUSH, MASKED, 1>(p, stream);
 }
 
 template <class S, class R, int COLL, bool MASKED>

@@ -247,7 +247,7 @@ class Engine:
         self.desc.streaming = int(simulation.streaming_strategy.value)
         self.desc.n_ops = len(transformer)
         self.desc.collision_index = int(simulation.collision_index)
-        self.desc.variant = int(os.environ.get("LBM_B200_VARIANT", "0"))
+        self.desc.variant = 0
         self._keep: List[torch.Tensor] = []     # tensors whose pointers the descriptor borrows
         self.transformer = transformer
         for i, op in enumerate(transformer):

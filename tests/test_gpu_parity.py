@@ -492,19 +492,6 @@ def test_ragged_lattices_match_oracle(stencil, res, strategy):
     assert max_rel(get_f(flow), ref) < 1e-12
 
 
-def test_d2q9_multi_node_variants_match(monkeypatch):
-    """the 2- and 4-nodes-per-thread kernels (desc.variant) give the same bits as the default kernel"""
-    ctx = cuda_ctx(torch.float32)
-    results = []
-    for variant in ("0", "2", "4"):
-        monkeypatch.setenv("LBM_B200_VARIANT", variant)
-        flow = make_obstacle(ObstacleEqOut, ctx, [96, 200], lt.D2Q9())
-        sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
-        sim(7)
-        results.append(flow.f.clone())
-    assert torch.equal(results[0], results[1]) and torch.equal(results[0], results[2])
-
-
 # ------------------------------------------------------------------ size-independent properties at BASELINE sizes
 def test_streaming_round_trip_is_bit_exact_at_full_size():
     """Pure streaming is a permutation: after lcm(resolution) steps every population is back
