@@ -12,6 +12,7 @@ into x-slabs).  Prints ONE JSON line:
             the final populations are downloaded -- all inside the timed region
   roofline  algorithmic bytes (2*q*4 B per node update) / measured launch duration vs the measured
             HBM copy bandwidth in MEASURED_PEAKS.json
+  torch_gpu_port the reference's torch path restated op for op (oracle/torch_port.py), timed on the same GPU
   cpu_baseline   the NumPy oracle port of the reference's algorithm timed on this box's host cores
                  on a bounded sample (smaller lattice, same workload)
 
@@ -134,6 +135,26 @@ def cpu_arm(steps: int, warmup: int, budget_s: float):
     return {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port",
             "sample": f"TGV3D D3Q19 BGK fp32 {n}^3, {steps} steps, PRE_STREAMING, NumPy oracle with a {cores}-thread "
                       f"pool (host has {os.cpu_count()} cores)"}, dt / steps * 1e3
+
+
+def torch_gpu_port(f0, tau, steps, strategy, dev):
+    """MLUPS of oracle/torch_port.py (lettuce's sequence of full-size torch ops) on the GPU, explicit syncs."""
+    import torch
+    from oracle.torch_port import TorchBGK
+    port = TorchBGK("D3Q19", tau, dev, torch.float32)
+    f = f0.clone()
+    f = port.step(f, strategy)                                  # warm-up (allocator, cuBLAS handles)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f = port.step(f, strategy)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    nodes = f0[0].numel()
+    assert torch.isfinite(f).all()
+    return {"value": steps * nodes / 1e6 / dt, "unit": "MLUPS", "kind": "port", "steps": steps,
+            "what": "oracle/torch_port.py: the reference's torch path restated op for op (sum, einsum, elementwise "
+                    "equilibrium temporaries, one torch.roll per population), fp32 on this GPU, device-synchronised"}
 
 
 def reference_main(args):
@@ -270,6 +291,13 @@ def gpu_main(args):
            "h2d_bytes_per_step": fbytes * world / args.steps, "d2h_bytes_per_step": fbytes * world / args.steps + 8,
            "note": how + "; transfers amortised over K steps"}
 
+    torch_port = None
+    if world == 1 and not args.slab:
+        # the reference's torch GPU path (restated, see oracle/torch_port.py) on the same lattice, for context
+        try:
+            torch_port = torch_gpu_port(flow.f, flow.units.relaxation_parameter_lu, 10, args.strategy, dev)
+        except torch.OutOfMemoryError:
+            torch_port = {"unavailable": "out of memory"}
     if world > 1:
         # orderly teardown on every rank: unmap the neighbours' buffers, then leave the process group together
         sim.close()
@@ -293,6 +321,8 @@ def gpu_main(args):
             "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_arm(steps=3, warmup=1, budget_s=20.0)
+    if torch_port is not None:
+        line["torch_gpu_port"] = torch_port
     print(json.dumps(line))
 
 
