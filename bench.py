@@ -228,18 +228,19 @@ def gpu_main(args):
         stop.record()
         barrier()
         launches = native.launch_count() - launches0
-        # the timed region is only tens of milliseconds: keep the same kernel running (untimed) for
-        # about half a second so that the 50 ms clock samples are taken under this load
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
-            stepper(20 if args.steps >= 20 else 2 * ((args.steps + 1) // 2))
-            torch.cuda.synchronize(dev)
+        ms = start.elapsed_time(stop)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        # The timed region is only tens of milliseconds: keep the same kernel running (untimed) for about half
+        # a second so that the 50 ms clock samples are taken under this load.  The number of extra batches is
+        # derived from the all-reduced time, i.e. identical on every rank (slabs advance in lock step).
+        batch = 20 if args.steps >= 20 else 2 * ((args.steps + 1) // 2)
+        for _ in range(int(600.0 / max(ms / args.steps * batch, 1e-3)) + 1):
+            stepper(batch)
+        torch.cuda.synchronize(dev)
         barrier()
-    ms = start.elapsed_time(stop)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     mlups = args.steps * nodes_total / 1e6 / (ms * 1e-3)
     assert torch.isfinite(flow.f).all()
 
@@ -247,52 +248,53 @@ def gpu_main(args):
                    else "step_sync (slab, in-kernel lock step)")
     # ---- e2e: HOST populations in, HOST populations out, every step's kinetic energy read back
     e2e = None
-    f_host = torch.empty(flow.f.shape, dtype=torch.float32).pin_memory()
-    f_host.copy_(flow.f)
-    out_host = torch.empty_like(f_host).pin_memory()
-    fbytes = f_host.numel() * 4
-    if world == 1:
-        # N = 1: one call of the C ABI's host-buffer entry
-        import ctypes as C
-        energy = torch.zeros(args.steps, dtype=torch.float64).pin_memory()
-        eng = native.engine_of(sim)
-        torch.cuda.synchronize(dev)
-        native.check(native.lib().lbm_run_host(C.byref(eng.desc), f_host.data_ptr(), out_host.data_ptr(), 1, None))
-        dt = float("inf")
-        for _ in range(2):      # host-side noise (page placement, PCIe contention) is large: best of two calls
+    if not args.no_e2e:
+        f_host = torch.empty(flow.f.shape, dtype=torch.float32).pin_memory()
+        f_host.copy_(flow.f)
+        out_host = torch.empty_like(f_host).pin_memory()
+        fbytes = f_host.numel() * 4
+        if world == 1:
+            # N = 1: one call of the C ABI's host-buffer entry
+            import ctypes as C
+            energy = torch.zeros(args.steps, dtype=torch.float64).pin_memory()
+            eng = native.engine_of(sim)
+            torch.cuda.synchronize(dev)
+            native.check(native.lib().lbm_run_host(C.byref(eng.desc), f_host.data_ptr(), out_host.data_ptr(), 1, None))
+            dt = float("inf")
+            for _ in range(2):      # host-side noise (page placement, PCIe contention) is large: best of two calls
+                t0 = time.perf_counter()
+                native.check(native.lib().lbm_run_host(C.byref(eng.desc), f_host.data_ptr(), out_host.data_ptr(),
+                                                       args.steps, energy.data_ptr()))
+                dt = min(dt, time.perf_counter() - t0)
+            assert torch.isfinite(energy).all() and float(energy[-1]) > 0
+            how = "lbm_run_host (C ABI): pinned host f uploaded, K steps, kinetic energy read back every step, final f downloaded"
+        else:
+            # N > 1: the public Python API on every rank's slab -- upload, Simulation(K) with a global
+            # kinetic-energy reporter of interval 1 (reduce kernel + all-reduce + D2H per step), download
+            from lettuce_b200 import slab
+            rep = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=1, out=None)
+            sim.reporter.append(rep)
+            flow.i = 1                      # skip the step-0 report so exactly K reports fall in the timed region
+            barrier()
             t0 = time.perf_counter()
-            native.check(native.lib().lbm_run_host(C.byref(eng.desc), f_host.data_ptr(), out_host.data_ptr(),
-                                                   args.steps, energy.data_ptr()))
-            dt = min(dt, time.perf_counter() - t0)
-        assert torch.isfinite(energy).all() and float(energy[-1]) > 0
-        how = "lbm_run_host (C ABI): pinned host f uploaded, K steps, kinetic energy read back every step, final f downloaded"
-    else:
-        # N > 1: the public Python API on every rank's slab -- upload, Simulation(K) with a global
-        # kinetic-energy reporter of interval 1 (reduce kernel + all-reduce + D2H per step), download
-        from lettuce_b200 import slab
-        rep = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=1, out=None)
-        sim.reporter.append(rep)
-        flow.i = 1                      # skip the step-0 report so exactly K reports fall in the timed region
-        barrier()
-        t0 = time.perf_counter()
-        native.engine_of(sim).load(f_host.to(dev, non_blocking=True))
-        sim(args.steps)
-        out_host.copy_(flow.f, non_blocking=True)
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        assert len(rep.out) == args.steps and rep.out[-1][2] > 0
-        sim.reporter.pop()
-        how = ("public API per rank: pinned host slab uploaded, Simulation(K) with a global kinetic-energy reporter "
-               "(interval 1: reduce + all-reduce + D2H), final slab downloaded; wall clock, max over ranks")
-    e2e = {"value": args.steps * nodes_total / 1e6 / dt, "unit": "MLUPS",
-           "h2d_bytes_per_step": fbytes * world / args.steps, "d2h_bytes_per_step": fbytes * world / args.steps + 8,
-           "note": how + "; transfers amortised over K steps"}
+            native.engine_of(sim).load(f_host.to(dev, non_blocking=True))
+            sim(args.steps)
+            out_host.copy_(flow.f, non_blocking=True)
+            barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            assert len(rep.out) == args.steps and rep.out[-1][2] > 0
+            sim.reporter.pop()
+            how = ("public API per rank: pinned host slab uploaded, Simulation(K) with a global kinetic-energy reporter "
+                   "(interval 1: reduce + all-reduce + D2H), final slab downloaded; wall clock, max over ranks")
+        e2e = {"value": args.steps * nodes_total / 1e6 / dt, "unit": "MLUPS",
+               "h2d_bytes_per_step": fbytes * world / args.steps, "d2h_bytes_per_step": fbytes * world / args.steps + 8,
+               "note": how + "; transfers amortised over K steps"}
 
     torch_port = None
-    if world == 1 and not args.slab:
+    if world == 1 and not args.slab and not args.no_e2e:
         # the reference's torch GPU path (restated, see oracle/torch_port.py) on the same lattice, for context
         try:
             torch_port = torch_gpu_port(flow.f, flow.units.relaxation_parameter_lu, 10, args.strategy, dev)
@@ -336,6 +338,7 @@ def main():
     ap.add_argument("--strategy", default="PRE_STREAMING",
                     choices=["NO_STREAMING", "PRE_STREAMING", "POST_STREAMING", "DOUBLE_STREAMING"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large --size)")
     ap.add_argument("--slab", action="store_true",
                     help="with --gpus 1: run the multi-GPU slab kernel (in-kernel lock step) with the rank as its own "
                          "neighbour, e.g. to profile it under ncu")
