@@ -249,6 +249,7 @@ class Engine:
         self.desc.collision_index = int(simulation.collision_index)
         self.desc.variant = 0
         self._keep: List[torch.Tensor] = []     # tensors whose pointers the descriptor borrows
+        self._eq_state = {}                     # EquilibriumBoundaryPU entries: converted tensors + source versions
         self.transformer = transformer
         for i, op in enumerate(transformer):
             self._fill_op(i, op)
@@ -278,14 +279,12 @@ class Engine:
         if kind == OP_REGULARIZED:
             op.tau = units.relaxation_parameter_lu      # regularized_collision.py:19, same quirk
         if kind == OP_EQUILIBRIUM:
-            rho = units.convert_pressure_pu_to_density_lu(op.pressure)
-            u = units.convert_velocity_to_lu(op.velocity)
-            rho = rho.to(device=self.device, dtype=flow.f.dtype).contiguous()
-            u = u.to(device=self.device, dtype=flow.f.dtype).contiguous()
+            rho, u = self._equilibrium_boundary_values(op)
             d = flow.stencil.d
             if rho.dim() != d + 1 or u.dim() != d + 1 or rho.shape[0] != 1:
                 raise ValueError("EquilibriumBoundaryPU needs pressure of shape [1,...] and velocity [d or 1,...]")
             self._keep += [rho, u]
+            self._eq_state[i] = (rho, u, self._tensor_key(op.pressure), self._tensor_key(op.velocity))
             o.rho, o.u = rho.data_ptr(), u.data_ptr()
             for a in range(d):
                 o.rho_stride[a] = rho.stride(a + 1) if rho.shape[a + 1] > 1 else 0
@@ -301,9 +300,32 @@ class Engine:
             if kind == OP_OUTLET_P:
                 o.p0 = float(op.rho_outlet)
 
+    @staticmethod
+    def _tensor_key(t):
+        return (id(t), getattr(t, "_version", None))
+
+    def _equilibrium_boundary_values(self, op):
+        """density and velocity of an EquilibriumBoundaryPU in lattice units, lattice dtype, on the device"""
+        units, f = self.flow.units, self.flow.f
+        rho = units.convert_pressure_pu_to_density_lu(op.pressure)
+        u = units.convert_velocity_to_lu(op.velocity)
+        return (rho.to(device=self.device, dtype=f.dtype).contiguous(),
+                u.to(device=self.device, dtype=f.dtype).contiguous())
+
     def refresh_parameters(self):
-        """Re-read scalar operator parameters (the reference passes 1/tau on every call,
-        cuda_native/ext/_collision/bgk_collision.py:29-33)."""
+        """Re-read operator parameters before a launch, like the reference's generated call does on every step
+        (cuda_native/ext/_collision/bgk_collision.py:29-33, ext/_boundary/equilibrium_pu.py:15-18,55-58): scalars
+        are copied, tensors (inlet velocity / pressure, acceleration) only when they were replaced or modified in
+        place (torch's version counter), so the common case costs no device work."""
+        for i, (rho, u, pkey, ukey) in self._eq_state.items():
+            op = self.transformer[i]
+            if (self._tensor_key(op.pressure), self._tensor_key(op.velocity)) != (pkey, ukey):
+                new_rho, new_u = self._equilibrium_boundary_values(op)
+                if new_rho.shape != rho.shape or new_u.shape != u.shape:
+                    raise RuntimeError("EquilibriumBoundaryPU changed the shape of its velocity / pressure; "
+                                       "create a new Simulation")
+                rho.copy_(new_rho); u.copy_(new_u)          # same storage: the descriptor's pointers stay valid
+                self._eq_state[i] = (rho, u, self._tensor_key(op.pressure), self._tensor_key(op.velocity))
         for i, op in enumerate(self.transformer):
             o = self.desc.ops[i]
             if o.kind == OP_BGK:

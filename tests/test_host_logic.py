@@ -248,3 +248,33 @@ def test_descriptor_validation_without_gpu():
     d.ops[2].kind, d.ops[2].axis, d.ops[2].side = native.OP_OUTLET_P, 1, 1
     d.labels, d.frozen = 1 << 20, 1 << 21
     assert L.lbm_step(ctypes.byref(d), 1 << 22, 1 << 30, None) == -2          # outlets on two axes
+
+
+def test_equilibrium_boundary_parameters_are_re_read_when_modified():
+    """the reference converts the inlet velocity / pressure on every step (cuda_native/ext/_boundary/
+    equilibrium_pu.py:15-18,55-58); the engine re-converts them when the tensors change"""
+    ctx = cpu()
+    boundaries = []
+
+    class F(lt.TaylorGreenVortex):
+        @property
+        def post_boundaries(self):
+            if not boundaries:
+                m = torch.zeros(self.resolution, dtype=torch.bool); m[0] = True
+                boundaries.append(lt.EquilibriumBoundaryPU(self.context, self, m, velocity=[0.5, 0.0], pressure=0.1))
+            return boundaries
+
+    flow = F(ctx, [8, 8], 10.0, 0.05, stencil=lt.D2Q9())
+    sim = lt.Simulation(flow, lt.NoCollision(), [])
+    eng = native.Engine(sim, dry=True)
+    rho, u = eng._eq_state[1][:2]
+    u_before, ptr = u.clone(), eng.desc.ops[1].u
+    eng.refresh_parameters()
+    assert torch.equal(u, u_before)
+    boundaries[0].velocity[0] = 1.0                       # in-place edit bumps the version counter
+    eng.refresh_parameters()
+    assert torch.allclose(u.flatten()[0], flow.units.convert_velocity_to_lu(torch.tensor(1.0, dtype=u.dtype)))
+    assert eng.desc.ops[1].u == ptr                       # same storage, descriptor still valid
+    boundaries[0].pressure = boundaries[0].pressure * 2   # replaced tensor
+    eng.refresh_parameters()
+    assert torch.allclose(rho.flatten()[0], flow.units.convert_pressure_pu_to_density_lu(torch.tensor(0.2, dtype=rho.dtype)))
