@@ -166,7 +166,8 @@ int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, v
  * (`no_collision_mask` uint8 [nx,ny,nz] and `no_streaming_mask` uint8 [q,nx,ny,nz],
  * lettuce/_simulation.py:100-146).  label = ncm value, with bit 7 set on every node
  * that needs the general path: a label other than the collision's, a frozen slot of its own,
- * a neighbour slot it would stream into that is frozen, or membership in an outlet plane of `desc`. */
+ * a neighbour slot it would stream into that is frozen, or membership in an outlet plane of `desc`.
+ * Set-up call: it waits for `stream` before returning (its small staging buffer lives on the caller's stack). */
 int lbm_pack_masks(const lbm_step_desc *desc, const uint8_t *d_ncm, const uint8_t *d_nsm,
                    uint8_t *d_labels, uint32_t *d_frozen, void *stream);
 

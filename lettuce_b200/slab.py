@@ -286,6 +286,7 @@ class SlabEngine(native.Engine):
             dist.barrier(group=self.group)
         self.flow.f = self.flow.f.clone()
         self.flow._f_next = None
+        self.t = None                      # the tensors below alias memory that is about to be freed
         for b in self.buf + [self.flags]:
             b.free()
 
