@@ -43,7 +43,7 @@ def test_decomposition_ranges():
 def test_slab_initial_state_and_ring_exchange_gloo(world):
     import slab_worker
     port = free_port()
-    with mp.Manager() as mgr:
+    with mp.get_context("spawn").Manager() as mgr:
         results = mgr.dict()
         mp.spawn(slab_worker.cpu_worker, args=(world, port, results), nprocs=world, join=True)
         assert len(results) == world
