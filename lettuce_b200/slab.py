@@ -310,7 +310,8 @@ class SlabSimulation(Simulation):
                  decomposition: Optional[SlabDecomposition] = None, group=None):
         self.decomposition = decomposition or flow.decomposition
         super().__init__(flow, collision, reporter, streaming_strategy)
-        self._b200_engine = SlabEngine(self, self.decomposition, group)
+        # the engine maps the neighbours' GPU buffers; on a CPU context only the host side (masks) exists
+        self._b200_engine = SlabEngine(self, self.decomposition, group) if flow.f.is_cuda else None
 
     def _build_masks(self):
         dec = self.decomposition
@@ -327,7 +328,8 @@ class SlabSimulation(Simulation):
         return super()._boundary_masks(boundary, shape)
 
     def close(self):
-        self._b200_engine.close()
+        if self._b200_engine is not None:
+            self._b200_engine.close()
 
 
 class _GlobalReduce(Observable):

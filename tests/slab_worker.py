@@ -195,6 +195,26 @@ def cpu_worker(rank, world, port, results):
                 g = lo.step(st, g, coll)
             whole = gather_slabs(torch.from_numpy(np.ascontiguousarray(f)), dec, dev).numpy()
             out[name + "_step"] = float(np.abs(whole - g).max())
+        # boundaries on slabs: every rank's local label / no-stream masks are the slices of the global ones,
+        # with the x-normal outlet active only on the rank that owns the plane
+        for name, cls, res in (("D2Q9", lt.D2Q9, [24, 16]), ("D3Q19", lt.D3Q19, [12, 8, 8])):
+            dec = slab.SlabDecomposition(res[0], world, rank)
+            D = res[1] / 8
+            flow = SlabObstacleEqOut(ctx, res, 100, 0.05, res[0] / D, dec, stencil=cls())
+            flow.mask = _solid(flow, flow.global_extent_pu)
+            sim = slab.SlabSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [],
+                                      lt.StreamingStrategy.POST_STREAMING, dec)
+            one = ObstacleEqOut(ctx, res, 100, 0.05, res[0] / D, stencil=cls())
+            one.mask = _solid(one, [gi.max() for gi in one.grid])
+            ref = lt.Simulation(one, lt.BGKCollision(one.units.relaxation_parameter_lu), [])
+            sl = dec.local_slice()
+            out[name + "_mask"] = float((flow.mask.to(torch.uint8) != one.mask[sl].to(torch.uint8)).sum())
+            out[name + "_ncm"] = float((sim.no_collision_mask != ref.no_collision_mask[sl]).sum())
+            out[name + "_nsm"] = float((sim.no_streaming_mask != ref.no_streaming_mask[:, sl]).sum())
+            owner = rank == world - 1
+            assert [getattr(b, "_slab_disabled", False) for b in sim.post_boundaries] == [False, not owner, False]
+            d = lt.native.describe(sim)
+            assert d["ops"][2]["side"] == (1 if owner else 0)
         results[rank] = out
     finally:
         dist.destroy_process_group()
