@@ -156,6 +156,16 @@ typedef struct lbm_step_desc {
  * f_out once.  f_in and f_out must not overlap.  Launches on `stream`, does not sync. */
 int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream);
 
+/* One time step that also returns the kinetic energy sum 0.5|u|^2 (lattice units) of the state it writes:
+ * the IncompressibleKineticEnergy reporter (ext/_reporter/observable_reporter.py:34-42 with
+ * lettuce/_flow.py:200-204) fused into the step kernel, so that a reporter with interval 1 costs no second pass
+ * over the populations.  Available for steps without boundaries that do not stream after the collide phase
+ * (NO_STREAMING, PRE_STREAMING); otherwise LBM_ERR_UNSUPPORTED (use lbm_step + lbm_reduce).  `d_scratch` needs
+ * lbm_step_energy_scratch_bytes(desc) bytes (0 = not available for desc); *d_energy receives one double. */
+size_t lbm_step_energy_scratch_bytes(const lbm_step_desc *desc);
+int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
+                    size_t scratch_bytes, double *d_energy, void *stream);
+
 /* `n` consecutive steps ping-ponging between two buffers (a -> b -> a ...), without returning
  * to the caller in between: the loop `for _ in range(num_steps)` of Simulation.__call__
  * (lettuce/_simulation.py:317-318) when no reporter is due.  The newest populations end up in

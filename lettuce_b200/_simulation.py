@@ -128,6 +128,19 @@ class Simulation:
             k = min(k, interval - self.flow.i % interval)
         return max(k, 1)
 
+    def _energy_reporter_due(self, k: int) -> bool:
+        """True when, `k` steps from now, a reporter evaluates an observable that the step kernel can reduce on
+        the fly (`fused_with_step`, i.e. IncompressibleKineticEnergy of this flow) and the engine has that
+        kernel for this simulation (no boundaries, no stream after the collide phase)."""
+        if self._collide_and_stream is not native.invoke or not self.flow.f.is_cuda:
+            return False
+        for r in self.reporter:
+            obs = getattr(r, "observable", None)
+            if (getattr(obs, "fused_with_step", False) and getattr(obs, "flow", None) is self.flow
+                    and (self.flow.i + k) % max(int(r.interval), 1) == 0):
+                return native.engine_of(self).energy_fusable()
+        return False
+
     def __call__(self, num_steps: int) -> float:
         """Run `num_steps` time steps; returns MLUPS (lettuce/_simulation.py:311-323).  The
         device is synchronised before the clock is read."""
@@ -138,7 +151,11 @@ class Simulation:
         remaining = int(num_steps)
         while remaining > 0:
             k = self._batch_length(remaining)
-            if k == 1:
+            if self._energy_reporter_due(k):
+                if k > 1:
+                    native.invoke_n(self, k - 1)
+                native.engine_of(self).step_with_energy()
+            elif k == 1:
                 self._collide_and_stream(self)
             else:
                 native.invoke_n(self, k)

@@ -17,6 +17,7 @@ template <class S, class R>
 int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, int n2, double *partials, double *out,
                   cudaStream_t st);
 size_t reduce_scratch_bytes();
+int launch_fold_sum(const double *partials, int n, double *stage, double *out, cudaStream_t st);
 template <class S, class R>
 int launch_equilibrium(const R *rho, const int64_t *rs, const R *u, const int64_t *us, int n0, int n1, int n2, R *f,
                        cudaStream_t stream);
@@ -53,6 +54,8 @@ static int cuda_fail(int e) {
 
 int cuda_fail_public(int e) { return cuda_fail(e); }
 int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream);
+int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync,
+                 double *energy_partials, void *stream);
 
 struct Dims {
     int n0, n1, n2, d, q;
@@ -190,10 +193,11 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
 
 template <class S, class R>
 static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, const SlabSync *sync,
-                      cudaStream_t st) {
+                      double *energy_partials, cudaStream_t st) {
     StepParams<R> p;
     fill_params<S, R>(d, dm, f_in, f_out, p);
     if (sync) p.sync = *sync;
+    p.energy_partials = energy_partials;
     const bool masked = d->n_ops > 1;
     return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, d->variant, st));
 }
@@ -316,6 +320,12 @@ int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void 
 namespace lbm {
 // lbm_step plus the optional in-kernel slab lock step (used by lbm_slab_step_n)
 int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream) {
+    return step_general(desc, d_f_in, d_f_out, sync, nullptr, stream);
+}
+
+// lbm_step plus the optional in-kernel slab lock step (lbm_slab_step_n) or fused energy partials (lbm_step_energy)
+int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync,
+                 double *energy_partials, void *stream) {
     Dims dm;
     int rc = validate_desc(desc, dm);
     if (rc) return rc;
@@ -324,12 +334,38 @@ int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out,
     const char *a = (const char *)d_f_in, *b = (const char *)d_f_out;
     if (a < b + bytes && b < a + bytes) return LBM_ERR_ALIASING;
     LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype,
-                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, sync, (cudaStream_t)stream)));
+                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, sync, energy_partials, (cudaStream_t)stream)));
     return LBM_ERR_BAD_ARGUMENT;
 }
 }  // namespace lbm
 
 extern "C" {
+
+static bool energy_fusable(const lbm_step_desc *desc) {
+    return desc && desc->n_ops == 1 && !(desc->streaming & LBM_POST_STREAMING);
+}
+
+size_t lbm_step_energy_scratch_bytes(const lbm_step_desc *desc) {
+    Dims dm;
+    if (!desc || lattice_dims(&desc->lat, dm) || !energy_fusable(desc)) return 0;
+    dim3 grid, block;
+    bulk_geometry(dm.n0, dm.n1, dm.n2, grid, block);
+    // one partial per CTA of the step kernel + the staging area of the two-stage fold
+    return sizeof(double) * (size_t)grid.x * grid.y * grid.z + reduce_scratch_bytes();
+}
+
+int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
+                    size_t scratch_bytes, double *d_energy, void *stream) {
+    if (!d_scratch || !d_energy) return LBM_ERR_BAD_ARGUMENT;
+    if (!energy_fusable(desc)) return LBM_ERR_UNSUPPORTED;
+    const size_t need = lbm_step_energy_scratch_bytes(desc);
+    if (need == 0 || scratch_bytes < need) return LBM_ERR_BAD_ARGUMENT;
+    const int rc = step_general(desc, d_f_in, d_f_out, nullptr, (double *)d_scratch, stream);
+    if (rc) return rc;
+    const int n_partials = (int)((need - reduce_scratch_bytes()) / sizeof(double));
+    return cuda_fail(launch_fold_sum((const double *)d_scratch, n_partials, (double *)d_scratch + n_partials, d_energy,
+                                     (cudaStream_t)stream));
+}
 
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream) {
     if (n < 0) return LBM_ERR_BAD_ARGUMENT;
@@ -445,17 +481,22 @@ int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int6
         cudaStreamDestroy(st);
         return code;
     };
+    // non-pushing steps without boundaries reduce the energy inside the step kernel (lbm_step_energy)
+    const size_t fused_bytes = h_energy ? lbm_step_energy_scratch_bytes(desc) : 0;
+    const size_t scratch_bytes = fused_bytes > reduce_scratch_bytes() ? fused_bytes : reduce_scratch_bytes();
     if ((e = (int)cudaMalloc(&a, bytes)) || (e = (int)cudaMalloc(&b, bytes)) ||
-        (e = (int)cudaMalloc(&scratch, reduce_scratch_bytes())) || (e = (int)cudaMalloc(&d_e, sizeof(double))))
+        (e = (int)cudaMalloc(&scratch, scratch_bytes)) || (e = (int)cudaMalloc(&d_e, sizeof(double))))
         return cleanup(cuda_fail(e));
     if ((e = (int)cudaMemcpyAsync(a, h_f, bytes, cudaMemcpyHostToDevice, st))) return cleanup(cuda_fail(e));
     for (int64_t k = 0; k < nsteps; ++k) {
-        rc = lbm_step(desc, a, b, st);
+        rc = fused_bytes ? lbm_step_energy(desc, a, b, scratch, scratch_bytes, d_e, st) : lbm_step(desc, a, b, st);
         if (rc) return cleanup(rc);
         void *t = a; a = b; b = t;
         if (h_energy) {
-            rc = lbm_reduce(&desc->lat, LBM_SUM_HALF_U2, a, nullptr, scratch, d_e, st);
-            if (rc) return cleanup(rc);
+            if (!fused_bytes) {
+                rc = lbm_reduce(&desc->lat, LBM_SUM_HALF_U2, a, nullptr, scratch, d_e, st);
+                if (rc) return cleanup(rc);
+            }
             // result of this step read back to the host (reporter with interval 1)
             if ((e = (int)cudaMemcpyAsync(h_energy + k, d_e, sizeof(double), cudaMemcpyDeviceToHost, st)))
                 return cleanup(cuda_fail(e));

@@ -8,6 +8,17 @@ namespace lbm {
 
 extern int64_t g_launch_count;
 
+// launch geometry of the bulk kernels: threadIdx.x along the contiguous axis, blocks of up to 256 threads
+// filled with rows, one grid layer per x-plane
+inline void bulk_geometry(int n0, int n1, int n2, dim3 &grid, dim3 &block) {
+    int tz = 32;
+    while (tz < n2 && tz < 256) tz <<= 1;
+    int ty = 256 / tz;
+    while (ty > 1 && ty / 2 >= n1) ty >>= 1;
+    block = dim3(tz, ty, 1);
+    grid = dim3((n2 + tz - 1) / tz, (n1 + ty - 1) / ty, n0);
+}
+
 // returns cudaError_t as int (0 = success) or a negative lbm_status; defined in lbm_step_inst.cu
 template <class S, class R, int COLL>
 int launch_step_coll(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream);

@@ -263,4 +263,27 @@ LBM_INSTANTIATE(D3Q27, double)
 
 size_t reduce_scratch_bytes() { return sizeof(double) * (size_t)kReduceBlocks; }
 
+// sum of n partials in a fixed order -> *out.  More than 16 per thread are first folded by kReduceBlocks CTAs into
+// `stage` (kReduceBlocks doubles), so that one CTA never walks hundreds of dependent iterations.
+__global__ void fold_stage_kernel(const double *__restrict__ partials, int n, double *stage) {
+    double v = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += partials[i];
+    block_fold_store<false>(v, stage);
+}
+
+int launch_fold_sum(const double *partials, int n, double *stage, double *out, cudaStream_t st) {
+    if (n > 16 * kReduceThreads) {
+        const int g = grid_for(n / 4);
+        fold_stage_kernel<<<g, kReduceThreads, 0, st>>>(partials, n, stage);
+        ++g_launch_count;
+        int e = (int)cudaGetLastError();
+        if (e) return e;
+        partials = stage;
+        n = g;
+    }
+    fold_partials_kernel<false><<<1, kReduceThreads, 0, st>>>(partials, n, out);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
 }  // namespace lbm

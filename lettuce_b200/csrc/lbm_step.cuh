@@ -12,6 +12,7 @@
 //                        launched right before the bulk kernel, which overlaps it (programmatic
 //                        dependent launch); the two kernels write disjoint slots
 //   step_sync_kernel     bulk kernel for multi-GPU slabs with the in-kernel lock step (SlabSync)
+//   step_energy_kernel   bulk kernel that also reduces the kinetic energy of its output (reporter fusion)
 //
 // Planes x = -1 and x = n0 resolve to the wrapped plane of the same buffer (single GPU) or to a
 // peer-mapped plane of the neighbour rank's buffer (in_plane / out_plane).
@@ -74,6 +75,7 @@ struct StepParams {
     R ca, cb;  // scalars of the collision entry
     ForceArgs<R> force;  // LBM_OP_BGK_FORCED only
     SlabSync sync;
+    double *energy_partials;  // step_energy_kernel: one partial sum of 0.5|u|^2 per CTA
     AddrTables<R> tbl;
     OpDev<R> ops[LBM_MAX_OPS];
 };
@@ -310,8 +312,8 @@ constexpr int min_blocks_per_sm() {
 // one node: gather, collide, scatter.  An address is a block-uniform table entry (AddrTables, read from the
 // constant bank) plus one 32-bit node index per thread, chosen from nine precomputed (row, column)
 // combinations: one IMAD.WIDE per access.
-template <class S, class R, int COLL, bool PULL, bool PUSH>
-LBM_D void node_update(const StepParams<R> &p, int x, int y, int z) {
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool ENERGY = false>
+LBM_D R node_update(const StepParams<R> &p, int x, int y, int z) {
     constexpr int Q = S::Q;
     // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
     const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
@@ -336,6 +338,18 @@ LBM_D void node_update(const StepParams<R> &p, int x, int y, int z) {
         const int zd = (!PUSH || e2 == 0) ? z : (e2 == 1 ? zp : zm);
         p.tbl.st[k][q][rd + zd] = f[q];
     });
+    if constexpr (ENERGY) {
+        // without a push the node's output IS f: its kinetic energy 0.5 |j|^2 / rho^2 (Flow.incompressible_energy,
+        // lettuce/_flow.py:200-204) comes from the registers, no second pass over the populations
+        static_assert(!PUSH, "the output state of a pushing step is assembled from several nodes");
+        R rho, j[3];
+        moments<S, R>(f, rho, j);
+        const R inv = R(1) / rho;
+        const R u0 = j[0] * inv, u1 = j[1] * inv, u2 = j[2] * inv;
+        return R(0.5) * (u0 * u0 + u1 * u1 + u2 * u2);
+    } else {
+        return R(0);
+    }
 }
 
 template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
@@ -351,6 +365,30 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
         if (p.labels[(int64_t)x * p.n1 * p.n2 + (int64_t)y * p.n2 + z] != p.collision_index) return;
     }
     node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+}
+
+// Bulk kernel that also reduces the kinetic energy of the state it writes (unmasked, non-pushing steps): the
+// IncompressibleKineticEnergy reporter (observable_reporter.py:34-42) fused into the step.  Warp shuffles, one
+// shared-memory exchange, one partial per CTA; a fixed-order fold kernel follows (deterministic, no atomics).
+template <class S, class R, int COLL, bool PULL>
+__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
+    step_energy_kernel(const __grid_constant__ StepParams<R> p) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.z;
+    double e = 0.0;
+    if (z < p.n2 && y < p.n1) e = (double)node_update<S, R, COLL, PULL, false, true>(p, x, y, z);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    __shared__ double warp_sum[8];
+    const int t = threadIdx.y * blockDim.x + threadIdx.x, nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+    if ((t & 31) == 0) warp_sum[t >> 5] = e;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += warp_sum[w];
+        p.energy_partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
 }
 
 // Slab variant of the bulk kernel (unmasked, multi-GPU): identical arithmetic, plus the in-kernel lock

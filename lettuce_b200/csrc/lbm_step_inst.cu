@@ -22,14 +22,19 @@ namespace {
 template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
 int launch_scalar(const StepParams<R> &p, int variant, cudaStream_t stream) {
     (void)variant;
-    // threadIdx.x runs along the contiguous axis; fill the block up to 256 threads with rows.
-    int tz = 32;
-    while (tz < p.n2 && tz < 256) tz <<= 1;
-    int ty = 256 / tz;
-    while (ty > 1 && ty / 2 >= p.n1) ty >>= 1;
-    dim3 block(tz, ty, 1);
-    dim3 grid((p.n2 + tz - 1) / tz, (p.n1 + ty - 1) / ty, p.n0);
+    dim3 grid, block;
+    bulk_geometry(p.n0, p.n1, p.n2, grid, block);
     void (*bulk)(const StepParams<R>) = step_scalar_kernel<S, R, COLL, PULL, PUSH, MASKED>;
+    if (p.energy_partials) {       // lbm_step_energy: step + kinetic energy of the output in one kernel
+        if constexpr (!MASKED && !PUSH) {
+            if (p.sync.on) return LBM_ERR_UNSUPPORTED;
+            step_energy_kernel<S, R, COLL, PULL><<<grid, block, 0, stream>>>(p);
+            ++g_launch_count;
+            return (int)cudaGetLastError();
+        } else {
+            return LBM_ERR_UNSUPPORTED;
+        }
+    }
     if constexpr (!MASKED) {
         if (p.sync.on) {       // multi-GPU slab with in-kernel lock step (lbm_slab_step_n)
             StepParams<R> ps = p;

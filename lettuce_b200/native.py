@@ -75,7 +75,7 @@ class LbmSlab(C.Structure):
 
 
 EXPORTS = ["lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
-           "lbm_step", "lbm_step_n", "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
+           "lbm_step", "lbm_step_n", "lbm_step_energy", "lbm_step_energy_scratch_bytes", "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
            "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
            "lbm_launch_count", "lbm_step_variant_name"]
 
@@ -96,6 +96,10 @@ def lib() -> C.CDLL:
     L.lbm_step.restype = i32
     L.lbm_step_n.argtypes = [C.POINTER(LbmStepDesc), vp, vp, i64, vp]
     L.lbm_step_n.restype = i32
+    L.lbm_step_energy_scratch_bytes.argtypes = [C.POINTER(LbmStepDesc)]
+    L.lbm_step_energy_scratch_bytes.restype = C.c_size_t
+    L.lbm_step_energy.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, C.c_size_t, vp, vp]
+    L.lbm_step_energy.restype = i32
     L.lbm_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
     L.lbm_ipc_alloc.restype = i32
     L.lbm_ipc_open.argtypes = [vp, C.POINTER(vp)]
@@ -399,6 +403,34 @@ class Engine:
                                f"({list(f.shape)} {f.dtype} {f.device}); create a new Simulation")
         return f, g
 
+    def energy_fusable(self) -> bool:
+        """True when `step_with_energy` exists for this simulation: single-GPU engine, no boundaries, no
+        stream after the collide phase (NO_STREAMING / PRE_STREAMING)."""
+        return type(self) is Engine and int(self.lib.lbm_step_energy_scratch_bytes(C.byref(self.desc))) > 0
+
+    def step_with_energy(self) -> torch.Tensor:
+        """One time step that also returns sum 0.5|u|^2 (lattice units, 0-d float64 CUDA tensor) of the new
+        state, reduced inside the step kernel (`lbm_step_energy`).  Raises for steps with boundaries or a
+        post-collision stream; callers then use `step()` + the IncompressibleKineticEnergy observable.
+        The value is also left on the flow (`fused_energy_lu`) for the observable to pick up."""
+        if type(self) is not Engine:
+            raise RuntimeError("lbm_step_energy is a single-GPU entry point (slabs reduce with GlobalSum)")
+        self.refresh_parameters()
+        f, g = self._buffers()
+        need = int(self.lib.lbm_step_energy_scratch_bytes(C.byref(self.desc)))
+        if need == 0:
+            raise RuntimeError("lbm_step_energy is not available for this simulation (boundaries or post-streaming)")
+        if getattr(self, "_energy_scratch", None) is None or self._energy_scratch.numel() < need:
+            self._energy_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty((), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.lbm_step_energy(C.byref(self.desc), f.data_ptr(), g.data_ptr(),
+                                           self._energy_scratch.data_ptr(), need, out.data_ptr(),
+                                           _stream_ptr(self.device)), "lbm_step_energy")
+        self.flow.f, self.flow.f_next = g, f
+        self.flow._b200_energy = (g.data_ptr(), g._version, out)
+        return out
+
     def _variant_of(self, streaming: int, stream_only: bool = False) -> LbmStepDesc:
         d = LbmStepDesc.from_buffer_copy(self.desc)
         d.streaming = streaming
@@ -418,6 +450,7 @@ class Engine:
         self.refresh_parameters()
         f, g = self._buffers()
         flow = self.flow
+        flow._b200_energy = None            # a fused energy (step_with_energy) describes the state before this step
         bufs, cur = [f, g], 0
         with torch.cuda.device(self.device):
             stream = _stream_ptr(self.device)
@@ -454,6 +487,15 @@ def describe(simulation):
     return dict(stencil=int(eng.desc.lat.stencil), dtype=int(eng.desc.lat.dtype),
                 resolution=[int(eng.desc.lat.nx), int(eng.desc.lat.ny), int(eng.desc.lat.nz)],
                 streaming=int(eng.desc.streaming), collision_index=int(eng.desc.collision_index), ops=out)
+
+
+def fused_energy_lu(flow, f: torch.Tensor) -> Optional[torch.Tensor]:
+    """sum 0.5|u|^2 of `f` if the step that produced it already reduced it (`Engine.step_with_energy`) and `f`
+    has not been written through torch since; else None."""
+    cached = getattr(flow, "_b200_energy", None)
+    if cached is None or f is not flow.f or cached[0] != f.data_ptr() or cached[1] != f._version:
+        return None
+    return cached[2]
 
 
 def engine_of(simulation) -> Engine:

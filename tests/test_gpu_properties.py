@@ -253,3 +253,70 @@ def test_convergence_orders():
     from lettuce_b200.cli import run_convergence
     order_u, order_p = run_convergence(ctx(torch.float64), echo=lambda *_: None)
     assert 1.9 < order_u < 2.1 and 0.9 < order_p < 1.1
+
+
+@pytest.mark.parametrize("stencil,res,coll,dtype", [("D3Q19", [24, 20, 36], "bgk", torch.float32),
+                                                    ("D3Q27", [12, 16, 20], "kbc", torch.float64),
+                                                    ("D2Q9", [40, 33], "trt", torch.float64),
+                                                    # 4200 CTAs: the partials take the two-stage fold
+                                                    ("D2Q9", [4200, 40], "bgk", torch.float64)])
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING"])
+def test_fused_step_energy_equals_reporter(stencil, res, coll, dtype, strategy):
+    """lbm_step_energy: same populations as lbm_step, and the energy it returns equals the
+    IncompressibleKineticEnergy reduction of the new state"""
+    from lettuce_b200 import native as nv
+    c = ctx(dtype)
+    mk = lambda: lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=STENCILS[stencil]())
+    make = lambda fl: {"bgk": lt.BGKCollision(fl.units.relaxation_parameter_lu), "kbc": lt.KBCCollision(),
+                       "trt": lt.TRTCollision(fl.units.relaxation_parameter_lu)}[coll]
+    fa, fb = mk(), mk()
+    sa = lt.Simulation(fa, make(fa), [], lt.StreamingStrategy[strategy])
+    sb = lt.Simulation(fb, make(fb), [], lt.StreamingStrategy[strategy])
+    for _ in range(3):
+        nv.invoke(sa)
+        e = float(nv.engine_of(sb).step_with_energy().cpu())
+        assert torch.equal(fa.f, fb.f)
+        ref = float(nv.reduce(fa.stencil, nv.SUM_HALF_U2, fa.f).cpu())
+        assert e == pytest.approx(ref, rel=1e-12 if dtype == torch.float64 else 1e-6)
+    post = lt.Simulation(mk(), lt.NoCollision(), [])              # POST_STREAMING: not available
+    with pytest.raises(RuntimeError):
+        nv.engine_of(post).step_with_energy()
+
+
+@pytest.mark.parametrize("interval", [1, 3])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_energy_reporter_rides_on_the_step_kernel(interval, dtype):
+    """Simulation.__call__ runs the step before a due IncompressibleKineticEnergy reporter through
+    lbm_step_energy: same populations and same reporter values as a step-by-step run with the stand-alone
+    reduction, and no reduce kernel is launched (one step kernel per step + the small fold)"""
+    from lettuce_b200 import native as nv
+    c = ctx(dtype)
+    res, steps = [40, 24, 36], 6
+    mk = lambda: lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=lt.D3Q19())
+    fa, fb = mk(), mk()
+    rep = lt.ObservableReporter(lt.IncompressibleKineticEnergy(fa), interval=interval, out=None)
+    sa = lt.Simulation(fa, lt.BGKCollision(fa.units.relaxation_parameter_lu), [rep], lt.StreamingStrategy.PRE_STREAMING)
+    sb = lt.Simulation(fb, lt.BGKCollision(fb.units.relaxation_parameter_lu), [], lt.StreamingStrategy.PRE_STREAMING)
+    nv.engine_of(sa)
+    before = nv.launch_count()
+    sa(steps)
+    launched = nv.launch_count() - before
+    energy_b = lt.IncompressibleKineticEnergy(fb)
+    expect = [[0, float(energy_b().cpu())]]
+    for i in range(1, steps + 1):
+        nv.invoke(sb)
+        if i % interval == 0:
+            expect.append([i, float(energy_b().cpu())])
+    assert torch.equal(fa.f, fb.f)
+    assert [e[0] for e in rep.out] == [e[0] for e in expect]
+    for got, want in zip(rep.out, expect):
+        assert got[2] == pytest.approx(want[1], rel=1e-12 if dtype == torch.float64 else 1e-6)
+    # step 0 report: reduce + fold; then `steps` step kernels and one fold per due report (tiny lattice: one stage)
+    assert launched == 2 + steps + steps // interval
+    # the cached value is dropped as soon as the populations move on or are written through torch
+    assert nv.fused_energy_lu(fa, fa.f) is not None
+    fa.f.mul_(1.0)
+    assert nv.fused_energy_lu(fa, fa.f) is None
+    sa(interval)
+    nv.invoke(sa)
+    assert nv.fused_energy_lu(fa, fa.f) is None
