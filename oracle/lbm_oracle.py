@@ -569,6 +569,22 @@ def enstrophy(st, f, units):
     return vort * dx ** st["d"]
 
 
+def energy_spectrum(st, f, units):
+    """observable_reporter.py:71-137: shell sums of 0.5 |fft(u_pu)/norm|^2 over k-0.5 < |k| <= k+0.5 for
+    k = 0 .. int(max |k|) - 1; `norm` uses the FIRST resolution entry (:86-89)."""
+    res = f.shape[1:]
+    d = st["d"]
+    dx = units.length_to_pu(1.0)
+    freqs = [np.fft.fftfreq(n, d=1.0 / n) for n in res]
+    knorm = np.sqrt(sum(k * k for k in np.meshgrid(*freqs, indexing="ij")))
+    norm = res[0] * np.sqrt(2 * np.pi) / dx ** 2 if d == 3 else res[0] / dx
+    up = units.velocity_to_pu(u(st, f))
+    uh = np.stack([np.fft.fftn(up[a]) for a in range(d)]) / norm
+    ekin = (0.5 * (uh.imag ** 2 + uh.real ** 2)).sum(axis=0)
+    shells = np.arange(int(knorm.max()))
+    return np.array([ekin[(knorm > k - 0.5) & (knorm <= k + 0.5)].sum() for k in shells])
+
+
 def mass(f, no_mass_mask=None):
     """observable_reporter.py:140-158 (drops the border of the last two axes)."""
     m = f[..., 1:-1, 1:-1].sum()

@@ -280,7 +280,23 @@ def stock_obstacle_case():
     obstacle_case("obstacle3d_abb_bgk", lt.Obstacle, "D3Q19", [24, 12, 12], "bgk", 8, ["POST_STREAMING"])
 
 
+def spectrum_case():
+    """EnergySpectrum (observable_reporter.py:71-137) of evolved TGV states, incl. a non-cubic lattice."""
+    out = {}
+    for tag, stencil, res in (("2d", "D2Q9", [24, 24]), ("3d", "D3Q19", [12, 12, 12]), ("3d_ragged", "D3Q27", [12, 10, 8])):
+        ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+        flow = lt.TaylorGreenVortex(ctx, list(res), 100.0, 0.05, stencil=STENCILS[stencil]())
+        lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])(5)
+        out["f_" + tag] = npy(flow.f)
+        out["spectrum_" + tag] = npy(lt.EnergySpectrum(flow)(flow.f))
+        out["meta_" + tag] = np.array([stencil, "100.0", "0.05"])
+    save("energy_spectrum", **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["spectrum"]:
+        spectrum_case()
+        sys.exit(0)
     all4 = list(STRATS)
     tgv_case("tgv2d_d2q9_bgk", "D2Q9", [24, 24], 1.0, 0.05, "bgk", 10, all4, observables=True)
     tgv_case("tgv3d_d3q19_bgk", "D3Q19", [12, 12, 12], 1600.0, 0.05, "bgk", 10, all4, observables=True)
@@ -307,3 +323,4 @@ if __name__ == "__main__":
     other_flows_case()
     random_collision_case()
     native_known_answers()
+    spectrum_case()

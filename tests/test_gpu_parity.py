@@ -89,6 +89,20 @@ def test_observables_match_reference_golden(name, dtype):
         assert np.max(np.abs(flow.j().cpu().numpy() - g["u_POST_STREAMING"] * g["rho_POST_STREAMING"])) < 1e-15
 
 
+@pytest.mark.parametrize("tag", ["2d", "3d", "3d_ragged"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_energy_spectrum_matches_reference_golden(tag, dtype):
+    """EnergySpectrum from the engine's velocity field + cuFFT + shell bincount against the reference's output"""
+    g = load_golden("energy_spectrum")
+    stencil, re, ma = g["meta_" + tag]
+    f, want = g["f_" + tag], g["spectrum_" + tag]
+    flow = lt.TaylorGreenVortex(cuda_ctx(dtype), list(f.shape[1:]), float(re), float(ma), stencil=STENCILS[stencil]())
+    set_f(flow, f)
+    got = lt.EnergySpectrum(flow)(flow.f).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= (1e-12 if dtype == torch.float64 else 1e-5) * np.max(np.abs(want))
+
+
 # ------------------------------------------------------------------ obstacle golden vectors
 class ObstacleEqOut(lt.Obstacle):
     """BASELINE.md section 5 helper: inlet + EquilibriumOutletP + bounce-back."""
