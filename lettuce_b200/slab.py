@@ -23,7 +23,8 @@ from .ext.flows import Obstacle, TaylorGreenVortex
 from .ext.reporter import Observable
 
 __all__ = ["SlabDecomposition", "SlabTaylorGreenVortex", "SlabObstacle", "SlabSimulation", "SlabEngine",
-           "GlobalSum", "GlobalMax", "SlabEnstrophy", "make_tgv_slab_simulation"]
+           "GlobalSum", "GlobalMax", "SlabEnstrophy", "make_tgv_slab_simulation", "gather_populations",
+           "dump_slabs", "load_slabs"]
 
 
 class SlabDecomposition:
@@ -330,6 +331,87 @@ class SlabSimulation(Simulation):
     def close(self):
         if self._b200_engine is not None:
             self._b200_engine.close()
+
+    def dump(self, filename, group=None):
+        """Checkpoint of the GLOBAL lattice in `Flow.dump`'s format (lettuce/_flow.py:258-262), written by rank 0:
+        a single-GPU `Flow.load` or a run with another number of slabs can restart from it."""
+        dump_slabs(self.flow, self.decomposition, filename, group)
+
+    def load(self, filename, group=None):
+        """Restart from a global checkpoint (`Flow.dump` / `SlabSimulation.dump`): every rank takes its x-range."""
+        local = load_slabs(self.flow, self.decomposition, filename, group)
+        if self._b200_engine is not None:
+            self._b200_engine.load(local)          # populations stay in the IPC-exported buffers
+        else:
+            self.flow.f = local
+            self.flow._f_next = None
+
+
+def gather_populations(flow, dec: SlabDecomposition, group=None, dst: int = 0) -> Optional[torch.Tensor]:
+    """The global populations `[q, nx_global, ...]` in host memory on rank `dst` (None elsewhere).  Slabs travel
+    one at a time (point-to-point, on the device the populations live on), so rank `dst` needs one slab of
+    staging memory, not the whole lattice, on its GPU; the device-to-host copies go to pinned memory and overlap
+    the next slab's transfer."""
+    local = flow.f
+    if dec.world == 1:
+        return local.detach().cpu()
+    if dec.rank != dst:
+        dist.send(local.contiguous(), dst, group=group)
+        return None
+    shape = list(local.shape)
+    shape[1] = dec.nx_global
+    whole = torch.empty(shape, dtype=local.dtype, pin_memory=local.is_cuda)
+    for r in range(dec.world):
+        if r == dst:
+            part = local
+        else:
+            pshape = list(local.shape)
+            pshape[1] = dec.sizes[r]
+            part = torch.empty(pshape, dtype=local.dtype, device=local.device)
+            dist.recv(part, r, group=group)
+        whole[:, dec.offsets[r]:dec.offsets[r] + dec.sizes[r]].copy_(part, non_blocking=True)
+    if local.is_cuda:
+        torch.cuda.synchronize(local.device)
+    return whole
+
+
+def dump_slabs(flow, dec: SlabDecomposition, filename, group=None):
+    whole = gather_populations(flow, dec, group, dst=0)
+    if dec.rank == 0:
+        import pickle
+        with open(filename, "wb") as fh:
+            pickle.dump(whole.numpy(), fh)
+    if dec.world > 1:
+        dist.barrier(group=group)           # the file is complete when any rank returns
+
+
+def load_slabs(flow, dec: SlabDecomposition, filename, group=None) -> torch.Tensor:
+    """This rank's x-range of the global checkpoint `filename`, on the flow's device and in its dtype.  Rank 0
+    reads the file and sends every other rank its planes."""
+    like = flow.f
+    expect = list(like.shape)
+    if dec.rank == 0:
+        import pickle
+        with open(filename, "rb") as fh:
+            whole = torch.as_tensor(pickle.load(fh))
+        full = list(expect)
+        full[1] = dec.nx_global
+        ok = list(whole.shape) == full
+        if dec.world > 1:
+            dist.broadcast_object_list([ok], src=0, group=group)
+        if not ok:
+            raise ValueError(f"checkpoint holds populations of shape {list(whole.shape)}, the run needs {full}")
+        for r in range(1, dec.world):
+            part = whole[:, dec.offsets[r]:dec.offsets[r] + dec.sizes[r]]
+            dist.send(part.to(device=like.device, dtype=like.dtype).contiguous(), r, group=group)
+        return whole[:, dec.x0:dec.x1].to(device=like.device, dtype=like.dtype).contiguous()
+    flag = [None]
+    dist.broadcast_object_list(flag, src=0, group=group)
+    if not flag[0]:
+        raise ValueError("checkpoint does not match the global lattice (see rank 0)")
+    local = torch.empty(expect, dtype=like.dtype, device=like.device)
+    dist.recv(local, 0, group=group)
+    return local
 
 
 class _GlobalReduce(Observable):

@@ -215,6 +215,38 @@ def cpu_worker(rank, world, port, results):
             assert [getattr(b, "_slab_disabled", False) for b in sim.post_boundaries] == [False, not owner, False]
             d = lt.native.describe(sim)
             assert d["ops"][2]["side"] == (1 if owner else 0)
+        # checkpoints: rank 0 writes the GLOBAL lattice in Flow.dump's format; a single-process Flow.load reads it,
+        # and SlabSimulation.load hands every rank its planes back
+        import pickle
+        path = f"/tmp/lettuce_b200_slab_ckpt_{port}.pkl"
+        res = [11, 6, 8]
+        dec = slab.SlabDecomposition(res[0], world, rank)
+        flow = slab.SlabTaylorGreenVortex(ctx, res, 400.0, 0.05, lt.D3Q19(), dec)
+        sim = slab.SlabSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [],
+                                  lt.StreamingStrategy.POST_STREAMING, dec)
+        mine = flow.f.clone()
+        sim.dump(path)
+        one = lt.TaylorGreenVortex(ctx, res, 400.0, 0.05, stencil=lt.D3Q19())
+        expect = one.f.clone()
+        one.f = torch.zeros_like(one.f)
+        one.load(path)
+        out["ckpt_global_step"] = float((one.f - expect).abs().max())
+        flow.f = torch.zeros_like(mine)
+        sim.load(path)
+        out["ckpt_reload_step"] = float((flow.f - mine).abs().max())
+        dist.barrier()
+        if rank == 0:
+            with open(path, "wb") as fh:
+                pickle.dump(np.zeros((19, res[0] + 1, 6, 8)), fh)       # wrong global shape: every rank raises
+        dist.barrier()
+        try:
+            sim.load(path)
+            out["ckpt_shape_step"] = 1.0
+        except ValueError:
+            out["ckpt_shape_step"] = 0.0
+        dist.barrier()
+        if rank == 0:
+            os.remove(path)
         results[rank] = out
     finally:
         dist.destroy_process_group()
