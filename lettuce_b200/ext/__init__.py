@@ -2,3 +2,4 @@ from .boundary import *
 from .collision import *
 from .flows import *
 from .reporter import *
+from .vtk import *

@@ -320,3 +320,27 @@ def test_energy_reporter_rides_on_the_step_kernel(interval, dtype):
     sa(interval)
     nv.invoke(sa)
     assert nv.fused_energy_lu(fa, fa.f) is None
+
+
+def test_vtk_reporter_writes_engine_fields(tmp_path):
+    """VTKReporter (tests/reporter/test_vtk_reporter_no_mask.py, test_vtk_reporter_mask.py): one file per due
+    step, written in the background, holding the engine's pressure and velocity in physical units"""
+    c = ctx(torch.float32)
+    flow = lt.TaylorGreenVortex(c, [16, 24], 10.0, 0.05, stencil=lt.D2Q9())
+    rep = lt.VTKReporter(interval=2, filename_base=str(tmp_path / "data" / "output"))
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [rep])
+    sim(4)
+    rep.wait()
+    names = sorted(p.name for p in (tmp_path / "data").iterdir())
+    assert names == ["output_00000000.vtr", "output_00000002.vtr", "output_00000004.vtr"]
+    back = lt.read_vtr(tmp_path / "data" / "output_00000004.vtr")
+    assert back["p"].shape == (16, 24, 1) and back["ux"].dtype == np.float32
+    assert np.array_equal(back["p"][..., 0], flow.p_pu[0].cpu().numpy())
+    assert np.array_equal(back["uy"][..., 0], flow.u_pu[1].cpu().numpy())
+    with pytest.raises(ValueError):
+        rep.output_mask(sim)
+    obstacle = lt.Obstacle(c, [24, 12, 12], 100.0, 0.05, 4.0, stencil=lt.D3Q19())
+    obstacle.mask = (obstacle.grid[0] - 1.0) ** 2 + (obstacle.grid[1] - 1.0) ** 2 < 0.3
+    sim3 = lt.Simulation(obstacle, lt.BGKCollision(obstacle.units.relaxation_parameter_lu), [])
+    mask_file = lt.VTKReporter(1, str(tmp_path / "m" / "o")).output_mask(sim3)
+    assert np.array_equal(lt.read_vtr(mask_file)["mask"], sim3.no_collision_mask.cpu().numpy())
