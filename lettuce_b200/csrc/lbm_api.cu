@@ -8,7 +8,7 @@
 
 namespace lbm {
 
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 static thread_local char g_cuda_error[256] = "";
 
 template <class S, class R>
@@ -309,7 +309,7 @@ const char *lbm_status_string(int s) {
 
 const char *lbm_last_cuda_error(void) { return g_cuda_error; }
 
-int64_t lbm_launch_count(void) { return g_launch_count; }
+int64_t lbm_launch_count(void) { return g_launch_count.load(); }
 
 int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream) {
     return step_with_sync(desc, d_f_in, d_f_out, nullptr, stream);

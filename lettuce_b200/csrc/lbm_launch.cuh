@@ -2,11 +2,13 @@
 // triple is compiled in its own translation unit (lbm_step_inst.cu with -DLBM_INST_STENCIL /
 // -DLBM_INST_REAL / -DLBM_INST_COLL) so the 40 units build in parallel.
 #pragma once
+#include <atomic>
+
 #include "lbm_step.cuh"
 
 namespace lbm {
 
-extern int64_t g_launch_count;
+extern std::atomic<int64_t> g_launch_count;  // kernels launched by this library (lbm_launch_count)
 
 // launch geometry of the bulk kernels: threadIdx.x along the contiguous axis, blocks of up to 256 threads
 // filled with rows, one grid layer per x-plane
