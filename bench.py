@@ -39,7 +39,9 @@ RE, MA = 1600.0, 0.05
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed
 # `ncu --set full` captures (profiles/r1_step_d3q19_bgk_{pre,post}_256.csv); algorithmic = 2.550e9
 NCU_DRAM_BYTES_PER_LAUNCH = {(256, "PRE_STREAMING"): 1.275082e9 + 1.224746e9,
-                             (256, "POST_STREAMING"): 1.276132e9 + 1.225850e9}
+                             (256, "POST_STREAMING"): 1.276132e9 + 1.225850e9,
+                             # profiles/r1_step_d3q19_bgk_pre_512_dram.csv; algorithmic = 20.401e9
+                             (512, "PRE_STREAMING"): 10.200856e9 + 10.150541e9}
 
 
 def measured_hbm_peak():
@@ -316,7 +318,7 @@ def gpu_main(args):
             "config": workload_config(world, n, args.strategy),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((n, args.strategy)),
-                         "traffic_unit": "bytes per launch (ncu, profiles/r1_step_d3q19_bgk_*_256.csv)",
+                         "traffic_unit": "bytes per launch (ncu, profiles/r1_step_d3q19_bgk_*.csv)",
                          "algorithmic_bytes_per_launch": nodes_local * BYTES_PER_NODE, "peak_source": peak_src,
                          "kernel": kernel_name,
                          "bytes_per_node": BYTES_PER_NODE},

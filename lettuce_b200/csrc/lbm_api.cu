@@ -2,7 +2,9 @@
 // descriptor -> kernel-parameter translation, dispatch, mask packing, host-buffer
 // end-to-end entry.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "lbm_launch.cuh"
 
@@ -367,9 +369,116 @@ int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out
                                      (cudaStream_t)stream));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-graph replay of step batches on small lattices.  Below a few hundred thousand nodes one step takes a few
+// microseconds and the loop is bound by launch latency; kGraphSteps consecutive steps (a -> b -> a ...) are
+// captured once per (descriptor, buffer pair, device) into an executable graph and replayed.  Opt-in:
+// LBM_B200_GRAPH_MAX_NODES=<largest lattice, in nodes, that takes this path> (default 0 = never).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kGraphSteps = 32;   // even: a replay leaves the newest populations where they were before it
+constexpr int kGraphSlots = 4;
+
+struct GraphSlot {
+    lbm_step_desc desc;
+    void *a = nullptr, *b = nullptr;
+    int device = -1;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t used = 0;
+};
+std::mutex g_graph_mutex;
+GraphSlot g_graph_slots[kGraphSlots];
+uint64_t g_graph_clock = 0;
+
+int64_t graph_max_nodes() {           // read per call: cheap, and a host program may switch it at run time
+    const char *e = getenv("LBM_B200_GRAPH_MAX_NODES");
+    return e ? (int64_t)atoll(e) : (int64_t)0;
+}
+
+// captures kGraphSteps steps on a private stream (the caller's may be the legacy default stream, which cannot
+// be captured) and instantiates them; returns 0 or a cudaError / lbm_status
+int capture_steps(const lbm_step_desc *desc, void *a, void *b, cudaGraphExec_t *exec) {
+    cudaStream_t cs = nullptr;
+    int e = (int)cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    if (e) return e;
+    const int64_t launches_before = lbm::g_launch_count.load();
+    e = (int)cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed);
+    int rc = 0;
+    cudaGraph_t graph = nullptr;
+    if (!e) {
+        void *x = a, *y = b;
+        for (int k = 0; k < kGraphSteps && !rc; ++k) {
+            rc = lbm_step(desc, x, y, cs);
+            void *t = x; x = y; y = t;
+        }
+        e = (int)cudaStreamEndCapture(cs, &graph);
+    }
+    lbm::g_launch_count.store(launches_before);      // captured, not launched
+    if (!e && !rc) e = (int)cudaGraphInstantiate(exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cs);
+    return rc ? rc : e;
+}
+
+// replays as many whole graphs as fit into n; returns the number of steps done (0 = path not taken) or < 0
+int64_t graph_steps(const lbm_step_desc *desc, void *a, void *b, int64_t n, cudaStream_t stream, int *status) {
+    *status = LBM_OK;
+    lbm::Dims dm;
+    if (n < kGraphSteps || desc->n_ops != 1 || graph_max_nodes() <= 0 || lbm::lattice_dims(&desc->lat, dm)) return 0;
+    if ((int64_t)dm.n0 * dm.n1 * dm.n2 > graph_max_nodes()) return 0;
+    const lbm_halo &h = desc->halo;
+    if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return 0;
+    int device = -1;
+    if (cudaGetDevice(&device)) return 0;
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    GraphSlot *slot = nullptr, *victim = &g_graph_slots[0];
+    for (GraphSlot &s : g_graph_slots) {
+        if (s.exec && s.a == a && s.b == b && s.device == device && !memcmp(&s.desc, desc, sizeof *desc)) slot = &s;
+        if (s.used < victim->used) victim = &s;
+    }
+    if (!slot) {
+        cudaGraphExec_t exec = nullptr;
+        const int e = capture_steps(desc, a, b, &exec);
+        if (e) {
+            *status = lbm::cuda_fail_public(e);
+            return -1;
+        }
+        if (victim->exec) cudaGraphExecDestroy(victim->exec);
+        victim->desc = *desc;
+        victim->a = a;
+        victim->b = b;
+        victim->device = device;
+        victim->exec = exec;
+        slot = victim;
+    }
+    slot->used = ++g_graph_clock;
+    int64_t done = 0;
+    while (n - done >= kGraphSteps) {
+        const int e = (int)cudaGraphLaunch(slot->exec, stream);
+        if (e) {
+            *status = lbm::cuda_fail_public(e);
+            return -1;
+        }
+        lbm::g_launch_count += kGraphSteps;
+        done += kGraphSteps;
+    }
+    return done;
+}
+
+}  // namespace
+
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream) {
-    if (n < 0) return LBM_ERR_BAD_ARGUMENT;
+    if (n < 0 || !desc) return LBM_ERR_BAD_ARGUMENT;
     void *a = d_f_a, *b = d_f_b;
+    if (n >= kGraphSteps && graph_max_nodes() > 0) {
+        lbm::Dims dm;
+        int rc = lbm::validate_desc(desc, dm);
+        if (rc) return rc;
+        const int64_t done = graph_steps(desc, a, b, n, (cudaStream_t)stream, &rc);
+        if (done < 0) return rc;
+        n -= done;                                   // kGraphSteps is even: a still holds the newest populations
+    }
     for (int64_t k = 0; k < n; ++k) {
         const int rc = lbm_step(desc, a, b, stream);
         if (rc) return rc;

@@ -344,3 +344,34 @@ def test_vtk_reporter_writes_engine_fields(tmp_path):
     sim3 = lt.Simulation(obstacle, lt.BGKCollision(obstacle.units.relaxation_parameter_lu), [])
     mask_file = lt.VTKReporter(1, str(tmp_path / "m" / "o")).output_mask(sim3)
     assert np.array_equal(lt.read_vtr(mask_file)["mask"], sim3.no_collision_mask.cpu().numpy())
+
+
+@pytest.mark.parametrize("stencil,res,strategy", [("D2Q9", [64, 48], "PRE_STREAMING"), ("D3Q19", [16, 12, 20], "POST_STREAMING")])
+def test_graph_replay_of_small_lattices_is_bit_identical(stencil, res, strategy, monkeypatch):
+    """LBM_B200_GRAPH_MAX_NODES: lbm_step_n replays 32-step CUDA graphs on small lattices; same populations as
+    step-by-step launches, same launch count, odd remainders and changed parameters handled"""
+    from lettuce_b200 import native as nv
+    c = ctx(torch.float64)
+    mk = lambda: lt.TaylorGreenVortex(c, res, 100.0, 0.05, stencil=STENCILS[stencil]())
+    fa, fb = mk(), mk()
+    sa = lt.Simulation(fa, lt.BGKCollision(fa.units.relaxation_parameter_lu), [], lt.StreamingStrategy[strategy])
+    sb = lt.Simulation(fb, lt.BGKCollision(fb.units.relaxation_parameter_lu), [], lt.StreamingStrategy[strategy])
+    for _ in range(71):
+        nv.invoke(sb)
+    monkeypatch.setenv("LBM_B200_GRAPH_MAX_NODES", "100000")
+    before = nv.launch_count()
+    nv.invoke_n(sa, 71)                       # two graphs of 32 steps + 7 plain steps
+    assert nv.launch_count() - before == 71
+    assert torch.equal(fa.f, fb.f)
+    nv.invoke_n(sa, 33)                       # odd batch on the swapped buffer pair: a second cached graph
+    sa.collision.tau = sb.collision.tau = 0.8  # parameters are part of the cache key
+    nv.invoke_n(sa, 40)
+    monkeypatch.delenv("LBM_B200_GRAPH_MAX_NODES")
+    nv.invoke_n(sb, 33)
+    nv.invoke_n(sb, 40)
+    assert torch.equal(fa.f, fb.f)
+    monkeypatch.setenv("LBM_B200_GRAPH_MAX_NODES", "10")        # lattice larger than the limit: plain launches
+    nv.invoke_n(sa, 32)
+    monkeypatch.delenv("LBM_B200_GRAPH_MAX_NODES")
+    nv.invoke_n(sb, 32)
+    assert torch.equal(fa.f, fb.f)
