@@ -169,7 +169,9 @@ int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out
 /* `n` consecutive steps ping-ponging between two buffers (a -> b -> a ...), without returning
  * to the caller in between: the loop `for _ in range(num_steps)` of Simulation.__call__
  * (lettuce/_simulation.py:317-318) when no reporter is due.  The newest populations end up in
- * d_f_b if n is odd and in d_f_a if n is even. */
+ * d_f_b if n is odd and in d_f_a if n is even.  On lattices of up to LBM_B200_GRAPH_MAX_NODES nodes
+ * (environment variable, default 2^20, 0 = off) without boundaries, batches of >= 32 steps are replayed from
+ * a cached CUDA graph of 32 steps (launch-latency bound regime); results are identical to n lbm_step calls. */
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream);
 
 /* Builds the per-node label byte and frozen-slot word from lettuce's masks

