@@ -49,7 +49,7 @@ def benchmark(ctx, steps, resolution, flow, streaming_strategy):
                     stencil=stencil)
     collision = BGKCollision(tau=fl.units.relaxation_parameter_lu)
     simulation = Simulation(fl, collision, [], streaming_strategy=getattr(StreamingStrategy, streaming_strategy))
-    simulation(min(steps, 10))                    # warm-up: context creation, first launches
+    simulation(min(steps, 64))                    # warm-up: context creation, first launches, graph capture
     mlups = simulation(steps)
     click.echo("Finished {} ({}, {}) for {} steps in {} bit precision with {}. MLUPS: {:10.2f}".format(
         fl.__class__.__name__, fl.stencil.__class__.__name__, ctx.obj["device"], steps,
