@@ -529,6 +529,150 @@ def run(st, f, nsteps, collision, pre=(), post=(), strategy="POST_STREAMING"):
 
 
 # --------------------------------------------------------------------------
+# link-wise bounce-back boundaries applied AFTER streaming
+# (examples/advanced_projects/efficient_bounce_back_obstacle; `ebb/` below is that directory)
+# --------------------------------------------------------------------------
+def solid_fluid_links(st, mask, periodicity=None, other_solid=None):
+    """All (q_in, solid node, fluid node) triples of a solid `mask`: q_in points from the fluid node into the solid
+    node.  Restates the neighbour search of ebb/boundary/fullway_bounce_back_boundary.py:50-123 and
+    halfway_bounce_back_boundary.py:65-152 INCLUDING its index quirk: a neighbour index of -1 on a non-periodic
+    axis silently wraps (NumPy negative indexing) while an index of n raises IndexError and is skipped.
+    `other_solid` marks nodes that belong to other solid boundaries (no link towards them).  Order: solid nodes in
+    C order, q ascending (the reference's loop order)."""
+    mask = np.asarray(mask, dtype=bool)
+    res, d = mask.shape, st["d"]
+    periodicity = tuple(periodicity) if periodicity is not None else (False,) * d
+    blocked = mask if other_solid is None else (mask | np.asarray(other_solid, dtype=bool))
+    solid = np.argwhere(mask)                                    # [n, d], C order
+    q_in, s_nodes, f_nodes = [], [], []
+    for i in range(st["q"]):
+        nb = solid + st["e"][i][None, :]
+        ok = np.ones(len(solid), dtype=bool)
+        for a in range(d):
+            if periodicity[a]:
+                nb[:, a] %= res[a]
+            else:
+                ok &= nb[:, a] < res[a]                          # IndexError in the reference: skipped
+                nb[:, a] = np.where(nb[:, a] < 0, nb[:, a] + res[a], nb[:, a])   # negative index wraps
+        nbc = np.where(ok[:, None], nb, 0)
+        ok &= ~blocked[tuple(nbc.T)]
+        q_in.append(np.full(int(ok.sum()), st["opposite"][i]))
+        s_nodes.append(solid[ok])
+        f_nodes.append(nb[ok])
+    q_in, s_nodes, f_nodes = np.concatenate(q_in), np.concatenate(s_nodes), np.concatenate(f_nodes)
+    # reference order: outer loop over solid nodes (C order), inner loop over stencil direction i
+    flat = np.ravel_multi_index(tuple(s_nodes.T), res)
+    order = np.lexsort((st["opposite"][q_in], flat))            # i = opposite[q_in]
+    return q_in[order], s_nodes[order], f_nodes[order]
+
+
+def cylinder_wall_distance(st, q_in, f_nodes, x_center, y_center, radius):
+    """Distance d in (0, 1] (in units of the link length) from the fluid node to a circular cylinder's surface along
+    link q_in (ebb/flow/obstacle_cylinder.py:322-365: the p-q formula; the first root that is <= 1 wins)."""
+    c = st["e"][q_in][:, :2].astype(float)
+    px, py = f_nodes[:, 0].astype(float), f_nodes[:, 1].astype(float)
+    cc = c[:, 0] ** 2 + c[:, 1] ** 2
+    h1 = (px * c[:, 0] + py * c[:, 1] - c[:, 0] * x_center - c[:, 1] * y_center) / cc
+    h2 = (px * px + py * py + x_center ** 2 + y_center ** 2 - 2 * px * x_center - 2 * py * y_center - radius ** 2) / cc
+    root = np.sqrt(h1 * h1 - h2)
+    d1, d2 = -h1 + root, -h1 - root
+    return np.where(d1 <= 1, d1, d2)
+
+
+def fullway_links(st, mask, periodicity=None, global_solid_mask=None):
+    """dict(kind='fullway'): links stored on the SOLID node (fullway_bounce_back_boundary.py:20-123)."""
+    mask = np.asarray(mask, dtype=bool)
+    other = None if global_solid_mask is None else np.where(~mask, np.asarray(global_solid_mask, dtype=bool), False)
+    q_in, s_nodes, _ = solid_fluid_links(st, mask, periodicity, other)
+    return dict(kind="fullway", mask=mask, q=q_in, nodes=s_nodes)
+
+
+def halfway_links(st, mask, periodicity=None, global_solid_mask=None):
+    """dict(kind='halfway'): links stored on the FLUID node, legacy neighbour search
+    (halfway_bounce_back_boundary.py:60-152)."""
+    mask = np.asarray(mask, dtype=bool)
+    other = None if global_solid_mask is None else np.asarray(global_solid_mask, dtype=bool)
+    q_in, _, f_nodes = solid_fluid_links(st, mask, periodicity, other)
+    return dict(kind="halfway", mask=mask, q=q_in, nodes=f_nodes)
+
+
+def cylinder_links(st, mask, x_center, y_center, radius, kind="interpolated"):
+    """Link lists of ObstacleCylinder.make_ibb_index_lists (obstacle_cylinder.py:283-466): every axis is treated
+    as periodic in the neighbour search, d <= 0.5 links first ('lt'), then d > 0.5 ('gt'), each in loop order.
+    kind='halfway' uses the same links without the distances (halfway_bounce_back_boundary.py:48-56)."""
+    mask = np.asarray(mask, dtype=bool)
+    q_in, _, f_nodes = solid_fluid_links(st, mask, (True,) * st["d"])
+    dist = cylinder_wall_distance(st, q_in, f_nodes, x_center, y_center, radius)
+    lt = dist <= 0.5
+    order = np.concatenate([np.flatnonzero(lt), np.flatnonzero(~lt)])
+    return dict(kind=kind, mask=mask, q=q_in[order], nodes=f_nodes[order], d=dist[order])
+
+
+def ebb_masks(st, res, pre, post, post_streaming):
+    """Masks of EbbSimulation (ebb/simulation/ebb_simulation.py:22-57): the post-streaming boundaries continue
+    the label numbering; fullway has no no-streaming mask, halfway / interpolated freeze every slot of their solid
+    nodes."""
+    ncm, nsm = build_masks(st, res, list(pre), list(post))
+    if not post_streaming:
+        return ncm, nsm
+    ci = len(pre)
+    if ncm is None:
+        ncm = np.full(res, ci, dtype=np.uint8)
+        nsm = np.full((st["q"], *res), ci, dtype=np.uint8)
+    for i, b in enumerate(post_streaming, start=ci + 1 + len(post)):
+        ncm[b["mask"]] = i
+        if b["kind"] != "fullway":
+            nsm |= b["mask"].astype(np.uint8)[None]
+    return ncm, nsm
+
+
+def apply_links(st, f, fc, b):
+    """One post-streaming boundary on the streamed populations `f` (in place); `fc` are the populations between
+    collision and streaming.  Returns the momentum-exchange force [d] in lattice units
+    (fullway_bounce_back_boundary.py:132-170, halfway_bounce_back_boundary.py:167-215,
+    linear_interpolated_bounce_back_boundary.py:57-143)."""
+    q, nodes = b["q"], tuple(b["nodes"].T)
+    opp = st["opposite"][q]
+    e = st["e"][q].astype(f.dtype)
+    if b["kind"] == "fullway":
+        incoming = f[(q,) + nodes]
+        force = 2 * (incoming[:, None] * e).sum(axis=0)
+        f[(opp,) + nodes] = incoming
+        return force
+    fcq = fc[(q,) + nodes]
+    if b["kind"] == "halfway":
+        force = 2 * (fcq[:, None] * e).sum(axis=0)
+        f[(opp,) + nodes] = fcq
+        return force
+    d = b["d"].astype(f.dtype)
+    lt = b["d"] <= 0.5
+    bounced_lt = 2 * d * fcq + (1 - 2 * d) * f[(q,) + nodes]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        bounced_gt = (1 / (2 * d)) * fcq + (1 - 1 / (2 * d)) * fc[(opp,) + nodes]
+    f[(opp[lt],) + tuple(c[lt] for c in nodes)] = bounced_lt[lt]          # d <= 0.5 first, then d > 0.5
+    f[(opp[~lt],) + tuple(c[~lt] for c in nodes)] = bounced_gt[~lt]
+    bounced = f[(opp,) + nodes]
+    return ((fcq + bounced)[:, None] * e).sum(axis=0)
+
+
+def ebb_step(st, f, collision, pre=(), post=(), post_streaming=(), ncm=None, nsm=None):
+    """One EbbSimulation step: collide, remember the collided populations, stream, post-streaming boundaries in
+    order (ebb_simulation.py:71-104).  Returns (f, [force of each post-streaming boundary])."""
+    fc = collide(st, f, collision, pre, post, ncm)
+    f = stream(st, fc, nsm)
+    forces = [apply_links(st, f, fc, b) for b in post_streaming]
+    return f, forces
+
+
+def ebb_run(st, f, nsteps, collision, pre=(), post=(), post_streaming=()):
+    ncm, nsm = ebb_masks(st, f.shape[1:], pre, post, post_streaming)
+    forces = []
+    for _ in range(nsteps):
+        f, forces = ebb_step(st, f, collision, pre, post, post_streaming, ncm, nsm)
+    return f, forces
+
+
+# --------------------------------------------------------------------------
 # reporter reductions (lettuce/ext/_reporter/observable_reporter.py:27-68,140-158)
 # --------------------------------------------------------------------------
 _W6 = (-1 / 60, 3 / 20, -3 / 4, 3 / 4, -3 / 20, 1 / 60)

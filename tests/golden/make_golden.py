@@ -293,7 +293,58 @@ def spectrum_case():
     save("energy_spectrum", **out)
 
 
+def ebb_cases():
+    """The reference's example project examples/advanced_projects/efficient_bounce_back_obstacle (EbbSimulation with
+    fullway / halfway / linearly interpolated bounce-back applied after streaming, momentum-exchange force)."""
+    base = "/root/reference/examples/advanced_projects/efficient_bounce_back_obstacle"
+    for sub in ("boundary", "simulation", "flow"):
+        sys.path.insert(0, os.path.join(base, sub))
+    from examples.advanced_projects.efficient_bounce_back_obstacle.flow.obstacle_cylinder import ObstacleCylinder
+    from examples.advanced_projects.efficient_bounce_back_obstacle.simulation.ebb_simulation import EbbSimulation
+    import contextlib
+    import io
+    cases = [("ebb2d_hwbb", "D2Q9", [40, 20], "hwbb", "periodic", 6.0, 12),
+             ("ebb2d_ibb1", "D2Q9", [40, 20], "ibb1", "periodic", 6.0, 12),
+             ("ebb2d_fwbb", "D2Q9", [40, 20], "fwbb", "periodic", 6.0, 12),
+             # (lateral_walls='bounceback' unpacks three resolution entries: 3-D only, obstacle_cylinder.py:161)
+             ("ebb3d_fwbb_walls", "D3Q19", [20, 12, 5], "fwbb", "bounceback", 4.0, 6),
+             ("ebb3d_ibb1", "D3Q19", [24, 14, 6], "ibb1", "periodic", 5.0, 8),
+             ("ebb3d_hwbb_walls", "D3Q27", [20, 12, 5], "hwbb", "bounceback", 4.0, 6)]
+    for name, stencil, res, bc, walls, diameter, steps in cases:
+        ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+        with contextlib.redirect_stdout(io.StringIO()):
+            flow = ObstacleCylinder(ctx, list(res), 100.0, 0.05, char_length_pu=1.0, char_length_lu=diameter,
+                                    bc_type=bc, lateral_walls=walls, calc_force_coefficients=True,
+                                    stencil=STENCILS[stencil](), u_init=1,
+                                    perturb_init=len(res) == 2)   # the 3-D perturbation needs ny == nz (:279-284)
+            sim = EbbSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+        out = dict(f0=npy(flow.f), tau=np.float64(flow.units.relaxation_parameter_lu), res=np.array(res),
+                   meta=np.array([stencil, bc, walls, str(steps), str(diameter)]),
+                   obstacle_mask=flow.obstacle_mask.copy(), wall_mask=flow.wall_mask.copy(),
+                   in_mask=flow.in_mask.copy(), u_inlet=np.asarray(flow.u_inlet, dtype=np.float64),
+                   center=np.array([flow.x_pos_lu - 1, flow.y_pos_lu - 1, flow.radius_lu]),
+                   ncm=npy(sim.no_collision_mask), nsm=npy(sim.no_streaming_mask))
+        obstacle = sim.post_streaming_boundaries[-1]
+        if bc == "fwbb":
+            out["f_index_fwbb"] = npy(obstacle.f_index_fwbb)
+        elif bc == "hwbb":
+            out["f_index"] = npy(obstacle.f_index)
+        else:
+            out.update(f_index_lt=npy(obstacle.f_index_lt), f_index_gt=npy(obstacle.f_index_gt),
+                       d_lt=npy(obstacle.d_lt), d_gt=npy(obstacle.d_gt))
+        if walls == "bounceback":
+            out["wall_f_index_fwbb"] = npy(sim.post_streaming_boundaries[0].f_index_fwbb)
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim(steps)
+        out["f"] = npy(flow.f)
+        out["force"] = npy(obstacle.force_sum)
+        save(name, **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["ebb"]:
+        ebb_cases()
+        sys.exit(0)
     if sys.argv[1:] == ["spectrum"]:
         spectrum_case()
         sys.exit(0)
@@ -324,3 +375,4 @@ if __name__ == "__main__":
     random_collision_case()
     native_known_answers()
     spectrum_case()
+    ebb_cases()

@@ -1,0 +1,77 @@
+"""Link-wise bounce-back boundaries applied after streaming (the reference's example project
+examples/advanced_projects/efficient_bounce_back_obstacle): the oracle's link search, wall distances, masks, the
+C -> S -> B step and the momentum-exchange force against goldens produced by that project's own classes
+(tests/golden/make_golden.py ebb_cases)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, max_rel
+from oracle import lbm_oracle as lo
+
+CASES = ["ebb2d_hwbb", "ebb2d_ibb1", "ebb2d_fwbb", "ebb3d_fwbb_walls", "ebb3d_ibb1", "ebb3d_hwbb_walls"]
+
+
+def ebb_setup(g):
+    """(stencil tables, units, collision, post boundaries, post-streaming boundaries) of a golden case, built
+    with the oracle's own link search"""
+    stencil, bc, walls, steps, diameter = g["meta"]
+    st = lo.stencil(stencil)
+    d = st["d"]
+    units = lo.Units(100.0, 0.05, characteristic_length_lu=float(diameter))
+    assert units.tau == pytest.approx(float(g["tau"]), rel=1e-14)
+    direction = [1] + [0] * (d - 1)
+    u_inlet = np.asarray(g["u_inlet"], dtype=np.float64)
+    if u_inlet.ndim == 1:
+        u_inlet = u_inlet.reshape((d,) + (1,) * d)
+    post = [lo.equilibrium_pu(g["in_mask"], units.pressure_pu_to_density_lu(np.zeros((1,) * (d + 1))),
+                              units.velocity_to_lu(u_inlet)),
+            lo.outlet_p(direction, 1.0)]
+    obstacle, wall = g["obstacle_mask"].astype(bool), g["wall_mask"].astype(bool)
+    periodicity = (False, False) if d == 2 else (False, False, True)
+    cx, cy, radius = (float(v) for v in g["center"])
+    post_streaming = []
+    if walls == "bounceback":
+        post_streaming.append(lo.fullway_links(st, wall, periodicity))
+    if bc == "fwbb":
+        post_streaming.append(lo.fullway_links(st, obstacle, periodicity))
+    else:
+        post_streaming.append(lo.cylinder_links(st, obstacle, cx, cy, radius,
+                                                kind="halfway" if bc == "hwbb" else "interpolated"))
+    return st, units, dict(kind="bgk", tau=units.tau), post, post_streaming, int(steps)
+
+
+def index_rows(b):
+    return np.concatenate([b["q"][:, None], b["nodes"]], axis=1)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_link_lists_and_masks_match_reference(name):
+    g = load_golden(name)
+    st, units, coll, post, post_streaming, steps = ebb_setup(g)
+    bc, walls = g["meta"][1], g["meta"][2]
+    obstacle = post_streaming[-1]
+    if bc == "fwbb":
+        assert np.array_equal(index_rows(obstacle), g["f_index_fwbb"])
+    elif bc == "hwbb":
+        assert np.array_equal(index_rows(obstacle), g["f_index"])
+    else:
+        n_lt = len(g["d_lt"])
+        assert np.array_equal(index_rows(obstacle)[:n_lt], g["f_index_lt"])
+        assert np.array_equal(index_rows(obstacle)[n_lt:], g["f_index_gt"])
+        assert np.allclose(obstacle["d"][:n_lt], g["d_lt"], rtol=1e-13, atol=0)
+        assert np.allclose(obstacle["d"][n_lt:], g["d_gt"], rtol=1e-13, atol=0)
+        assert (obstacle["d"][:n_lt] <= 0.5).all() and (obstacle["d"][n_lt:] > 0.5).all()
+    if walls == "bounceback":
+        assert np.array_equal(index_rows(post_streaming[0]), g["wall_f_index_fwbb"])
+    ncm, nsm = lo.ebb_masks(st, g["f0"].shape[1:], [], post, post_streaming)
+    assert np.array_equal(ncm, g["ncm"]) and np.array_equal(nsm, g["nsm"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ebb_steps_and_force_match_reference(name):
+    g = load_golden(name)
+    st, units, coll, post, post_streaming, steps = ebb_setup(g)
+    f, forces = lo.ebb_run(st, g["f0"].copy(), steps, coll, [], post, post_streaming)
+    assert max_rel(f, g["f"]) < 1e-12
+    # components that vanish by symmetry are sums of cancelling terms: tolerance relative to the force's size
+    assert np.max(np.abs(forces[-1] - g["force"])) < 1e-12 * np.max(np.abs(g["force"]))
