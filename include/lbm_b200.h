@@ -166,6 +166,39 @@ size_t lbm_step_energy_scratch_bytes(const lbm_step_desc *desc);
 int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
                     size_t scratch_bytes, double *d_energy, void *stream);
 
+/* Link-wise bounce-back boundaries applied AFTER streaming -- the "efficient bounce-back" boundaries of the
+ * reference's example project examples/advanced_projects/efficient_bounce_back_obstacle: its EbbSimulation runs
+ * collide, stream, then every post_streaming_boundary (simulation/ebb_simulation.py:71-104).  A link is (node, q)
+ * with population q pointing from a fluid node into a solid node:
+ *   FULLWAY       link stored on the SOLID node: slot (opposite(q), node) <- slot (q, node) after streaming
+ *                 (boundary/fullway_bounce_back_boundary.py:132-155); force 2 sum e_q f_q (:157-170)
+ *   HALFWAY       link stored on the FLUID node: slot (opposite(q), node) <- fc_q(node), fc = populations between
+ *                 collision and streaming (boundary/halfway_bounce_back_boundary.py:167-182); force 2 sum e_q fc_q
+ *   INTERPOLATED  Bouzidi's linear interpolation with wall distance d in (0, 1]
+ *                 (boundary/linear_interpolated_bounce_back_boundary.py:57-100); force sum e_q (fc_q + bounced)
+ * All right-hand sides are evaluated before any slot is written, as in the reference. */
+typedef enum lbm_link_kind { LBM_LINK_FULLWAY = 0, LBM_LINK_HALFWAY = 1, LBM_LINK_INTERPOLATED = 2 } lbm_link_kind;
+
+typedef struct lbm_links {
+    int32_t kind; /* lbm_link_kind */
+    int32_t _pad;
+    int64_t n;            /* number of links (0 is allowed: nothing happens, force = 0) */
+    const int32_t *node;  /* flat node index (x slowest) */
+    const uint8_t *q;     /* population index of the link */
+    const void *d;        /* INTERPOLATED: n wall distances, dtype of the lattice; else NULL */
+    void *bounced;        /* scratch: n reals */
+    double *force_scratch; /* scratch: lbm_links_scratch_doubles(n) doubles, or NULL when no force is wanted */
+    double *force;        /* device, 3 doubles: momentum-exchange force in lattice units (x, y, z), or NULL */
+} lbm_links;
+
+int64_t lbm_links_scratch_doubles(int64_t n);
+
+/* Applies one post-streaming boundary to `d_f_post`, the output of lbm_step(desc, d_f_pre, d_f_post): `d_f_pre`
+ * must still hold the step's input (HALFWAY / INTERPOLATED re-evaluate the collide phase of their fluid nodes from
+ * it).  desc->streaming must be LBM_POST_STREAMING (collide, then stream, then this call). */
+int lbm_apply_links(const lbm_step_desc *desc, const lbm_links *links, const void *d_f_pre, void *d_f_post,
+                    void *stream);
+
 /* `n` consecutive steps ping-ponging between two buffers (a -> b -> a ...), without returning
  * to the caller in between: the loop `for _ in range(num_steps)` of Simulation.__call__
  * (lettuce/_simulation.py:317-318) when no reporter is due.  The newest populations end up in

@@ -43,6 +43,22 @@ static int launch_step(const StepParams<R> &p, int coll, int streaming, bool mas
 }
 
 template <class S, class R>
+static int launch_links(const StepParams<R> &p, const LinkArgs<R> &a, int coll, cudaStream_t stream) {
+    switch (coll) {
+        case LBM_OP_NO_COLLISION: return launch_links_coll<S, R, LBM_OP_NO_COLLISION>(p, a, stream);
+        case LBM_OP_BGK: return launch_links_coll<S, R, LBM_OP_BGK>(p, a, stream);
+        case LBM_OP_TRT: return launch_links_coll<S, R, LBM_OP_TRT>(p, a, stream);
+        case LBM_OP_KBC:
+            if constexpr (S::ID == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
+            else return launch_links_coll<S, R, LBM_OP_KBC>(p, a, stream);
+        case LBM_OP_REGULARIZED: return launch_links_coll<S, R, LBM_OP_REGULARIZED>(p, a, stream);
+        case LBM_OP_SMAGORINSKY: return launch_links_coll<S, R, LBM_OP_SMAGORINSKY>(p, a, stream);
+        case LBM_OP_BGK_FORCED: return launch_links_coll<S, R, LBM_OP_BGK_FORCED>(p, a, stream);
+    }
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+template <class S, class R>
 static const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int) {
     return masked ? "scalar_masked+general_nodes" : "scalar";
 }
@@ -116,6 +132,7 @@ static int validate_desc(const lbm_step_desc *d, Dims &dm) {
         }
     }
     if (d->n_ops > 1 && (!d->labels || !d->frozen)) return LBM_ERR_BAD_ARGUMENT;
+    if ((d->labels == nullptr) != (d->frozen == nullptr)) return LBM_ERR_BAD_ARGUMENT;
     if (d->n_general < 0 || (d->n_general > 0 && !d->general_nodes)) return LBM_ERR_BAD_ARGUMENT;
     if (d->ops[d->collision_index].kind == LBM_OP_KBC && d->lat.stencil == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
     return LBM_OK;
@@ -200,7 +217,7 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     fill_params<S, R>(d, dm, f_in, f_out, p);
     if (sync) p.sync = *sync;
     p.energy_partials = energy_partials;
-    const bool masked = d->n_ops > 1;
+    const bool masked = d->n_ops > 1 || d->labels != nullptr;
     return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, d->variant, st));
 }
 
@@ -344,7 +361,7 @@ int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, c
 extern "C" {
 
 static bool energy_fusable(const lbm_step_desc *desc) {
-    return desc && desc->n_ops == 1 && !(desc->streaming & LBM_POST_STREAMING);
+    return desc && desc->n_ops == 1 && !desc->labels && !(desc->streaming & LBM_POST_STREAMING);
 }
 
 size_t lbm_step_energy_scratch_bytes(const lbm_step_desc *desc) {
@@ -426,7 +443,7 @@ int capture_steps(const lbm_step_desc *desc, void *a, void *b, cudaGraphExec_t *
 int64_t graph_steps(const lbm_step_desc *desc, void *a, void *b, int64_t n, cudaStream_t stream, int *status) {
     *status = LBM_OK;
     lbm::Dims dm;
-    if (n < kGraphSteps || desc->n_ops != 1 || graph_max_nodes() <= 0 || lbm::lattice_dims(&desc->lat, dm)) return 0;
+    if (n < kGraphSteps || desc->n_ops != 1 || desc->labels || graph_max_nodes() <= 0 || lbm::lattice_dims(&desc->lat, dm)) return 0;
     if ((int64_t)dm.n0 * dm.n1 * dm.n2 > graph_max_nodes()) return 0;
     const lbm_halo &h = desc->halo;
     if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return 0;
@@ -469,6 +486,63 @@ int64_t graph_steps(const lbm_step_desc *desc, void *a, void *b, int64_t n, cuda
 
 }  // namespace
 
+// three rows of per-CTA partials + the staging row of the two-stage fold
+int64_t lbm_links_scratch_doubles(int64_t n) {
+    return n > 0 ? 3 * (int64_t)link_blocks(n) + (int64_t)(reduce_scratch_bytes() / sizeof(double)) : 0;
+}
+
+}  // extern "C"
+
+template <class S, class R>
+static int links_typed(const lbm_step_desc *desc, const Dims &dm, const lbm_links *l, const void *f_pre, void *f_post,
+                       cudaStream_t st) {
+    StepParams<R> p;
+    fill_params<S, R>(desc, dm, f_pre, f_post, p);
+    LinkArgs<R> a;
+    a.kind = l->kind;
+    a.n = (int)l->n;
+    a.node = l->node;
+    a.q = l->q;
+    a.d = (const R *)l->d;
+    a.bounced = (R *)l->bounced;
+    a.partials = l->force ? l->force_scratch : nullptr;
+    int e = launch_links<S, R>(p, a, desc->ops[desc->collision_index].kind, st);
+    if (e || !l->force) return cuda_fail(e);
+    // fold the per-CTA partials in a fixed order; internal axis order -> (x, y, z) of the caller
+    const int blocks = link_blocks(l->n);
+    for (int c = 0; c < 3; ++c) {
+        if (c < S::D && l->n > 0) {
+            e = launch_fold_sum(l->force_scratch + (size_t)S::axis_of(c) * blocks, blocks,
+                                l->force_scratch + (size_t)3 * blocks, l->force + c, st);
+        } else {
+            e = (int)cudaMemsetAsync(l->force + c, 0, sizeof(double), st);
+        }
+        if (e) return cuda_fail(e);
+    }
+    return LBM_OK;
+}
+
+extern "C" {
+
+int lbm_apply_links(const lbm_step_desc *desc, const lbm_links *links, const void *d_f_pre, void *d_f_post,
+                    void *stream) {
+    Dims dm;
+    int rc = validate_desc(desc, dm);
+    if (rc) return rc;
+    if (!links || !d_f_pre || !d_f_post || links->n < 0) return LBM_ERR_BAD_ARGUMENT;
+    if (links->kind < LBM_LINK_FULLWAY || links->kind > LBM_LINK_INTERPOLATED) return LBM_ERR_BAD_ARGUMENT;
+    if (desc->streaming != LBM_POST_STREAMING) return LBM_ERR_UNSUPPORTED;
+    if (links->n > 0 && (!links->node || !links->q || !links->bounced)) return LBM_ERR_BAD_ARGUMENT;
+    if (links->n > 0 && links->kind == LBM_LINK_INTERPOLATED && !links->d) return LBM_ERR_BAD_ARGUMENT;
+    if (links->force && links->n > 0 && !links->force_scratch) return LBM_ERR_BAD_ARGUMENT;
+    if (links->n > (int64_t)1 << 30) return LBM_ERR_TOO_LARGE;
+    const lbm_halo &h = desc->halo;
+    if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return LBM_ERR_UNSUPPORTED;      // single-GPU entry point
+    LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype,
+                 return (links_typed<S, R>(desc, dm, links, d_f_pre, d_f_post, (cudaStream_t)stream)));
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream) {
     if (n < 0 || !desc) return LBM_ERR_BAD_ARGUMENT;
     void *a = d_f_a, *b = d_f_b;
@@ -491,7 +565,7 @@ int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, v
 const char *lbm_step_variant_name(const lbm_step_desc *desc) {
     Dims dm;
     if (validate_desc(desc, dm)) return "invalid";
-    const bool masked = desc->n_ops > 1;
+    const bool masked = desc->n_ops > 1 || desc->labels != nullptr;
     LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype, {
         StepParams<R> p;
         fill_params<S, R>(desc, dm, nullptr, nullptr, p);

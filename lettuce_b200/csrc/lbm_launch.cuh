@@ -25,4 +25,9 @@ inline void bulk_geometry(int n0, int n1, int n2, dim3 &grid, dim3 &block) {
 template <class S, class R, int COLL>
 int launch_step_coll(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream);
 
+// link-wise post-streaming boundary (lbm_apply_links): gather kernel, then scatter kernel
+inline int link_blocks(int64_t n) { return (int)((n + kLinkThreads - 1) / kLinkThreads); }
+template <class S, class R, int COLL>
+int launch_links_coll(const StepParams<R> &p, const LinkArgs<R> &a, cudaStream_t stream);
+
 }  // namespace lbm

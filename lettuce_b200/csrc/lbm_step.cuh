@@ -13,6 +13,9 @@
 //                        dependent launch); the two kernels write disjoint slots
 //   step_sync_kernel     bulk kernel for multi-GPU slabs with the in-kernel lock step (SlabSync)
 //   step_energy_kernel   bulk kernel that also reduces the kinetic energy of its output (reporter fusion)
+//   link_gather_kernel / link_scatter_kernel
+//                        link-wise bounce-back boundaries applied AFTER streaming (fullway / halfway / linearly
+//                        interpolated, momentum-exchange force), sparse over the list of boundary links
 //
 // Planes x = -1 and x = n0 resolve to the wrapped plane of the same buffer (single GPU) or to a
 // peer-mapped plane of the neighbour rank's buffer (in_plane / out_plane).
@@ -206,10 +209,10 @@ __device__ void neighbour_state(const StepParams<R> &p, int i, int x, int y, int
     u[0] = j[0] * inv; u[1] = j[1] * inv; u[2] = j[2] * inv;
 }
 
-template <class S, class R, int COLL, bool PULL, bool PUSH>
-__device__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
+// populations of node (x,y,z) after the collide phase (all transformer entries), before any post-streaming
+template <class S, class R, int COLL, bool PULL>
+__device__ void node_pipeline(const StepParams<R> &p, int x, int y, int z, int label, R (&f)[S::Q]) {
     constexpr int Q = S::Q;
-    R f[Q];
     gather_node<S, R, PULL>(p, x, y, z, f);
 
     for (int i = 0; i < p.n_ops; ++i) {
@@ -259,6 +262,13 @@ __device__ void general_node(const StepParams<R> &p, int x, int y, int z, int la
             apply_local_op<S, R, COLL>(p, i, label, x, y, z, f);
         }
     }
+}
+
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+__device__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
+    constexpr int Q = S::Q;
+    R f[Q];
+    node_pipeline<S, R, COLL, PULL>(p, x, y, z, label, f);
 
     // scatter with the destination-side frozen-slot rule (_simulation.py:252-255):
     // slot (q, dst) takes the streamed value unless it is frozen, in which case the
@@ -447,6 +457,106 @@ __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constan
     const int y = (n / p.n2) % p.n1;
     const int x = n / (p.n1 * p.n2);
     general_node<S, R, COLL, PULL, PUSH>(p, x, y, z, p.labels[n] & 0x7f);
+}
+
+// ---------------------------------------------------------------------------
+// Link-wise bounce-back boundaries applied after streaming: the "efficient bounce-back" boundaries of the
+// reference's example project examples/advanced_projects/efficient_bounce_back_obstacle (ebb/ below).  A link is
+// (node, q): q points from a fluid node into a solid node.  FULLWAY links live on the solid node and reverse the
+// population that streamed in (ebb/boundary/fullway_bounce_back_boundary.py:132-155); HALFWAY and INTERPOLATED
+// links live on the fluid node and need the populations between collision and streaming, fc
+// (halfway_bounce_back_boundary.py:167-182, linear_interpolated_bounce_back_boundary.py:57-100).  The step kernels
+// do not keep fc (it streams away, or is dropped at the frozen solid node), so the gather kernel re-evaluates the
+// node's collide phase from the step's INPUT buffer, which the two-buffer scheme leaves intact.  Two kernels because
+// the reference evaluates every right-hand side before it assigns (a node with links q and opposite(q) swaps).
+// ---------------------------------------------------------------------------
+template <class R>
+struct LinkArgs {
+    int kind;                 // lbm_link_kind
+    int n;                    // number of links
+    const int32_t *node;      // flat node index
+    const uint8_t *q;         // population index pointing into the solid
+    const R *d;               // INTERPOLATED: wall distance in link lengths, (0, 1]
+    R *bounced;               // scratch [n]: value of slot (opposite(q), node) after the boundary
+    double *partials;         // [3][gridDim.x] momentum-exchange partial sums (internal axis order) or nullptr
+};
+
+constexpr int kLinkThreads = 128;
+
+template <class S, class R, int COLL>
+__global__ void __launch_bounds__(kLinkThreads) link_gather_kernel(const __grid_constant__ StepParams<R> p,
+                                                                     const LinkArgs<R> a) {
+    constexpr int Q = S::Q;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double force[3] = {0.0, 0.0, 0.0};
+    if (i < a.n) {
+        const int n = a.node[i];
+        const int q = a.q[i];
+        const R streamed = p.out[(int64_t)q * p.N + n];            // slot (q, node) after streaming
+        R val, mom;                                                 // new slot value; coefficient of e_q in the force
+        if (a.kind == LBM_LINK_FULLWAY) {
+            val = streamed;
+            mom = R(2) * streamed;                                  // fullway_bounce_back_boundary.py:157-170
+        } else {
+            const int z = n % p.n2;
+            const int y = (n / p.n2) % p.n1;
+            const int x = n / (p.n1 * p.n2);
+            R f[Q];
+            const int label = p.labels ? (p.labels[n] & 0x7f) : p.collision_index;
+            node_pipeline<S, R, COLL, false>(p, x, y, z, label, f);
+            R fcq = R(0), fco = R(0);                               // fc[q], fc[opposite(q)] of this node
+            ForQ<Q>::run([&]<int k>() {
+                if (k == q) {
+                    fcq = f[k];
+                    fco = f[S::opp(k)];
+                }
+            });
+            if (a.kind == LBM_LINK_HALFWAY) {
+                val = fcq;
+                mom = R(2) * fcq;                                   // halfway_bounce_back_boundary.py:206-215
+            } else {
+                const R d = a.d[i];
+                if (d <= R(0.5)) val = R(2) * d * fcq + (R(1) - R(2) * d) * streamed;
+                else val = (R(1) / (R(2) * d)) * fcq + (R(1) - R(1) / (R(2) * d)) * fco;
+                mom = fcq + val;                                    // linear_interpolated_...py:116-143
+            }
+        }
+        a.bounced[i] = val;
+        ForQ<Q>::run([&]<int k>() {
+            if (k == q) {
+                force[0] = (double)(R(S::e(k, 0)) * mom);
+                force[1] = (double)(R(S::e(k, 1)) * mom);
+                force[2] = (double)(R(S::e(k, 2)) * mom);
+            }
+        });
+    }
+    if (a.partials == nullptr) return;
+    __shared__ double warp_sum[3][kLinkThreads / 32];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double v = force[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) warp_sum[c][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int w = 0; w < kLinkThreads / 32; ++w) s += warp_sum[threadIdx.x][w];
+        a.partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+template <class S, class R>
+__global__ void __launch_bounds__(kLinkThreads) link_scatter_kernel(R *out, int64_t N, const LinkArgs<R> a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int q = a.q[i];
+    int o = 0;
+    ForQ<S::Q>::run([&]<int k>() {
+        if (k == q) o = S::opp(k);
+    });
+    out[(int64_t)o * N + a.node[i]] = a.bounced[i];
 }
 
 }  // namespace lbm

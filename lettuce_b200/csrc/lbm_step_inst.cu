@@ -98,6 +98,23 @@ int launch_step_coll(const StepParams<R> &p, int streaming, bool masked, int var
     return by_mask<S, R, COLL>(p, streaming, masked, variant, stream);
 }
 
+template <class S, class R, int COLL>
+int launch_links_coll(const StepParams<R> &p, const LinkArgs<R> &a, cudaStream_t stream) {
+    if (a.n <= 0) return 0;
+    const int blocks = link_blocks(a.n);
+    link_gather_kernel<S, R, COLL><<<blocks, kLinkThreads, 0, stream>>>(p, a);
+    ++g_launch_count;
+    int e = (int)cudaGetLastError();
+    if (e) return e;
+    link_scatter_kernel<S, R><<<blocks, kLinkThreads, 0, stream>>>(p.out, p.N, a);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
+template int launch_links_coll<LBM_INST_STENCIL, LBM_INST_REAL, LBM_INST_COLL>(const StepParams<LBM_INST_REAL> &,
+                                                                               const LinkArgs<LBM_INST_REAL> &,
+                                                                               cudaStream_t);
+
 template int launch_step_coll<LBM_INST_STENCIL, LBM_INST_REAL, LBM_INST_COLL>(const StepParams<LBM_INST_REAL> &, int,
                                                                               bool, int, cudaStream_t);
 

@@ -3,3 +3,4 @@ from .collision import *
 from .flows import *
 from .reporter import *
 from .vtk import *
+from .bounce_back import *

@@ -74,7 +74,13 @@ class LbmSlab(C.Structure):
                 ("epoch", C.c_uint64)]
 
 
-EXPORTS = ["lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
+class LbmLinks(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("n", C.c_int64),
+                ("node", C.c_void_p), ("q", C.c_void_p), ("d", C.c_void_p), ("bounced", C.c_void_p),
+                ("force_scratch", C.c_void_p), ("force", C.c_void_p)]
+
+
+EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
            "lbm_step", "lbm_step_n", "lbm_step_energy", "lbm_step_energy_scratch_bytes", "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
            "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
            "lbm_launch_count", "lbm_step_variant_name"]
@@ -100,6 +106,10 @@ def lib() -> C.CDLL:
     L.lbm_step_energy_scratch_bytes.restype = C.c_size_t
     L.lbm_step_energy.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, C.c_size_t, vp, vp]
     L.lbm_step_energy.restype = i32
+    L.lbm_links_scratch_doubles.argtypes = [i64]
+    L.lbm_links_scratch_doubles.restype = i64
+    L.lbm_apply_links.argtypes = [C.POINTER(LbmStepDesc), C.POINTER(LbmLinks), vp, vp, vp]
+    L.lbm_apply_links.restype = i32
     L.lbm_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
     L.lbm_ipc_alloc.restype = i32
     L.lbm_ipc_open.argtypes = [vp, C.POINTER(vp)]
@@ -263,7 +273,8 @@ class Engine:
         if dry:
             self.variant_name = "dry"
             return
-        if len(transformer) > 1:
+        if len(transformer) > 1 or getattr(simulation, "no_collision_mask", None) is not None:
+            # boundaries in the transformer list, or masks of post-streaming boundaries (EbbSimulation)
             self._pack_masks()
         self.variant_name = self.lib.lbm_step_variant_name(C.byref(self.desc)).decode()
 
@@ -430,6 +441,19 @@ class Engine:
         self.flow.f, self.flow.f_next = g, f
         self.flow._b200_energy = (g.data_ptr(), g._version, out)
         return out
+
+    def apply_links(self, boundary):
+        """One post-streaming link boundary (ext/bounce_back.py) on the populations the last `step(1)` produced:
+        `lbm_apply_links` with the step's input (now `flow.f_next`, left intact by the two-buffer scheme) and its
+        output (`flow.f`).  Updates the boundary's force if it was built with calc_force."""
+        if self.desc.streaming != POST_STREAMING:
+            raise RuntimeError("post-streaming boundaries need StreamingStrategy.POST_STREAMING "
+                               "(collide, stream, boundary: ebb_simulation.py:71-104)")
+        f_post, f_pre = self._buffers()
+        links = boundary.link_descriptor(f_post)
+        with torch.cuda.device(self.device):
+            check(self.lib.lbm_apply_links(C.byref(self.desc), C.byref(links), f_pre.data_ptr(), f_post.data_ptr(),
+                                           _stream_ptr(self.device)), "lbm_apply_links")
 
     def _variant_of(self, streaming: int, stream_only: bool = False) -> LbmStepDesc:
         d = LbmStepDesc.from_buffer_copy(self.desc)

@@ -75,3 +75,38 @@ def test_ebb_steps_and_force_match_reference(name):
     assert max_rel(f, g["f"]) < 1e-12
     # components that vanish by symmetry are sums of cancelling terms: tolerance relative to the force's size
     assert np.max(np.abs(forces[-1] - g["force"])) < 1e-12 * np.max(np.abs(g["force"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_package_host_side_matches_reference(name):
+    """lettuce_b200's ObstacleCylinder / EbbSimulation / link boundaries on a CPU context (host logic only, no
+    kernels): initial populations, label and no-streaming masks, link lists and wall distances"""
+    import torch
+    import lettuce_b200 as lt
+    g = load_golden(name)
+    stencil, bc, walls, steps, diameter = g["meta"]
+    res = [int(r) for r in g["res"]]
+    flow = lt.ObstacleCylinder(lt.Context("cpu", dtype=torch.float64), res, 100.0, 0.05, char_length_pu=1.0,
+                               char_length_lu=float(diameter), bc_type=bc, lateral_walls=walls,
+                               calc_force_coefficients=True, u_init=1, perturb_init=len(res) == 2,
+                               stencil={"D2Q9": lt.D2Q9, "D3Q19": lt.D3Q19, "D3Q27": lt.D3Q27}[stencil]())
+    assert max_rel(flow.f.numpy(), g["f0"]) < 1e-14
+    assert flow.units.relaxation_parameter_lu == pytest.approx(float(g["tau"]), rel=1e-14)
+    sim = lt.EbbSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+    assert np.array_equal(sim.no_collision_mask.numpy(), g["ncm"])
+    assert np.array_equal(sim.no_streaming_mask.numpy(), g["nsm"])
+    obstacle = sim.post_streaming_boundaries[-1]
+    if bc == "fwbb":
+        assert np.array_equal(obstacle.f_index_fwbb.numpy(), g["f_index_fwbb"])
+    elif bc == "hwbb":
+        assert np.array_equal(obstacle.f_index.numpy(), g["f_index"])
+    else:
+        assert np.array_equal(obstacle.f_index_lt.numpy(), g["f_index_lt"])
+        assert np.array_equal(obstacle.f_index_gt.numpy(), g["f_index_gt"])
+        assert np.allclose(obstacle.d_lt.numpy(), g["d_lt"], rtol=1e-13, atol=0)
+        assert np.allclose(obstacle.d_gt.numpy(), g["d_gt"], rtol=1e-13, atol=0)
+    if walls == "bounceback":
+        assert np.array_equal(sim.post_streaming_boundaries[0].f_index_fwbb.numpy(), g["wall_f_index_fwbb"])
+    assert [o["kind"] for o in lt.native.describe(sim)["ops"]] == [1, 17, 18]     # BGK, inlet, outlet
+    with pytest.raises(AttributeError):
+        lt.FullwayBounceBackBoundary(flow.context, flow, flow.wall_mask).force_sum
