@@ -223,6 +223,35 @@ def test_ctypes_struct_layout_matches_header():
     assert ctypes.sizeof(native.LbmLattice) == 24
     assert ctypes.sizeof(native.LbmHalo) == 12 * 8
     assert ctypes.sizeof(native.LbmStepDesc) == 24 + 16 + 8 * 144 + 16 + 16 + 96
+    assert ctypes.sizeof(native.LbmLinks) == 8 + 8 + 6 * 8
+
+
+def test_link_boundary_validation_without_gpu():
+    """lbm_apply_links checks its arguments before any CUDA call"""
+    L = native.lib()
+    d = native.LbmStepDesc()
+    d.lat = native.LbmLattice(native.D2Q9, native.F64, 8, 8, 1, 0)
+    d.streaming, d.n_ops, d.collision_index = 1, 1, 0
+    d.ops[0].kind, d.ops[0].p0 = native.OP_BGK, 0.6
+    links = native.LbmLinks()
+    links.kind, links.n = 1, 4
+    links.node, links.q, links.bounced = 1 << 20, 1 << 21, 1 << 22
+    pre, post = 1 << 24, 1 << 26
+    assert L.lbm_links_scratch_doubles(0) == 0 and L.lbm_links_scratch_doubles(129) > 3 * 2
+    assert L.lbm_apply_links(ctypes.byref(d), None, pre, post, None) == -1
+    links.kind = 7
+    assert L.lbm_apply_links(ctypes.byref(d), ctypes.byref(links), pre, post, None) == -1        # unknown kind
+    links.kind = 2
+    assert L.lbm_apply_links(ctypes.byref(d), ctypes.byref(links), pre, post, None) == -1        # interpolated without d
+    links.kind = 1
+    links.force = 1 << 23
+    assert L.lbm_apply_links(ctypes.byref(d), ctypes.byref(links), pre, post, None) == -1        # force without scratch
+    links.force = None
+    d.streaming = 2
+    assert L.lbm_apply_links(ctypes.byref(d), ctypes.byref(links), pre, post, None) == -2        # needs POST_STREAMING
+    d.streaming = 1
+    d.labels = 1 << 27
+    assert L.lbm_apply_links(ctypes.byref(d), ctypes.byref(links), pre, post, None) == -1        # labels without frozen
 
 
 def test_descriptor_validation_without_gpu():
