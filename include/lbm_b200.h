@@ -199,6 +199,12 @@ int64_t lbm_links_scratch_doubles(int64_t n);
 int lbm_apply_links(const lbm_step_desc *desc, const lbm_links *links, const void *d_f_pre, void *d_f_post,
                     void *stream);
 
+/* `n` time steps of EbbSimulation.__call__ without returning to the caller (ebb_simulation.py:93-104 when no reporter
+ * is due): each step is lbm_step(desc, a, b) followed by lbm_apply_links for the `n_boundaries` entries of `links` in
+ * order, then the buffers swap roles.  The newest populations end up in d_f_b if n is odd, in d_f_a if n is even. */
+int lbm_step_links_n(const lbm_step_desc *desc, const lbm_links *links, int32_t n_boundaries, void *d_f_a,
+                     void *d_f_b, int64_t n, void *stream);
+
 /* `n` consecutive steps ping-ponging between two buffers (a -> b -> a ...), without returning
  * to the caller in between: the loop `for _ in range(num_steps)` of Simulation.__call__
  * (lettuce/_simulation.py:317-318) when no reporter is due.  The newest populations end up in

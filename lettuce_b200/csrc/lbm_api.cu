@@ -543,6 +543,19 @@ int lbm_apply_links(const lbm_step_desc *desc, const lbm_links *links, const voi
     return LBM_ERR_BAD_ARGUMENT;
 }
 
+int lbm_step_links_n(const lbm_step_desc *desc, const lbm_links *links, int32_t n_boundaries, void *d_f_a,
+                     void *d_f_b, int64_t n, void *stream) {
+    if (n < 0 || n_boundaries < 0 || (n_boundaries > 0 && !links)) return LBM_ERR_BAD_ARGUMENT;
+    void *a = d_f_a, *b = d_f_b;
+    for (int64_t k = 0; k < n; ++k) {
+        int rc = lbm_step(desc, a, b, stream);
+        for (int32_t i = 0; i < n_boundaries && !rc; ++i) rc = lbm_apply_links(desc, &links[i], a, b, stream);
+        if (rc) return rc;
+        void *t = a; a = b; b = t;
+    }
+    return LBM_OK;
+}
+
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream) {
     if (n < 0 || !desc) return LBM_ERR_BAD_ARGUMENT;
     void *a = d_f_a, *b = d_f_b;

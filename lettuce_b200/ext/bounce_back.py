@@ -16,7 +16,7 @@ gather all right-hand sides incl. the force partials, then scatter), after the o
 """
 from __future__ import annotations
 
-import ctypes as C
+import os
 from timeit import default_timer as timer
 from typing import List, Optional
 
@@ -285,11 +285,19 @@ class EbbSimulation(Simulation):
         beg = timer()
         if self.flow.i == 0:
             self._report()
-        for _ in range(int(num_steps)):
-            self._collide_and_stream(self)
-            self._post_streaming_boundaries()
-            self.flow.i += 1
+        batched = os.environ.get("LBM_B200_EBB_BATCH", "0") == "1" and self._collide_and_stream is native.invoke
+        remaining = int(num_steps)
+        while remaining > 0:
+            # opt-in (not yet measured on hardware): the steps up to the next due reporter in one library call
+            k = self._batch_length(remaining) if batched else 1
+            if batched:
+                native.engine_of(self).step_with_links(self.post_streaming_boundaries, k)
+            else:
+                self._collide_and_stream(self)
+                self._post_streaming_boundaries()
+            self.flow.i += k
             self._report()
+            remaining -= k
         self.context.synchronize()
         end = timer()
         return num_steps * int(np.prod(self.flow.resolution)) / 1e6 / (end - beg)

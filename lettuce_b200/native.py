@@ -80,7 +80,7 @@ class LbmLinks(C.Structure):
                 ("force_scratch", C.c_void_p), ("force", C.c_void_p)]
 
 
-EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
+EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_step_links_n", "lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
            "lbm_step", "lbm_step_n", "lbm_step_energy", "lbm_step_energy_scratch_bytes", "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
            "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
            "lbm_launch_count", "lbm_step_variant_name"]
@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
     L.lbm_links_scratch_doubles.restype = i64
     L.lbm_apply_links.argtypes = [C.POINTER(LbmStepDesc), C.POINTER(LbmLinks), vp, vp, vp]
     L.lbm_apply_links.restype = i32
+    L.lbm_step_links_n.argtypes = [C.POINTER(LbmStepDesc), C.POINTER(LbmLinks), i32, vp, vp, i64, vp]
+    L.lbm_step_links_n.restype = i32
     L.lbm_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
     L.lbm_ipc_alloc.restype = i32
     L.lbm_ipc_open.argtypes = [vp, C.POINTER(vp)]
@@ -454,6 +456,25 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.lbm_apply_links(C.byref(self.desc), C.byref(links), f_pre.data_ptr(), f_post.data_ptr(),
                                            _stream_ptr(self.device)), "lbm_apply_links")
+
+    def step_with_links(self, boundaries, n: int):
+        """`n` time steps, each followed by the post-streaming `boundaries` in order, in one library call
+        (`lbm_step_links_n`)."""
+        if n <= 0:
+            return
+        if self.desc.streaming != POST_STREAMING:
+            raise RuntimeError("post-streaming boundaries need StreamingStrategy.POST_STREAMING")
+        self.refresh_parameters()
+        f, g = self._buffers()
+        self.flow._b200_energy = None
+        array = (LbmLinks * max(len(boundaries), 1))()
+        for i, boundary in enumerate(boundaries):
+            array[i] = boundary.link_descriptor(f)
+        with torch.cuda.device(self.device):
+            check(self.lib.lbm_step_links_n(C.byref(self.desc), array, len(boundaries), f.data_ptr(), g.data_ptr(), n,
+                                            _stream_ptr(self.device)), "lbm_step_links_n")
+        if n & 1:
+            self.flow.f, self.flow.f_next = g, f
 
     def _variant_of(self, streaming: int, stream_only: bool = False) -> LbmStepDesc:
         d = LbmStepDesc.from_buffer_copy(self.desc)

@@ -107,3 +107,23 @@ def test_ebb_rejects_pre_streaming():
     sim.streaming_strategy = lt.StreamingStrategy.PRE_STREAMING
     with pytest.raises(RuntimeError):
         sim(1)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("LBM_B200_EXPERIMENTAL") != "1",
+                    reason="lbm_step_links_n (LBM_B200_EBB_BATCH=1) is written but not yet run on hardware; "
+                           "set LBM_B200_EXPERIMENTAL=1 to include it")
+def test_ebb_batched_library_call_equals_step_by_step(monkeypatch):
+    g = load_golden("ebb3d_hwbb_walls")
+    results = []
+    for batch in ("0", "1"):
+        monkeypatch.setenv("LBM_B200_EBB_BATCH", batch)
+        flow, steps = make_flow(g, torch.float64)
+        flow.f = flow.context.convert_to_tensor(g["f0"]).contiguous()
+        sim = lt.EbbSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+        drag = lt.ObservableReporter(lt.DragCoefficient(flow, sim.post_streaming_boundaries[-1], flow.solid_mask, 1.0),
+                                     interval=4, out=None)
+        sim.reporter.append(drag)
+        sim(steps + 1)                                   # odd number of steps: buffer parity
+        results.append((flow.f.clone(), [r[2] for r in drag.out]))
+    assert torch.equal(results[0][0], results[1][0])
+    assert results[0][1] == results[1][1]
