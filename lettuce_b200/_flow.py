@@ -19,7 +19,7 @@ import torch
 from . import native
 from ._stencil import TorchStencil
 
-__all__ = ["Equilibrium", "Boundary", "Flow", "QuadraticEquilibrium", "initialize_f_neq"]
+__all__ = ["Equilibrium", "Boundary", "Flow", "QuadraticEquilibrium", "initialize_f_neq", "pressure_poisson"]
 
 
 class Equilibrium(ABC):
@@ -116,12 +116,11 @@ class Flow(ABC):
     def initialize(self):
         """Equilibrium initialisation from `initial_pu`, optionally with first-order
         non-equilibrium (lettuce/_flow.py:127-143)."""
-        if self.initialize_pressure:
-            raise NotImplementedError("pressure-Poisson initialisation is outside the B200 hot path "
-                                      "(lettuce/_flow.py:271-320)")
         p, u = self.initial_pu()
         rho = self.context.convert_to_tensor(self.units.convert_pressure_pu_to_density_lu(p))
         u = self.context.convert_to_tensor(self.units.convert_velocity_to_lu(u))
+        if self.initialize_pressure:
+            rho = pressure_poisson(self.units, u, rho)
         if u.is_cuda and type(self.equilibrium) is QuadraticEquilibrium and u.dim() == self.stencil.d + 1:
             # one kernel, no full-size temporaries (the torch expression needs ~6x the size of f)
             self.f = native.equilibrium_field(self.stencil, rho, u, self.resolution)
@@ -202,6 +201,33 @@ def _gradient6(a: torch.Tensor) -> torch.Tensor:
     weights = (-1 / 60, 3 / 20, -3 / 4, 3 / 4, -3 / 20, 1 / 60)
     shifts = (3, 2, 1, -1, -2, -3)
     return torch.stack([sum(w * a.roll(s, dims=ax) for w, s in zip(weights, shifts)) for ax in range(a.dim())])
+
+
+def _gradient2(a: torch.Tensor, dx) -> torch.Tensor:
+    """2nd-order periodic central differences along every axis (lettuce/util/utility.py:37-99, order=2)"""
+    return torch.stack([(-0.5 * a.roll(1, dims=ax) + 0.5 * a.roll(-1, dims=ax)) for ax in range(a.dim())]) \
+        * torch.tensor(1.0 / dx, dtype=a.dtype, device=a.device)
+
+
+def pressure_poisson(units, u: torch.Tensor, rho0: torch.Tensor, tol_abs=1e-10, max_num_steps=100000) -> torch.Tensor:
+    """Density whose pressure solves lap p = -d_i d_j (u_i u_j), by Jacobi iteration on the periodic lattice
+    (lettuce/_flow.py:271-320 with util/utility.py:119-156).  Like the reference it treats the first two axes
+    (`dim=2`) -- "still not working in 3D" there.  Initial-condition helper: plain torch on the context device."""
+    dx = units.convert_length_to_pu(1.0)
+    u = units.convert_velocity_to_pu(u)
+    p = units.convert_density_lu_to_pressure_pu(rho0)[0]
+    rhs = torch.zeros_like(u[0])
+    for i in range(u.shape[0]):
+        for j in range(u.shape[0]):
+            rhs -= _gradient2(_gradient2(u[i] * u[j], dx)[i], dx)[j]
+    neighbours = lambda q: q.roll(1, dims=0) + q.roll(1, dims=1) + q.roll(-1, dims=0) + q.roll(-1, dims=1)
+    error, it = 1.0, 0
+    while error > tol_abs and it < max_num_steps:
+        it += 1
+        p = (rhs * dx ** 2 - neighbours(p)) * -1 / 4
+        residuum = rhs - (neighbours(p) - 4 * p) / dx ** 2
+        error = float(torch.mean(residuum ** 2))
+    return units.convert_pressure_pu_to_density_lu(p[None, ...])
 
 
 def initialize_f_neq(flow: Flow) -> torch.Tensor:

@@ -13,10 +13,10 @@ import sys
 import numpy as np
 
 from . import (BGKCollision, Context, D2Q9, D3Q19, D3Q27, ErrorReporter, Simulation, StreamingStrategy,
-               TaylorGreenVortex, __version__)
+               TaylorGreenVortex, __version__, flow_by_name)
 
-FLOWS = {"taylor2d": (TaylorGreenVortex, D2Q9), "taylor3d": (TaylorGreenVortex, D3Q27),
-         "taylor3d_d3q19": (TaylorGreenVortex, D3Q19)}
+# the reference's registry (lettuce/ext/_flows/_flow_by_name.py) plus a short name for the D3Q27 vortex
+FLOWS = {**flow_by_name, "taylor3d": (TaylorGreenVortex, D3Q27)}
 
 
 @click.group()

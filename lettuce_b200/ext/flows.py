@@ -14,7 +14,8 @@ from .._stencil import D2Q9, D3Q19
 from ..units import UnitConversion
 from .boundary import AntiBounceBackOutlet, BounceBackBoundary, EquilibriumBoundaryPU
 
-__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D", "Cavity2D", "DoublyPeriodicShear2D"]
+__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D", "Cavity2D", "DoublyPeriodicShear2D",
+           "CouetteFlow2D", "LambOseenVortex2D", "DecayingTurbulence", "flow_by_name"]
 
 
 class ExtFlow(Flow):
@@ -294,3 +295,208 @@ class DoublyPeriodicShear2D(ExtFlow):
     @property
     def post_boundaries(self):
         return []
+
+
+
+class CouetteFlow2D(ExtFlow):
+    """Plane Couette flow, initially at rest: equilibrium "moving wall" on column y = 1, bounce-back on y = ny-1
+    (lettuce/ext/_flows/couette.py:16-75)."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None):
+        self.u0 = 0
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, stencil, equilibrium)
+
+    def make_resolution(self, resolution, stencil=None) -> List[int]:
+        return [resolution] * 2 if isinstance(resolution, int) else list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution) -> UnitConversion:
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0], characteristic_length_pu=1,
+                              characteristic_velocity_pu=self.u0)
+
+    def analytic_solution(self):
+        _, y = self.grid
+        return self.context.convert_to_tensor(torch.stack([y / self.resolution[0] + self.u0]))
+
+    def initial_pu(self):
+        zeros = self.context.zero_tensor(self.resolution)
+        return zeros[None, ...], torch.stack([zeros, zeros], dim=0)
+
+    @property
+    def grid(self):
+        axes = [torch.linspace(0, 1, steps=n, device=self.context.device, dtype=self.context.dtype)
+                for n in self.resolution]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    @property
+    def post_boundaries(self):
+        top = torch.zeros(self.resolution, dtype=torch.bool)
+        top[:, 1] = True
+        bottom = torch.zeros(self.resolution, dtype=torch.bool)
+        bottom[:, -1] = True
+        return [EquilibriumBoundaryPU(flow=self, context=self.context, mask=top, velocity=np.array([1.0, 0.0])),
+                BounceBackBoundary(bottom)]
+
+
+class LambOseenVortex2D(ExtFlow):
+    """Lamb-Oseen vortex convected with `velocity_init` on a periodic box (Wissocq et al. 2017;
+    lettuce/ext/_flows/lamboseenvortex.py:19-134)."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None,
+                 initialize_fneq: bool = True, velocity_init=1, K=None, xc: int = None):
+        self.initialize_fneq = initialize_fneq
+        self.velocity_init = velocity_init
+        if stencil is None and not isinstance(resolution, list):
+            self.stencil = D2Q9()
+        else:
+            self.stencil = stencil() if callable(stencil) else stencil
+        first = resolution if isinstance(resolution, int) else resolution[0]
+        self.xc = first // 2 if xc is None else xc
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, self.stencil, equilibrium)
+
+    def make_resolution(self, resolution, stencil=None) -> List[int]:
+        if isinstance(resolution, int):
+            return [resolution] * self.stencil.d
+        assert len(resolution) == 2, "expected 2-dimensional resolution"
+        return list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution) -> UnitConversion:
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0], characteristic_length_pu=1,
+                              characteristic_velocity_pu=1)
+
+    @property
+    def grid(self):
+        axes = [self.units.convert_length_to_pu(torch.arange(0, n, device=self.context.device,
+                                                             dtype=self.context.dtype)) for n in self.resolution]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    def initial_pu(self):
+        return self.initial_lamboseenvortex()
+
+    def initial_lamboseenvortex(self):
+        units = self.units
+        yc = self.resolution[1] * 0.5
+        x, y = (units.convert_length_to_lu(g) for g in self.grid)
+        ux0 = units.convert_velocity_to_lu(self.velocity_init)
+        beta, rc, gamma, cv = 0.5, 20.0, 0.5, 1.0 / 3.0
+        r2 = (x - self.xc) ** 2 + (y - yc) ** 2
+        density = torch.pow(1.0 - (beta * ux0) ** 2 / (2.0 * cv) * torch.exp(1.0 - r2 / (2.0 * rc)),
+                            1.0 / (gamma - 1.0))
+        decay = torch.exp(-r2 / (2.0 * rc))
+        ux = ux0 - beta * ux0 * (y - yc) / rc * decay
+        uy = beta * ux0 * (x - self.xc) / rc * decay
+        return (units.convert_density_lu_to_pressure_pu(density),
+                torch.stack([units.convert_velocity_to_pu(ux), units.convert_velocity_to_pu(uy)], dim=0))
+
+    @property
+    def post_boundaries(self):
+        return []
+
+
+class DecayingTurbulence(ExtFlow):
+    """Homogeneous isotropic turbulence with a prescribed initial spectrum E(k) ~ k^4 exp(-2 (k/k0)^2), random
+    phases (`randseed`), divergence removed in spectral space; 2-D runs start from the pressure-Poisson solution
+    (lettuce/ext/_flows/decayingturbulence.py:23-189).  The characteristic velocity is set from the field."""
+
+    def __init__(self, context, resolution, reynolds_number, mach_number, k0=20, ic_energy=0.5, stencil=None,
+                 equilibrium=None, initialize_pressure: bool = True, initialize_fneq: bool = True, randseed=None):
+        self.initialize_pressure = initialize_pressure
+        self.initialize_fneq = initialize_fneq
+        self.randseed, self.k0, self.ic_energy = randseed, k0, ic_energy
+        self.wavenumbers, self.spectrum = [], []
+        if stencil is None:
+            stencil = D2Q9() if len(resolution) == 2 else D3Q19()
+        stencil = stencil() if callable(stencil) else stencil
+        if stencil.d != 2:
+            self.initialize_pressure = False
+        ExtFlow.__init__(self, context, resolution, reynolds_number, mach_number, stencil, equilibrium)
+
+    def make_resolution(self, resolution, stencil=None) -> List[int]:
+        if isinstance(resolution, int):
+            st = stencil() if callable(stencil) else stencil
+            return [resolution] * st.d
+        return list(resolution)
+
+    def make_units(self, reynolds_number, mach_number, resolution) -> UnitConversion:
+        return UnitConversion(reynolds_number=reynolds_number, mach_number=mach_number,
+                              characteristic_length_lu=resolution[0], characteristic_length_pu=2 * np.pi,
+                              characteristic_velocity_pu=None)
+
+    def analytic_solution(self, x, t=0):
+        return
+
+    def _generate_wavenumbers(self):
+        self.dimensions = tuple(self.resolution)
+        frequencies = [np.fft.fftfreq(n, d=1 / n) for n in self.dimensions]
+        wavenumber = np.meshgrid(*frequencies)          # default 'xy' indexing, as in the reference (:66)
+        wavenorms = np.linalg.norm(wavenumber, axis=0)
+        self.wavenumbers = np.arange(int(np.max(wavenorms)))
+        return wavenorms, wavenumber
+
+    def _generate_spectrum(self):
+        wavenorms, wavenumber = self._generate_wavenumbers()
+        ek = wavenorms ** 4 * np.exp(-2 * (wavenorms / self.k0) ** 2)
+        ek /= np.sum(ek)
+        ek *= self.ic_energy
+        shell = np.clip(np.ceil(wavenorms - 0.5), 0, len(self.wavenumbers)).astype(np.int64)
+        self.spectrum = np.bincount(shell.ravel(), weights=ek.ravel(),
+                                    minlength=len(self.wavenumbers) + 1)[:len(self.wavenumbers)]
+        return ek, wavenumber
+
+    def _generate_initial_velocity(self, ek, wavenumber):
+        d = self.stencil.d
+        axes = tuple(range(d))
+        dx = self.units.convert_length_to_pu(1.0)
+        np.random.seed(self.randseed)
+        phases = np.random.random(np.array(wavenumber).shape) * 2 * np.pi + 0j
+        uh = [np.fft.fftn(phases[a], axes=axes) for a in range(d)]
+        for a in range(d):
+            uh[a].ravel()[0] = 0
+        uh = [np.sqrt(2 / d * ek / (uh[a].imag ** 2 + uh[a].real ** 2 + 1.e-15)) * uh[a] for a in range(d)]
+        for a in range(d):
+            uh[a].ravel()[0] = 0
+        # remove the divergence with the modified wavenumber sin(k dx)/dx of 2nd-order central differences
+        kmod = [np.sin(wavenumber[a] * dx) / dx for a in range(d)]
+        knorm = np.linalg.norm(kmod, axis=0) + 1e-16
+        divergence = sum(kmod[a] * uh[a] for a in range(d))
+        uh = [uh[a] - divergence * kmod[a] / knorm ** 2 for a in range(d)]
+        for a in range(d):
+            uh[a].ravel()[0] = 0
+        e_kin = 0.5 * sum(np.sum(uh[a].real ** 2 + uh[a].imag ** 2) for a in range(d))
+        factor = np.sqrt(self.ic_energy / e_kin)
+        norm = (self.resolution[0] * dx ** (1 - d) * np.sqrt(self.units.characteristic_length_pu)) if d == 3 \
+            else (self.resolution[0] / dx)
+        return np.asarray([(np.fft.ifftn(uh[a] * factor, axes=axes) * norm).real for a in range(d)])
+
+    def initial_pu(self):
+        ek, wavenumber = self._generate_spectrum()
+        u = self._generate_initial_velocity(ek, wavenumber)
+        self.units.characteristic_velocity_pu = np.linalg.norm(u, axis=0).max()
+        return np.zeros(self.dimensions)[None, ...], u
+
+    @property
+    def energy_spectrum(self):
+        return self.spectrum, self.wavenumbers
+
+    @property
+    def grid(self):
+        axes = [torch.linspace(0, 2 * torch.pi * (1 - 1 / n), steps=n, device=self.context.device,
+                               dtype=self.context.dtype) for n in self.resolution]
+        return torch.meshgrid(*axes, indexing="ij")
+
+    @property
+    def post_boundaries(self):
+        return []
+
+
+def _flow_table():
+    from .._stencil import D3Q27
+    return {"taylor2d": (TaylorGreenVortex, D2Q9), "taylor3d_d3q19": (TaylorGreenVortex, D3Q19),
+            "taylor3d_d3q27": (TaylorGreenVortex, D3Q27), "poiseuille2d": (PoiseuilleFlow2D, D2Q9),
+            "shear2d": (DoublyPeriodicShear2D, D2Q9), "couette2d": (CouetteFlow2D, D2Q9),
+            "decay2d": (DecayingTurbulence, D2Q9), "lamboseen": (LambOseenVortex2D, D2Q9)}
+
+
+# name -> (flow class, stencil class), the registry behind `lettuce benchmark -f` (lettuce/ext/_flows/_flow_by_name.py)
+flow_by_name = _flow_table()

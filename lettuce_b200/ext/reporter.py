@@ -16,7 +16,7 @@ from .. import native
 from .._simulation import Reporter
 
 __all__ = ["Observable", "ObservableReporter", "MaximumVelocity", "IncompressibleKineticEnergy",
-           "Enstrophy", "EnergySpectrum", "Mass", "FailureReporterBase", "NaNReporter", "HighMaReporter", "ErrorReporter"]
+           "Enstrophy", "EnergySpectrum", "Mass", "ProgressReporter", "FailureReporterBase", "NaNReporter", "HighMaReporter", "ErrorReporter"]
 
 
 class Observable(ABC):
@@ -256,3 +256,68 @@ class ErrorReporter(Reporter):
             self.out.append([err_u, err_p])
         else:
             print(err_u, err_p, file=self.out)
+
+
+class ProgressReporter(Reporter):
+    """Logs wall time, time per step and the estimated time of completion every `interval` steps to
+    `<outdir>/progress_reporter_log.txt` and optionally to stdout
+    (lettuce/ext/_reporter/progress_reporter.py:12-137).  Reads no device data, so it never synchronises."""
+    batchable = True
+
+    def __init__(self, interval=1000, t_max=0, i_target=0, i_start=0, outdir=None, print_message=False,
+                 checkpoint=False):
+        super().__init__(interval)
+        self.t_max, self.i_start, self.i_target = t_max, i_start, i_target
+        self.outdir = None if outdir is None else str(outdir)
+        self.print_message, self.checkpoint = print_message, checkpoint
+        if self.outdir is not None:
+            import os
+            os.makedirs(self.outdir, exist_ok=True)
+        self.running = False
+        self.t_start = 0.0
+        self.t_elapsed = 0.0
+
+    def _log(self, line: str):
+        if self.outdir is not None:
+            import os
+            with open(os.path.join(self.outdir, "progress_reporter_log.txt"), "a") as fh:
+                fh.write(line + "\n")
+        if self.print_message:
+            print(line)
+
+    def start_timer(self):
+        from timeit import default_timer as timer
+        self.running = True
+        self.t_start = timer()
+        self.t_elapsed = 0.0
+        self._log(f"t_start: {self.t_start}, interval: {self.interval}, i_target: {self.i_target}")
+        self._log("|".join(["timestamp ".center(13), "step".center(10), "t_now".center(10), "t_elapsed".center(10),
+                            "t_per_step".center(10), "t_remain(est)".center(15), "t_total(est)".center(15),
+                            "DATE_FINISH(est)".center(20), " T WARNING"]))
+
+    def __call__(self, simulation):
+        import datetime
+        from timeit import default_timer as timer
+        if not self.running:
+            self.start_timer()
+            return
+        i = simulation.flow.i
+        if i % self.interval != 0:
+            return
+        now = datetime.datetime.now()
+        t_now = timer()
+        self.t_elapsed = t_now - self.t_start
+        t_per_step = self.t_elapsed / (self.interval if i == self.i_start else (i - self.i_start))
+        t_remaining = t_per_step * (self.i_target - i)
+        t_total = self.t_elapsed + t_remaining
+        finish = now + datetime.timedelta(seconds=t_remaining)
+        line = " ".join([now.strftime("%y%m%d_%H%M%S").ljust(13), str(i).rjust(10), f"{t_now:.2f}".rjust(10),
+                         f"{self.t_elapsed:.2f}".rjust(10), f"{t_per_step:.6f}".rjust(10),
+                         f"{t_remaining:.2f}".rjust(15), f"{t_total:.2f}".rjust(15),
+                         " " + finish.strftime("%Y-%m-%d %H:%M:%S").ljust(20)])
+        if t_total > self.t_max:
+            line += f" WARNING t_total>t_max={self.t_max}"
+        self._log(line)
+        if self.checkpoint and self.t_elapsed > self.t_max and self.outdir is not None:
+            import os
+            simulation.flow.dump(os.path.join(self.outdir, f"{now.strftime('%y%m%d_%H%M%S')}_f_{i}.cpt"))

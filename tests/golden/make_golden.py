@@ -280,6 +280,23 @@ def stock_obstacle_case():
     obstacle_case("obstacle3d_abb_bgk", lt.Obstacle, "D3Q19", [24, 12, 12], "bgk", 8, ["POST_STREAMING"])
 
 
+def more_flows_case():
+    """Initial states of the remaining entries of flow_by_name (lettuce/ext/_flows/_flow_by_name.py): Lamb-Oseen
+    vortex, decaying turbulence (2-D with the pressure-Poisson start, 3-D without), Couette masks."""
+    ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+    out = {}
+    out["lamb_f0"] = npy(lt.LambOseenVortex2D(ctx, [48, 40], 100, 0.05).f)
+    decay = lt.DecayingTurbulence(ctx, [32, 32], 1000, 0.05, k0=4, randseed=3)
+    out["decay2d_f0"] = npy(decay.f)
+    out["decay2d_spectrum"] = np.asarray(decay.energy_spectrum[0])
+    out["decay2d_tau"] = np.float64(decay.units.relaxation_parameter_lu)
+    out["decay3d_f0"] = npy(lt.DecayingTurbulence(ctx, [12, 12, 12], 1000, 0.05, k0=3, randseed=5).f)
+    couette = lt.Simulation(lt.CouetteFlow2D(ctx, [16, 12], 100, 0.05), lt.BGKCollision(0.6), [])
+    out["couette_ncm"] = npy(couette.no_collision_mask)
+    out["couette_f0_nan"] = np.isnan(npy(couette.flow.f))     # characteristic velocity 0: the reference's state is NaN
+    save("more_flows", **out)
+
+
 def spectrum_case():
     """EnergySpectrum (observable_reporter.py:71-137) of evolved TGV states, incl. a non-cubic lattice."""
     out = {}
@@ -345,6 +362,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["ebb"]:
         ebb_cases()
         sys.exit(0)
+    if sys.argv[1:] == ["flows"]:
+        more_flows_case()
+        sys.exit(0)
     if sys.argv[1:] == ["spectrum"]:
         spectrum_case()
         sys.exit(0)
@@ -376,3 +396,4 @@ if __name__ == "__main__":
     native_known_answers()
     spectrum_case()
     ebb_cases()
+    more_flows_case()

@@ -333,3 +333,45 @@ def test_write_vtk_round_trip(tmp_path):
     assert lt.read_vtr(path2)["p"].shape == (5, 4, 1)
     with pytest.raises(ValueError):
         lt.write_vtk({"p": p, "ux": ux[:4]}, id=2, filename_base=str(tmp_path / "bad"))
+
+
+def test_remaining_flows_match_reference():
+    """Lamb-Oseen vortex, decaying turbulence (incl. the pressure-Poisson start in 2-D), Couette masks and the
+    flow_by_name registry against the reference's initial states (tests/golden/more_flows.npz)"""
+    g = load_golden("more_flows")
+    ctx = cpu()
+    assert max_rel(lt.LambOseenVortex2D(ctx, [48, 40], 100, 0.05).f.numpy(), g["lamb_f0"]) < 1e-14
+    decay = lt.DecayingTurbulence(ctx, [32, 32], 1000, 0.05, k0=4, randseed=3)
+    assert max_rel(decay.f.numpy(), g["decay2d_f0"]) < 1e-12
+    assert np.allclose(decay.energy_spectrum[0], g["decay2d_spectrum"], rtol=1e-12, atol=1e-300)
+    assert decay.units.relaxation_parameter_lu == pytest.approx(float(g["decay2d_tau"]), rel=1e-13)
+    assert max_rel(lt.DecayingTurbulence(ctx, [12, 12, 12], 1000, 0.05, k0=3, randseed=5).f.numpy(),
+                   g["decay3d_f0"]) < 1e-12
+    couette = lt.Simulation(lt.CouetteFlow2D(ctx, [16, 12], 100, 0.05), lt.BGKCollision(0.6), [])
+    assert np.array_equal(couette.no_collision_mask.numpy(), g["couette_ncm"])
+    assert np.array_equal(np.isnan(couette.flow.f.numpy()), g["couette_f0_nan"])
+    assert sorted(lt.flow_by_name) == ["couette2d", "decay2d", "lamboseen", "poiseuille2d", "shear2d", "taylor2d",
+                                       "taylor3d_d3q19", "taylor3d_d3q27"]
+    for name, (flow_class, stencil) in lt.flow_by_name.items():
+        assert issubclass(flow_class, lt.ExtFlow) and stencil().q in (9, 19, 27)
+
+
+def test_progress_reporter_logs_and_stays_batchable(tmp_path):
+    """ProgressReporter (lettuce/ext/_reporter/progress_reporter.py): header on the first call, one line per due
+    step; it reads no device data, so the step loop may still batch"""
+    class FakeFlow:
+        i = 0
+
+    class FakeSim:
+        flow = FakeFlow()
+
+    rep = lt.ProgressReporter(interval=5, i_target=20, outdir=tmp_path / "log", t_max=1e9)
+    sim = FakeSim()
+    for i in (0, 5, 7, 10):
+        sim.flow.i = i
+        rep(sim)
+    lines = open(tmp_path / "log" / "progress_reporter_log.txt").read().splitlines()
+    assert lines[0].startswith("t_start:") and "t_per_step" in lines[1]
+    assert len(lines) == 4 and lines[2].split()[1] == "5" and lines[3].split()[1] == "10"
+    assert "WARNING" not in lines[2]
+    assert rep.batchable
