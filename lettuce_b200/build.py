@@ -7,6 +7,10 @@ once and selected at run time from the descriptor.  The 40 (stencil, dtype, coll
 triples are separate translation units and compile in parallel.
 
     python -m lettuce_b200.build [--force] [--verbose]
+
+A/B experiments: `LBM_B200_NVCC_DEFINES="-DLBM_KBC_PACKED=1" LBM_B200_BUILD_SUFFIX=packed python -m
+lettuce_b200.build` writes `liblbm_b200_packed.so` (objects under build_packed/); select it at run time with
+`LBM_B200_LIB=<path>` (lettuce_b200/native.py).
 """
 from __future__ import annotations
 
@@ -19,12 +23,14 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 ROOT = os.path.dirname(PKG)
-OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "liblbm_b200.so")
+_SUFFIX = os.environ.get("LBM_B200_BUILD_SUFFIX", "")
+OBJ = os.path.join(PKG, "build" + ("_" + _SUFFIX if _SUFFIX else ""))
+LIB = os.path.join(PKG, "liblbm_b200" + ("_" + _SUFFIX if _SUFFIX else "") + ".so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),
+         *os.environ.get("LBM_B200_NVCC_DEFINES", "").split()]
 
 STENCILS = ("D2Q9", "D3Q19", "D3Q27")
 REALS = ("float", "double")
