@@ -274,7 +274,10 @@ def gpu_main(args):
             # N > 1: the public Python API on every rank's slab -- upload, Simulation(K) with a global
             # kinetic-energy reporter of interval 1 (reduce kernel + all-reduce + D2H per step), download
             from lettuce_b200 import slab
-            rep = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=1, out=None)
+            # defer=False: every step's energy is read back to the host inside the timed region (the contract's
+            # per-step device-to-host read), not collected on the device and fetched at the end
+            rep = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=1, out=None,
+                                        defer=False)
             sim.reporter.append(rep)
             flow.i = 1                      # skip the step-0 report so exactly K reports fall in the timed region
             barrier()

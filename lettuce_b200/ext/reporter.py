@@ -124,28 +124,66 @@ class Mass(Observable):
 
 class ObservableReporter(Reporter):
     """Evaluates `observable` every `interval` steps and prints or stores
-    `[step, time_pu, value...]` (observable_reporter.py:161-200)."""
+    `[step, time_pu, value...]` (observable_reporter.py:161-200).
+
+    The reference converts every value to NumPy at once, which on a GPU is a device synchronisation per report
+    (`convert_to_ndarray`, observable_reporter.py:189-190).  When the rows are collected in a list (`out=None`)
+    and the value lives on a CUDA device, the device tensor is kept instead and all pending values are brought to
+    the host in ONE transfer the next time `reporter.out` is read, so a reporter with a short interval no longer
+    stalls the launch queue.  `defer` forces that behaviour on (True) or off (False)."""
     batchable = True
 
-    def __init__(self, observable, interval=1, out=sys.stdout):
+    def __init__(self, observable, interval=1, out=sys.stdout, defer: Optional[bool] = None):
         super().__init__(interval)
         self.observable = observable
-        self.out = [] if out is None else out
+        self._rows = [] if out is None else out
+        self._pending = []                   # (row index, device tensor) of rows whose values are still on the device
+        self._defer = defer
         self._parameter_name = observable.__class__.__name__
         if out is not None:
             print("steps    ", "time    ", self._parameter_name)
 
+    @property
+    def out(self):
+        """the list of rows (all values on the host) or the stream that was passed in"""
+        self._fetch_pending()
+        return self._rows
+
+    @out.setter
+    def out(self, value):
+        self._fetch_pending()
+        self._rows = value
+
+    def _fetch_pending(self):
+        if not self._pending:
+            return
+        pending, self._pending = self._pending, []
+        flat = torch.cat([v.reshape(-1).to(torch.float64) for _, v in pending]).cpu().tolist()
+        pos = 0
+        for index, v in pending:
+            n = v.numel()
+            self._rows[index] = self._rows[index][:2] + flat[pos:pos + n]
+            pos += n
+
     def __call__(self, simulation):
         if simulation.flow.i % self.interval != 0:
             return
-        observed = self.observable.context.convert_to_ndarray(self.observable(simulation.flow.f))
+        value = self.observable(simulation.flow.f)
+        head = [simulation.flow.i, simulation.units.convert_time_to_pu(simulation.flow.i)]
+        defer = self._defer if self._defer is not None else (torch.is_tensor(value) and value.is_cuda)
+        if defer and isinstance(self._rows, list) and torch.is_tensor(value):
+            assert value.dim() < 2
+            self._rows.append(head)
+            self._pending.append((len(self._rows) - 1, value.detach().clone()))
+            return
+        observed = self.observable.context.convert_to_ndarray(value)
         assert len(observed.shape) < 2
         observed = [observed.item()] if len(observed.shape) == 0 else observed.tolist()
-        entry = [simulation.flow.i, simulation.units.convert_time_to_pu(simulation.flow.i)] + observed
-        if isinstance(self.out, list):
-            self.out.append(entry)
+        entry = head + observed
+        if isinstance(self._rows, list):
+            self._rows.append(entry)
         else:
-            print(*entry, file=self.out)
+            print(*entry, file=self._rows)
 
 
 class FailureReporterBase(Reporter):

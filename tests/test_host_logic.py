@@ -375,3 +375,52 @@ def test_progress_reporter_logs_and_stays_batchable(tmp_path):
     assert len(lines) == 4 and lines[2].split()[1] == "5" and lines[3].split()[1] == "10"
     assert "WARNING" not in lines[2]
     assert rep.batchable
+
+
+def test_observable_reporter_defers_device_values_until_read():
+    """values that live on the device are fetched in one transfer when `reporter.out` is read; rows, order and
+    number formats are those of the eager path (observable_reporter.py:161-200)"""
+    class FakeUnits:
+        @staticmethod
+        def convert_time_to_pu(i):
+            return 0.5 * i
+
+    class FakeFlow:
+        i = 0
+        f = None
+
+    class FakeSim:
+        flow = FakeFlow()
+        units = FakeUnits()
+
+    class Scalar:
+        context = cpu(torch.float32)
+
+        def __call__(self, f=None):
+            return torch.tensor(1.0 + FakeSim.flow.i, dtype=torch.float32)
+
+    class Vector(Scalar):
+        def __call__(self, f=None):
+            return torch.arange(3, dtype=torch.float64) * FakeSim.flow.i
+
+    for obs, rows_at_4 in ((Scalar(), [[0, 0.0, 1.0], [2, 1.0, 3.0], [4, 2.0, 5.0]]),
+                           (Vector(), [[0, 0.0, 0.0, 0.0, 0.0], [2, 1.0, 0.0, 2.0, 4.0], [4, 2.0, 0.0, 4.0, 8.0]])):
+        lazy = lt.ObservableReporter(obs, interval=2, out=None, defer=True)
+        eager = lt.ObservableReporter(obs, interval=2, out=None, defer=False)
+        sim = FakeSim()
+        for i in range(5):
+            sim.flow.i = i
+            lazy(sim); eager(sim)
+            if i == 2:
+                assert lazy.out == eager.out and len(lazy._pending) == 0       # reading mid-run fetches what is there
+        assert len(lazy._pending) == 1 and len(lazy._rows[-1]) == 2
+        assert lazy.out == eager.out == rows_at_4
+        assert all(isinstance(v, float) for row in lazy.out for v in row[1:])
+        lazy.out = []
+        assert lazy.out == []
+    import io
+    stream = io.StringIO()
+    printed = lt.ObservableReporter(Scalar(), interval=1, out=stream, defer=True)     # streams are always eager
+    FakeSim.flow.i = 3
+    printed(FakeSim())
+    assert stream.getvalue().split() == ["3", "1.5", "4.0"] and printed.out is stream
