@@ -19,7 +19,8 @@ import torch
 from . import native
 from ._stencil import TorchStencil
 
-__all__ = ["Equilibrium", "Boundary", "Flow", "QuadraticEquilibrium", "initialize_f_neq", "pressure_poisson"]
+__all__ = ["Equilibrium", "Boundary", "Flow", "QuadraticEquilibrium", "QuadraticEquilibriumLessMemory",
+           "initialize_f_neq", "pressure_poisson"]
 
 
 class Equilibrium(ABC):
@@ -74,6 +75,12 @@ class QuadraticEquilibrium(Equilibrium):
 
     def native_available(self) -> bool:
         return True
+
+
+class QuadraticEquilibriumLessMemory(QuadraticEquilibrium):
+    """The reference's lower-memory evaluation order of the same polynomial
+    (lettuce/ext/_equilibrium/quadratic_equilibrium_less_memory.py:8-32); here both names share one
+    implementation (the step kernels never materialise an equilibrium tensor)."""
 
 
 class Flow(ABC):

@@ -255,6 +255,11 @@ class Engine:
             _require_cuda(flow.f, "flow.f")
         self.device = flow.f.device
         self.lat = lattice_of(flow.stencil, flow.f.shape[1:], flow.f.dtype)
+        # the kernels evaluate the quadratic equilibrium (quadratic_equilibrium.py:11-24; the less-memory variant
+        # is the same polynomial); the reference's collisions would call any other flow.equilibrium
+        equilibrium = type(getattr(flow, "equilibrium", None)).__name__
+        if equilibrium not in ("QuadraticEquilibrium", "QuadraticEquilibriumLessMemory", "NoneType"):
+            raise NotImplementedError(f"equilibrium {equilibrium} has no B200 kernel (quadratic equilibrium only)")
         transformer = list(simulation.transformer)
         if len(transformer) > LBM_MAX_OPS:
             raise NotImplementedError(f"at most {LBM_MAX_OPS} transformer entries, got {len(transformer)}")

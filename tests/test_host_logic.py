@@ -424,3 +424,19 @@ def test_observable_reporter_defers_device_values_until_read():
     FakeSim.flow.i = 3
     printed(FakeSim())
     assert stream.getvalue().split() == ["3", "1.5", "4.0"] and printed.out is stream
+
+
+def test_engine_rejects_other_equilibria():
+    """the kernels evaluate the quadratic equilibrium; a flow built with another one must not run silently"""
+    class Other(lt.Equilibrium):
+        def __call__(self, flow, rho=None, u=None):
+            return lt.QuadraticEquilibrium()(flow, rho, u)
+
+    ctx = cpu()
+    flow = lt.TaylorGreenVortex(ctx, [8, 8], 10, 0.05, stencil=lt.D2Q9(), equilibrium=Other())
+    sim = lt.Simulation(flow, lt.BGKCollision(0.6), [])
+    with pytest.raises(NotImplementedError):
+        native.describe(sim)
+    same = lt.TaylorGreenVortex(ctx, [8, 8], 10, 0.05, stencil=lt.D2Q9(), equilibrium=lt.QuadraticEquilibriumLessMemory())
+    assert native.describe(lt.Simulation(same, lt.BGKCollision(0.6), []))["ops"][0]["kind"] == native.OP_BGK
+    assert torch.equal(same.f, lt.TaylorGreenVortex(ctx, [8, 8], 10, 0.05, stencil=lt.D2Q9()).f)
