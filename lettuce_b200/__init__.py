@@ -18,6 +18,7 @@ from .units import *
 from ._flow import *
 from ._simulation import *
 from .ext import *
+from .util import *
 from . import native
 
 __version__ = "0.1.0"

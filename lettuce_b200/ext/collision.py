@@ -7,7 +7,8 @@ from __future__ import annotations
 
 from .._simulation import Collision
 
-__all__ = ["NoCollision", "BGKCollision", "TRTCollision", "KBCCollision", "RegularizedCollision",
+__all__ = ["NoCollision", "BGKCollision", "TRTCollision", "KBCCollision", "KBCCollision2D", "KBCCollision3D",
+           "RegularizedCollision",
            "SmagorinskyCollision", "Force", "Guo", "ShanChen"]
 
 
@@ -94,3 +95,21 @@ class ShanChen(Force):
     @property
     def ueq_scaling_factor(self):
         return self.tau * 1
+
+
+class KBCCollision2D(KBCCollision):
+    """deprecated alias (lettuce/ext/_collision/kbc_collision.py:169-173)"""
+
+    def __init__(self, tau: float = None):
+        import warnings
+        warnings.warn("KBCCollision2D is is deprecated! Use KBCCollision instead!")
+        super().__init__()
+
+
+class KBCCollision3D(KBCCollision):
+    """deprecated alias (lettuce/ext/_collision/kbc_collision.py:176-180)"""
+
+    def __init__(self, tau: float = None):
+        import warnings
+        warnings.warn("KBCCollision2D is is deprecated! Use KBCCollision instead!")
+        super().__init__()

@@ -14,7 +14,7 @@ from .._stencil import D2Q9, D3Q19
 from ..units import UnitConversion
 from .boundary import AntiBounceBackOutlet, BounceBackBoundary, EquilibriumBoundaryPU
 
-__all__ = ["ExtFlow", "TaylorGreenVortex", "Obstacle", "PoiseuilleFlow2D", "Cavity2D", "DoublyPeriodicShear2D",
+__all__ = ["ExtFlow", "TaylorGreenVortex", "TaylorGreenVortex2D", "TaylorGreenVortex3D", "Obstacle", "PoiseuilleFlow2D", "Cavity2D", "DoublyPeriodicShear2D",
            "CouetteFlow2D", "LambOseenVortex2D", "DecayingTurbulence", "flow_by_name"]
 
 
@@ -94,6 +94,20 @@ class TaylorGreenVortex(ExtFlow):
     @property
     def post_boundaries(self):
         return []
+
+
+def TaylorGreenVortex3D(context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None):
+    """deprecated alias (lettuce/ext/_flows/taylorgreen.py:101-110)"""
+    warnings.warn("TaylorGreenVortex3D is deprecated. Use TaylorGreenVortex instead", DeprecationWarning)
+    return TaylorGreenVortex(context=context, resolution=resolution, reynolds_number=reynolds_number,
+                             mach_number=mach_number, stencil=stencil, equilibrium=equilibrium)
+
+
+def TaylorGreenVortex2D(context, resolution, reynolds_number, mach_number, stencil=None, equilibrium=None):
+    """deprecated alias (lettuce/ext/_flows/taylorgreen.py:113-122)"""
+    warnings.warn("TaylorGreenVortex2D is deprecated. Use TaylorGreenVortex instead", DeprecationWarning)
+    return TaylorGreenVortex(context=context, resolution=resolution, reynolds_number=reynolds_number,
+                             mach_number=mach_number, stencil=stencil, equilibrium=equilibrium)
 
 
 class Obstacle(ExtFlow):

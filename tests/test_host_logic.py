@@ -440,3 +440,36 @@ def test_engine_rejects_other_equilibria():
     same = lt.TaylorGreenVortex(ctx, [8, 8], 10, 0.05, stencil=lt.D2Q9(), equilibrium=lt.QuadraticEquilibriumLessMemory())
     assert native.describe(lt.Simulation(same, lt.BGKCollision(0.6), []))["ops"][0]["kind"] == native.OP_BGK
     assert torch.equal(same.f, lt.TaylorGreenVortex(ctx, [8, 8], 10, 0.05, stencil=lt.D2Q9()).f)
+
+
+def test_util_helpers_and_deprecated_aliases():
+    """torch_gradient (orders 2/4/6) and torch_jacobi on analytic periodic fields, append_axes, the exception /
+    warning classes and the deprecated aliases user scripts still import (lettuce/util/utility.py)"""
+    n = 64
+    x = torch.linspace(0, 2 * np.pi * (1 - 1 / n), n, dtype=torch.float64)
+    X, Y = torch.meshgrid(x, x, indexing="ij")
+    field = torch.sin(X) * torch.cos(2 * Y)
+    dx = 2 * np.pi / n
+    errors = []
+    for order in (2, 4, 6):
+        g = lt.torch_gradient(field, dx=dx, order=order)
+        assert g.shape == (2, n, n)
+        errors.append(max(float((g[0] - torch.cos(X) * torch.cos(2 * Y)).abs().max()),
+                          float((g[1] + 2 * torch.sin(X) * torch.sin(2 * Y)).abs().max())))
+    assert errors[0] > 10 * errors[1] > 100 * errors[2] and errors[2] < 1e-6
+    # the order-6 weights are the ones the enstrophy kernel and initialize_f_neq use (oracle.gradient6)
+    assert np.allclose(lt.torch_gradient(field, dx=dx, order=6).numpy(), lo.gradient6(field.numpy(), dx), atol=1e-13)
+    with pytest.raises(lt.LettuceException):
+        lt.torch_gradient(torch.zeros(4), 1)
+    rhs = -5 * field                                        # lap(field) = -(1 + 4) field
+    p = lt.torch_jacobi(rhs, torch.zeros_like(field), dx, dim=2, tol_abs=1e-12, max_num_steps=20000)
+    assert float((p - p.mean() - field).abs().max()) < 5e-3          # 2nd-order discrete Laplacian
+    assert lt.append_axes(np.ones(3), 2).shape == (3, 1, 1)
+    assert issubclass(lt.InefficientCodeWarning, lt.LettuceWarning) and issubclass(lt.LettuceWarning, UserWarning)
+    ctx = cpu()
+    with pytest.warns(DeprecationWarning):
+        flow = lt.TaylorGreenVortex3D(ctx, [8, 8, 8], 100, 0.05, stencil=lt.D3Q19())
+    assert type(flow) is lt.TaylorGreenVortex
+    with pytest.warns(UserWarning):
+        kbc = lt.KBCCollision2D()
+    assert native.op_kind(kbc) == native.OP_KBC
