@@ -1,7 +1,7 @@
 """Measure every BASELINE.json configuration on ONE B200 (not the driver's bench contract; numbers
 for DESIGN.md / profiles).  Prints one JSON line per case.
 
-    python scripts/bench_configs.py [c1 c2 c3 c4 c5 ...] [--small]
+    python scripts/bench_configs.py [c1 c2 c3 c4 c5 ebb extra ...] [--small]
 """
 import gc
 import json
@@ -129,6 +129,31 @@ def main():
                        general_nodes=int(eng.desc.n_general),
                        max_mem_gb=torch.cuda.max_memory_allocated() / 1e9)
                 del flow, sim, eng
+        elif case == "ebb":
+            # cylinder with link-wise bounce-back after streaming (EbbSimulation): step loop in Python vs the
+            # batched library call (LBM_B200_EBB_BATCH=1)
+            res, diameter = ([1024, 256], 32.0) if small else ([4096, 1024], 128.0)
+            for bc in ("fwbb", "hwbb", "ibb1"):
+                for batch in ("0", "1"):
+                    os.environ["LBM_B200_EBB_BATCH"] = batch
+                    ctx = lt.Context("cuda", dtype=f32)
+                    flow = lt.ObstacleCylinder(ctx, res, 100.0, 0.05, char_length_pu=1.0, char_length_lu=diameter,
+                                               bc_type=bc, u_init=1, calc_force_coefficients=True, stencil=lt.D2Q9())
+                    sim = lt.EbbSimulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+                    sim(20)
+                    torch.cuda.synchronize()
+                    l0 = native.launch_count()
+                    t0 = time.perf_counter()
+                    sim(200)
+                    dt = (time.perf_counter() - t0) / 200
+                    n = res[0] * res[1]
+                    print(json.dumps(dict(case=f"EBB cylinder D2Q9 BGK {res[0]}x{res[1]} {bc}", batch=batch,
+                                          links=sim.post_streaming_boundaries[-1].n_links, ms_per_step=dt * 1e3,
+                                          mlups=n / 1e6 / dt, launches_per_step=(native.launch_count() - l0) / 200,
+                                          force=sim.post_streaming_boundaries[-1].force_sum.tolist(),
+                                          finite=bool(torch.isfinite(flow.f).all()))), flush=True)
+                    del flow, sim
+            os.environ.pop("LBM_B200_EBB_BATCH", None)
         elif case == "extra":
             for st, coll, dt_ in ((lt.D3Q27, "bgk", f32), (lt.D3Q27, "trt", f32), (lt.D3Q19, "bgk", f64),
                                   (lt.D3Q19, "trt", f32), (lt.D3Q27, "kbc", f64)):
