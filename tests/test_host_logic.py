@@ -473,3 +473,22 @@ def test_util_helpers_and_deprecated_aliases():
     with pytest.warns(UserWarning):
         kbc = lt.KBCCollision2D()
     assert native.op_kind(kbc) == native.OP_KBC
+
+
+def test_header_is_plain_c_and_matches_ctypes_sizes(tmp_path):
+    """include/lbm_b200.h compiles as strict C99 (the drop-in boundary has no C++ or torch types), and a C
+    program's sizeof of every struct equals the ctypes mirror in native.py"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "lbm_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(lbm_op), sizeof(lbm_lattice), '
+                   'sizeof(lbm_halo), sizeof(lbm_step_desc), sizeof(lbm_slab), sizeof(lbm_links)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True, capture_output=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    mirrors = [native.LbmOp, native.LbmLattice, native.LbmHalo, native.LbmStepDesc, native.LbmSlab, native.LbmLinks]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
