@@ -191,6 +191,45 @@ class Flow(ABC):
         u = self.u(f)
         return 0.5 * (u * u).sum(dim=0)
 
+    # diagnostics (lettuce/_flow.py:206-256): plain torch reductions over q, not on the step path -------------
+    def entropy(self, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """entropy according to the H-theorem, as the reference evaluates it (_flow.py:206-211)"""
+        f = self.f if f is None else f
+        w = self.torch_stencil.w.reshape([-1] + [1] * self.stencil.d)
+        return (f * -torch.log((f / w).sum(dim=0))).sum(dim=0)
+
+    def pseudo_entropy_global(self, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Taylor expansion of the entropy around the weights (_flow.py:213-218; like the reference the density
+        term is that of `flow.f`)"""
+        f = self.f if f is None else f
+        w = self.torch_stencil.w.reshape([-1] + [1] * self.stencil.d)
+        return self.rho() - (f * f / w).sum(dim=0)
+
+    def pseudo_entropy_local(self, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Taylor expansion of the entropy around the local equilibrium (_flow.py:220-226)"""
+        f = self.f if f is None else f
+        return self.rho(f) - (f * (f / self.equilibrium(self))).sum(dim=0)
+
+    def shear_tensor(self, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pi_ab = sum_q f_q e_qa e_qb, shape [d, d, *resolution] (_flow.py:228-234)"""
+        e = self.torch_stencil.e
+        return torch.einsum("q...,qab->ab...", self.f if f is None else f, torch.einsum("qa,qb->qab", e, e))
+
+    def einsum(self, equation, fields, *args) -> torch.Tensor:
+        """deprecated: Einstein summation that appends the spatial axes (_flow.py:236-256)"""
+        warnings.warn("The `einsum` method is deprecated and will be removed in a future version. "
+                      "Please use `torch.einsum` directly instead.", DeprecationWarning, stacklevel=2)
+        inputs, output = equation.split("->")
+        inputs = inputs.split(",")
+        for i, inp in enumerate(inputs):
+            if len(inp) == len(fields[i].shape) - self.stencil.d:
+                inputs[i] += "..."
+                if not output.endswith("..."):
+                    output += "..."
+            else:
+                assert len(inp) == len(fields[i].shape), "Bad dimension."
+        return torch.einsum(",".join(inputs) + "->" + output, fields, *args)
+
     # checkpoint (lettuce/_flow.py:258-268) -----------------------------------
     def dump(self, filename):
         with open(filename, "wb") as fh:

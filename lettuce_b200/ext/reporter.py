@@ -16,7 +16,7 @@ from .. import native
 from .._simulation import Reporter
 
 __all__ = ["Observable", "ObservableReporter", "MaximumVelocity", "IncompressibleKineticEnergy",
-           "Enstrophy", "EnergySpectrum", "Mass", "ProgressReporter", "FailureReporterBase", "NaNReporter", "HighMaReporter", "ErrorReporter"]
+           "Enstrophy", "EnergySpectrum", "Mass", "ProgressReporter", "write_image", "FailureReporterBase", "NaNReporter", "HighMaReporter", "ErrorReporter"]
 
 
 class Observable(ABC):
@@ -359,3 +359,15 @@ class ProgressReporter(Reporter):
         if self.checkpoint and self.t_elapsed > self.t_max and self.outdir is not None:
             import os
             simulation.flow.dump(os.path.join(self.outdir, f"{now.strftime('%y%m%d_%H%M%S')}_f_{i}.cpt"))
+
+
+def write_image(filename, array2d):
+    """2-D field as an image without axes (lettuce/ext/_reporter/write_image.py:4-13); needs matplotlib"""
+    from matplotlib import pyplot as plt
+    fig, ax = plt.subplots()
+    plt.tight_layout()
+    ax.imshow(array2d)
+    ax.get_xaxis().set_visible(False)
+    ax.get_yaxis().set_visible(False)
+    plt.savefig(filename)
+    plt.close(fig)

@@ -492,3 +492,18 @@ def test_header_is_plain_c_and_matches_ctypes_sizes(tmp_path):
     sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     mirrors = [native.LbmOp, native.LbmLattice, native.LbmHalo, native.LbmStepDesc, native.LbmSlab, native.LbmLinks]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_flow_diagnostics():
+    """shear tensor, H-theorem entropy and the deprecated einsum helper (lettuce/_flow.py:206-256); the
+    reference's own `entropy` expression raises a shape error in its current API, ours evaluates the formula"""
+    flow = lt.TaylorGreenVortex(cpu(), [10, 12], 100, 0.05, stencil=lt.D2Q9())
+    f = flow.f.numpy()
+    st = lo.stencil("D2Q9")
+    e = st["e"].astype(float)
+    want = np.einsum("qxy,qa,qb->abxy", f, e, e)
+    assert np.allclose(flow.shear_tensor().numpy(), want, atol=1e-15)
+    w = st["w"].reshape(-1, 1, 1)
+    assert np.allclose(flow.entropy().numpy(), (f * -np.log((f / w).sum(axis=0))).sum(axis=0), atol=1e-14)
+    with pytest.warns(DeprecationWarning):
+        assert torch.allclose(flow.einsum("q,q->", [flow.f, flow.f]), (flow.f * flow.f).sum(dim=0))
