@@ -4,3 +4,4 @@ from .flows import *
 from .reporter import *
 from .vtk import *
 from .bounce_back import *
+from .hdf5 import *

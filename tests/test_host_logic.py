@@ -507,3 +507,67 @@ def test_flow_diagnostics():
     assert np.allclose(flow.entropy().numpy(), (f * -np.log((f / w).sum(axis=0))).sum(axis=0), atol=1e-14)
     with pytest.warns(DeprecationWarning):
         assert torch.allclose(flow.einsum("q,q->", [flow.f, flow.f]), (flow.f * flow.f).sum(dim=0))
+
+
+def test_hdf5_reporter_with_a_stand_in_h5py(tmp_path, monkeypatch):
+    """HDF5Reporter (lettuce/util/datautils.py:17-80): file layout and append logic, exercised with an in-memory
+    stand-in for h5py (the real module is not installed here)"""
+    import sys
+    import types
+    store = {}
+
+    class Dataset:
+        def __init__(self, shape, dtype):
+            self.data = np.zeros(shape, dtype=dtype)
+
+        shape = property(lambda self: self.data.shape)
+
+        def resize(self, n, axis=0):
+            new = np.zeros((n, *self.data.shape[1:]), dtype=self.data.dtype)
+            new[:self.data.shape[0]] = self.data
+            self.data = new
+
+        def __setitem__(self, key, value):
+            self.data[key] = value
+
+    class File:
+        def __init__(self, name, mode):
+            if mode == "w":
+                store[name] = dict(attrs={}, sets={})
+            self.attrs, self.sets = store[name]["attrs"], store[name]["sets"]
+
+        def create_dataset(self, name, shape, maxshape, dtype):
+            self.sets[name] = Dataset(shape, dtype)
+
+        def __getitem__(self, name):
+            return self.sets[name]
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    fake = types.ModuleType("h5py")
+    fake.File = File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    flow = lt.TaylorGreenVortex(cpu(torch.float32), [6, 8], 100, 0.05, stencil=lt.D2Q9())
+    collision = lt.BGKCollision(0.7)
+    rep = lt.HDF5Reporter(flow, collision, interval=2, filebase=str(tmp_path / "out"), metadata={"note": "x"})
+
+    class Sim:
+        pass
+
+    sim = Sim()
+    sim.flow = flow
+    first = flow.f.clone()
+    for i in range(5):
+        flow.i = i
+        flow.f = first * (1 + i)
+        rep(sim)
+    rec = store[str(tmp_path / "out") + ".h5"]
+    assert rec["sets"]["f"].shape == (3, 9, 6, 8) and rec["sets"]["f"].data.dtype == np.float32
+    assert np.array_equal(rec["sets"]["f"].data[2], (first * 5).numpy())
+    assert rec["attrs"]["data"] == "3" and rec["attrs"]["steps"] == "4" and rec["attrs"]["note"] == "x"
+    import pickle
+    assert pickle.loads(bytes(rec["attrs"]["_collision"]))["cls"] == "BGKCollision"
