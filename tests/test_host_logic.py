@@ -483,15 +483,22 @@ def test_header_is_plain_c_and_matches_ctypes_sizes(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "lbm_b200.h"\n'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lbm_b200.h"\n'
                    'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(lbm_op), sizeof(lbm_lattice), '
-                   'sizeof(lbm_halo), sizeof(lbm_step_desc), sizeof(lbm_slab), sizeof(lbm_links)); return 0; }\n')
+                   'sizeof(lbm_halo), sizeof(lbm_step_desc), sizeof(lbm_slab), sizeof(lbm_links));\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", offsetof(lbm_op, rho_stride), offsetof(lbm_op, force), '
+                   'offsetof(lbm_step_desc, ops), offsetof(lbm_step_desc, labels), offsetof(lbm_step_desc, n_general), '
+                   'offsetof(lbm_step_desc, halo), offsetof(lbm_links, force)); return 0; }\n')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
                     str(src), "-o", str(exe)], check=True, capture_output=True)
-    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    lines = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    sizes, offsets = ([int(v) for v in line.split()] for line in lines)
     mirrors = [native.LbmOp, native.LbmLattice, native.LbmHalo, native.LbmStepDesc, native.LbmSlab, native.LbmLinks]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
+    assert offsets == [native.LbmOp.rho_stride.offset, native.LbmOp.force.offset, native.LbmStepDesc.ops.offset,
+                       native.LbmStepDesc.labels.offset, native.LbmStepDesc.n_general.offset,
+                       native.LbmStepDesc.halo.offset, native.LbmLinks.force.offset]
 
 
 def test_flow_diagnostics():
