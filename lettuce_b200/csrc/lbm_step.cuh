@@ -362,6 +362,47 @@ LBM_D R node_update(const StepParams<R> &p, int x, int y, int z) {
     }
 }
 
+#if defined(LBM_SPECULATIVE_MASKED_LOADS)
+// EXPERIMENT (not the default build; -DLBM_SPECULATIVE_MASKED_LOADS=1): node_update for masked runs with the label
+// byte loaded TOGETHER with the populations instead of in front of them.  The default masked kernel does
+// LDG(label) -> EXIT? -> LDG x q, i.e. two dependent memory round trips per node; here all q+1 loads are in flight
+// at once and the exit follows them (ptxas keeps that order: checked with cuobjdump).  The loads of the few nodes
+// that belong to the general-nodes kernel are wasted.
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+LBM_D void node_update_speculative(const StepParams<R> &p, int x, int y, int z) {
+    constexpr int Q = S::Q;
+    const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
+    const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
+    const int xoff = x * (p.n1 * p.n2);
+    const int rowm = xoff + ym * p.n2, row0 = xoff + y * p.n2, rowp = xoff + yp * p.n2;
+    const int k = (x == 0 ? 1 : 0) | (x == p.n0 - 1 ? 2 : 0);
+    const uint8_t lab = __ldg(p.labels + (row0 + z));
+    R f[Q];
+    ForQ<Q>::run([&]<int q>() {
+        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+        const int rs = (!PULL || e1 == 0) ? row0 : (e1 == 1 ? rowm : rowp);
+        const int zs = (!PULL || e2 == 0) ? z : (e2 == 1 ? zm : zp);
+        f[q] = __ldg(p.tbl.ld[k][q] + (rs + zs));
+    });
+    // ptxas sinks loads below an exit on whose path they are unused, which would restore the two round trips.  The
+    // exit therefore also tests a condition on the loaded bits that never holds for real populations (all nine /
+    // nineteen / twenty-seven values having every bit set, a NaN pattern): the loads must land first.
+    unsigned long long bits = ~0ull;
+    ForQ<Q>::run([&]<int q>() {
+        if constexpr (sizeof(R) == 4) bits &= (unsigned long long)__float_as_uint(f[q]) | 0xffffffff00000000ull;
+        else bits &= (unsigned long long)__double_as_longlong(f[q]);
+    });
+    if (lab != p.collision_index || bits == ~0ull) return;
+    collide_node<S, R, COLL>(p, f);
+    ForQ<Q>::run([&]<int q>() {
+        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+        const int rd = (!PUSH || e1 == 0) ? row0 : (e1 == 1 ? rowp : rowm);
+        const int zd = (!PUSH || e2 == 0) ? z : (e2 == 1 ? zp : zm);
+        p.tbl.st[k][q][rd + zd] = f[q];
+    });
+}
+#endif
+
 template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
 __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
     step_scalar_kernel(const __grid_constant__ StepParams<R> p) {
@@ -372,6 +413,10 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
     if (MASKED) {
         // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
         // bit 7 and are left to general_nodes_kernel; every output slot still has exactly one writer.
+#if defined(LBM_SPECULATIVE_MASKED_LOADS)
+        node_update_speculative<S, R, COLL, PULL, PUSH>(p, x, y, z);
+        return;
+#endif
         if (p.labels[(int64_t)x * p.n1 * p.n2 + (int64_t)y * p.n2 + z] != p.collision_index) return;
     }
     node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
