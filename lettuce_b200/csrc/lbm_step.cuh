@@ -269,6 +269,11 @@ __device__ void general_node(const StepParams<R> &p, int x, int y, int z, int la
     constexpr int Q = S::Q;
     R f[Q];
     node_pipeline<S, R, COLL, PULL>(p, x, y, z, label, f);
+#if defined(LBM_GENERAL_AFTER_BULK)
+    // EXPERIMENT: this kernel was launched BEHIND the bulk kernel, which updated every node as if it were plain
+    // fluid; wait for it to finish before overwriting the slots that belong to the general nodes
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 
     // scatter with the destination-side frozen-slot rule (_simulation.py:252-255):
     // slot (q, dst) takes the streamed value unless it is frozen, in which case the
@@ -413,6 +418,17 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
     if (MASKED) {
         // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
         // bit 7 and are left to general_nodes_kernel; every output slot still has exactly one writer.
+#if defined(LBM_GENERAL_AFTER_BULK)
+        // EXPERIMENT (not the default build; -DLBM_GENERAL_AFTER_BULK=1): no label test at all.  The bulk kernel
+        // treats every node as plain fluid -- it is then the unmasked kernel, no label traffic, no dependent load --
+        // and general_nodes_kernel, launched behind it with programmatic dependent launch, gathers and collides
+        // concurrently and overwrites the slots of the general nodes once this grid has finished.  Every slot the
+        // bulk kernel writes wrongly (from or into a general node) has a general node as its rightful writer:
+        // nodes that stream into a frozen slot carry the general bit, frozen slots are rewritten by their owner.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+        return;
+#endif
 #if defined(LBM_SPECULATIVE_MASKED_LOADS)
         node_update_speculative<S, R, COLL, PULL, PUSH>(p, x, y, z);
         return;
@@ -493,8 +509,10 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
 // ---------------------------------------------------------------------------
 template <class S, class R, int COLL, bool PULL, bool PUSH>
 __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constant__ StepParams<R> p) {
+#if !defined(LBM_GENERAL_AFTER_BULK)
     // let the bulk kernel (launched with programmatic stream serialization) start right away
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_general) return;
     const int n = p.general_nodes[i];

@@ -45,6 +45,29 @@ int launch_scalar(const StepParams<R> &p, int variant, cudaStream_t stream) {
         }
     }
     if (p.sync.on) return LBM_ERR_UNSUPPORTED;
+#if defined(LBM_GENERAL_AFTER_BULK)
+    if (MASKED && p.n_general > 0) {
+        // EXPERIMENT: bulk kernel over every node first, the sparse kernel behind it (see step_scalar_kernel)
+        bulk<<<grid, block, 0, stream>>>(p);
+        ++g_launch_count;
+        int e = (int)cudaGetLastError();
+        if (e) return e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((p.n_general + 127) / 128);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        void (*sparse)(const StepParams<R>) = general_nodes_kernel<S, R, COLL, PULL, PUSH>;
+        e = (int)cudaLaunchKernelEx(&cfg, sparse, p);
+        ++g_launch_count;
+        return e;
+    }
+#endif
     if (MASKED && p.n_general > 0) {
         // The sparse kernel is a chain of dependent loads on a handful of CTAs (~10 us at 15 k nodes); it
         // and the bulk kernel write disjoint slots, so the bulk kernel is launched with programmatic

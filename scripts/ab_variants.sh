@@ -6,9 +6,11 @@
 #
 # Variants:  packed = -DLBM_KBC_PACKED=1 (KBC on FFMA2/FADD2/FMUL2)
 #            spec   = -DLBM_SPECULATIVE_MASKED_LOADS=1 (label loaded together with the populations)
+#            gab    = -DLBM_GENERAL_AFTER_BULK=1 (bulk kernel ignores the labels, general nodes overwrite afterwards)
 set -euo pipefail
 cd "$(dirname "$0")/.."
-declare -A DEFINES=([packed]="-DLBM_KBC_PACKED=1" [spec]="-DLBM_SPECULATIVE_MASKED_LOADS=1")
+declare -A DEFINES=([packed]="-DLBM_KBC_PACKED=1" [spec]="-DLBM_SPECULATIVE_MASKED_LOADS=1"
+                    [gab]="-DLBM_GENERAL_AFTER_BULK=1")
 
 case "${1:-}" in
 build)
