@@ -297,6 +297,35 @@ def more_flows_case():
     save("more_flows", **out)
 
 
+def ebb_random_links_case():
+    """Link lists of the example project's FullwayBounceBackBoundary for random solid masks that touch the domain
+    border, with every periodicity combination: pins the wrap-at-minus-one / skip-at-n border behaviour of the
+    reference's loops.  (HalfwayBounceBackBoundary's own legacy search cannot run in the reference: it reads
+    `flow.context.d`, which does not exist, halfway_bounce_back_boundary.py:77,113.)"""
+    import contextlib
+    import io
+    import itertools
+    base = "/root/reference/examples/advanced_projects/efficient_bounce_back_obstacle"
+    for sub in ("boundary", "simulation", "flow"):
+        sys.path.insert(0, os.path.join(base, sub))
+    from examples.advanced_projects.efficient_bounce_back_obstacle import FullwayBounceBackBoundary
+    rng = np.random.default_rng(11)
+    out = {}
+    ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+    for tag, stencil, res in (("2d", "D2Q9", [9, 7]), ("3d", "D3Q19", [6, 5, 4]), ("3d27", "D3Q27", [5, 4, 4])):
+        flow = lt.TaylorGreenVortex(ctx, list(res), 10, 0.05, stencil=STENCILS[stencil]())
+        mask = rng.random(res) < 0.3
+        other = (rng.random(res) < 0.15) & ~mask
+        out[f"mask_{tag}"], out[f"other_{tag}"] = mask, other
+        for k, per in enumerate(itertools.product([False, True], repeat=len(res))):
+            per_arg = tuple(per) if len(res) == 3 else (per[0], per[1], None)
+            with contextlib.redirect_stdout(io.StringIO()):
+                fw = FullwayBounceBackBoundary(ctx, flow, mask, global_solid_mask=mask | other, periodicity=per_arg)
+            out[f"fw_{tag}_{k}"] = npy(fw.f_index_fwbb)
+            out[f"per_{tag}_{k}"] = np.array(per)
+    save("ebb_random_links", **out)
+
+
 def spectrum_case():
     """EnergySpectrum (observable_reporter.py:71-137) of evolved TGV states, incl. a non-cubic lattice."""
     out = {}
@@ -362,6 +391,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["ebb"]:
         ebb_cases()
         sys.exit(0)
+    if sys.argv[1:] == ["links"]:
+        ebb_random_links_case()
+        sys.exit(0)
     if sys.argv[1:] == ["flows"]:
         more_flows_case()
         sys.exit(0)
@@ -397,3 +429,4 @@ if __name__ == "__main__":
     spectrum_case()
     ebb_cases()
     more_flows_case()
+    ebb_random_links_case()

@@ -110,3 +110,31 @@ def test_package_host_side_matches_reference(name):
     assert [o["kind"] for o in lt.native.describe(sim)["ops"]] == [1, 17, 18]     # BGK, inlet, outlet
     with pytest.raises(AttributeError):
         lt.FullwayBounceBackBoundary(flow.context, flow, flow.wall_mask).force_sum
+
+
+def test_link_search_border_rules_match_reference_on_random_masks():
+    """random solid masks touching the border, every periodicity combination, a second solid body next to the
+    first: the oracle's and the package's vectorised link search against the reference's loops
+    (fullway_bounce_back_boundary.py:50-123; index -1 wraps, index n is skipped on non-periodic axes)"""
+    import torch
+    import lettuce_b200 as lt
+    g = load_golden("ebb_random_links")
+    for tag, stencil, cls in (("2d", "D2Q9", lt.D2Q9), ("3d", "D3Q19", lt.D3Q19), ("3d27", "D3Q27", lt.D3Q27)):
+        st = lo.stencil(stencil)
+        mask, other = g[f"mask_{tag}"], g[f"other_{tag}"]
+        flow = lt.TaylorGreenVortex(lt.Context("cpu", dtype=torch.float64), list(mask.shape), 10, 0.05, stencil=cls())
+        k = 0
+        while f"fw_{tag}_{k}" in g:
+            per = tuple(bool(p) for p in g[f"per_{tag}_{k}"])
+            want = g[f"fw_{tag}_{k}"]
+            assert len(want) > 0
+            ours = lo.fullway_links(st, mask, per, mask | other)
+            assert np.array_equal(index_rows(ours), want), (tag, per)
+            boundary = lt.FullwayBounceBackBoundary(flow.context, flow, mask, global_solid_mask=mask | other,
+                                                    periodicity=per)
+            assert np.array_equal(boundary.f_index_fwbb.numpy(), want), (tag, per)
+            # the half-way search stores the same links on the fluid side
+            hw = lo.halfway_links(st, mask, per, mask | other)
+            assert len(hw["q"]) == len(want) and np.array_equal(hw["q"], want[:, 0])
+            k += 1
+        assert k == 2 ** mask.ndim
