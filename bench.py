@@ -269,7 +269,8 @@ def gpu_main(args):
                                                        args.steps, energy.data_ptr()))
                 dt = min(dt, time.perf_counter() - t0)
             assert torch.isfinite(energy).all() and float(energy[-1]) > 0
-            how = "lbm_run_host (C ABI): pinned host f uploaded, K steps, kinetic energy read back every step, final f downloaded"
+            how = ("lbm_run_host (C ABI): pinned host f uploaded, K steps (fused step + energy kernel), kinetic energy read "
+                   "back every step, final f downloaded; wall clock of the faster of two calls")
         else:
             # N > 1: the public Python API on every rank's slab -- upload, Simulation(K) with a global
             # kinetic-energy reporter of interval 1 (reduce kernel + all-reduce + D2H per step), download
