@@ -116,6 +116,13 @@ class Simulation:
         for reporter in self.reporter:
             reporter(self)
 
+    def _flush_reporters(self):
+        """reporters that keep device values until they are read (ObservableReporter) complete their rows"""
+        for reporter in self.reporter:
+            flush = getattr(reporter, "flush", None)
+            if callable(flush):
+                flush()
+
     def _batch_length(self, remaining: int) -> int:
         """Number of steps that can run before any reporter has to see the state."""
         if self._collide_and_stream is not native.invoke:
@@ -162,6 +169,7 @@ class Simulation:
             self.flow.i += k
             self._report()
             remaining -= k
+        self._flush_reporters()
         self.context.synchronize()
         end = timer()
         nodes = 1
@@ -186,6 +194,7 @@ class BreakableSimulation(Simulation):
             self._collide_and_stream(self)
             self.flow.i += 1
             self._report()
+        self._flush_reporters()
         self.context.synchronize()
         end = timer()
         nodes = 1

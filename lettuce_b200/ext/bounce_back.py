@@ -298,6 +298,7 @@ class EbbSimulation(Simulation):
             self.flow.i += k
             self._report()
             remaining -= k
+        self._flush_reporters()
         self.context.synchronize()
         end = timer()
         return num_steps * int(np.prod(self.flow.resolution)) / 1e6 / (end - beg)

@@ -129,8 +129,8 @@ class ObservableReporter(Reporter):
     The reference converts every value to NumPy at once, which on a GPU is a device synchronisation per report
     (`convert_to_ndarray`, observable_reporter.py:189-190).  When the rows are collected in a list (`out=None`)
     and the value lives on a CUDA device, the device tensor is kept instead and all pending values are brought to
-    the host in ONE transfer the next time `reporter.out` is read, so a reporter with a short interval no longer
-    stalls the launch queue.  `defer` forces that behaviour on (True) or off (False)."""
+    the host in ONE transfer when `reporter.out` is read or the running `Simulation.__call__` returns, so a reporter
+    with a short interval no longer stalls the launch queue.  `defer` forces that behaviour on (True) or off (False)."""
     batchable = True
 
     def __init__(self, observable, interval=1, out=sys.stdout, defer: Optional[bool] = None):
@@ -146,15 +146,18 @@ class ObservableReporter(Reporter):
     @property
     def out(self):
         """the list of rows (all values on the host) or the stream that was passed in"""
-        self._fetch_pending()
+        self.flush()
         return self._rows
 
     @out.setter
     def out(self, value):
-        self._fetch_pending()
+        self.flush()
         self._rows = value
 
-    def _fetch_pending(self):
+    def flush(self):
+        """bring the values that are still on the device to the host and complete their rows (in place).  Called
+        when `out` is read and by `Simulation.__call__` before it returns, so a list obtained from `reporter.out`
+        earlier is complete after every run."""
         if not self._pending:
             return
         pending, self._pending = self._pending, []

@@ -414,6 +414,11 @@ def test_observable_reporter_defers_device_values_until_read():
             if i == 2:
                 assert lazy.out == eager.out and len(lazy._pending) == 0       # reading mid-run fetches what is there
         assert len(lazy._pending) == 1 and len(lazy._rows[-1]) == 2
+        held = lazy._rows                                     # a list a user obtained from `.out` earlier ...
+        sim_like = lt.Simulation.__new__(lt.Simulation)
+        sim_like.reporter = [lazy, eager]
+        sim_like._flush_reporters()                           # ... is complete once Simulation.__call__ returns
+        assert held == rows_at_4 and not lazy._pending
         assert lazy.out == eager.out == rows_at_4
         assert all(isinstance(v, float) for row in lazy.out for v in row[1:])
         lazy.out = []
