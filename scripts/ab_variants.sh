@@ -2,6 +2,9 @@
 # A/B of the compile-time kernel experiments against the default library.
 #
 #   scripts/ab_variants.sh build        # here (CPU, ~5 min per variant): liblbm_b200_<name>.so next to the default
+#                                       # (all three variants were built once in round 1 to check that they compile
+#                                       # and export the full ABI; the libraries were parked in lettuce_b200/build_<name>/,
+#                                       # which does not travel to the GPU box -- rebuilding relinks the cached objects)
 #   scripts/ab_variants.sh run          # on the GPU box: parity tests + config timings with every library
 #
 # Variants:  packed = -DLBM_KBC_PACKED=1 (KBC on FFMA2/FADD2/FMUL2)
