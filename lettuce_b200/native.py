@@ -424,7 +424,11 @@ class Engine:
     def energy_fusable(self) -> bool:
         """True when `step_with_energy` exists for this simulation: single-GPU engine, no boundaries, no
         stream after the collide phase (NO_STREAMING / PRE_STREAMING)."""
-        return type(self) is Engine and int(self.lib.lbm_step_energy_scratch_bytes(C.byref(self.desc))) > 0
+        cached = getattr(self, "_energy_fusable", None)      # depends on the lattice, the streaming mode and masks only
+        if cached is None:
+            cached = type(self) is Engine and int(self.lib.lbm_step_energy_scratch_bytes(C.byref(self.desc))) > 0
+            self._energy_fusable = cached
+        return cached
 
     def step_with_energy(self) -> torch.Tensor:
         """One time step that also returns sum 0.5|u|^2 (lattice units, 0-d float64 CUDA tensor) of the new
