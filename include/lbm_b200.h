@@ -138,7 +138,8 @@ typedef struct lbm_step_desc {
     int32_t streaming; /* lbm_streaming */
     int32_t n_ops;     /* 1 <= n_ops <= LBM_MAX_OPS */
     int32_t collision_index; /* index of the collision entry in ops (= number of pre-boundaries) */
-    int32_t variant;   /* reserved for kernel variant selection; must be 0 */
+    int32_t variant;   /* masked runs: 0 = library default, 1 = label-first, 2 = speculative loads, 3 = overwrite
+                          (how the bulk kernel skips general nodes; same results, see csrc/lbm_step.cuh) */
     lbm_op ops[LBM_MAX_OPS];
     /* Masked runs (any boundary present): per-node label byte produced by
      * lbm_pack_masks() and one frozen-slot word per node (bit q set = slot (q,node) is

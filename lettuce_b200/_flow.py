@@ -38,6 +38,20 @@ class Boundary(ABC):
     lettuce/_flow.py:31-52.  On the B200 engine a boundary is a *parameter holder*: the kernel
     family in csrc/lbm_step.cuh implements the operator, selected by class name."""
 
+    # boundaries whose reference implementation writes `flow.f` in place and returns it
+    # (equilibrium_outlet_p.py:63-73, anti_bounce_back_outlet.py:71-91)
+    in_place = False
+
+    def __call__(self, flow: "Flow") -> torch.Tensor:
+        """the boundary applied to every node it would act on if the whole lattice carried its label (the
+        reference evaluates `boundary(flow)` on the full grid and blends by label afterwards,
+        lettuce/_simulation.py:258-305); outlets rewrite their plane of `flow.f` in place like the reference"""
+        out = native.apply_operator(self, flow, is_collision=False)
+        if self.in_place:
+            flow.f.copy_(out)
+            return flow.f
+        return out
+
     @abstractmethod
     def make_no_collision_mask(self, shape: List[int], context) -> Optional[torch.Tensor]:
         ...

@@ -35,8 +35,13 @@ class StreamingStrategy(Enum):
 
 
 class Collision(ABC):
-    """Collision operators are parameter holders for the fused kernel; `native_available`
-    keeps the reference's query (lettuce/_simulation.py:17-28)."""
+    """Collision operators are parameter holders for the fused kernel; `collision(flow)` and `native_available`
+    keep the reference's operator contract (lettuce/_simulation.py:17-28)."""
+
+    def __call__(self, flow) -> torch.Tensor:
+        """post-collision populations of every node of `flow.f` as a new tensor (e.g.
+        lettuce/ext/_collision/bgk_collision.py:17-22): one collide-only launch of the step kernel"""
+        return native.apply_operator(self, flow, is_collision=True)
 
     def native_available(self) -> bool:
         try:

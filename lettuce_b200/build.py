@@ -8,9 +8,14 @@ triples are separate translation units and compile in parallel.
 
     python -m lettuce_b200.build [--force] [--verbose]
 
-A/B experiments: `LBM_B200_NVCC_DEFINES="-DLBM_KBC_PACKED=1" LBM_B200_BUILD_SUFFIX=packed python -m
-lettuce_b200.build` writes `liblbm_b200_packed.so` (objects under build_packed/); select it at run time with
-`LBM_B200_LIB=<path>` (lettuce_b200/native.py).
+Nothing but the default `liblbm_b200.so` (+ its `.sha256` stamp) is ever written inside the repository: objects
+go to `$LBM_B200_BUILD_DIR` (default `$TMPDIR/lbm_b200_build/<suffix>`), so that the tree that `gpurun` snapshots
+stays small.  The default library is built without `-lineinfo` (a third of the size); `LBM_B200_LINEINFO=1` adds it
+for ncu source-page sessions.
+
+A/B experiments: `LBM_B200_NVCC_DEFINES="-DFOO=1" LBM_B200_BUILD_SUFFIX=foo python -m lettuce_b200.build` writes
+`liblbm_b200_foo.so` into the build directory (or into `$LBM_B200_VARIANT_DIR`, e.g. `gpurun_out/../variants`, when it
+has to travel); select it at run time with `LBM_B200_LIB=<path>` (lettuce_b200/native.py).
 """
 from __future__ import annotations
 
@@ -18,17 +23,24 @@ import hashlib
 import os
 import subprocess
 import sys
+import tempfile
 from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 ROOT = os.path.dirname(PKG)
 _SUFFIX = os.environ.get("LBM_B200_BUILD_SUFFIX", "")
-OBJ = os.path.join(PKG, "build" + ("_" + _SUFFIX if _SUFFIX else ""))
-LIB = os.path.join(PKG, "liblbm_b200" + ("_" + _SUFFIX if _SUFFIX else "") + ".so")
+OBJ = os.environ.get("LBM_B200_BUILD_DIR") or os.path.join(tempfile.gettempdir(), "lbm_b200_build",
+                                                         _SUFFIX or "default")
+if _SUFFIX:
+    LIB = os.path.join(os.environ.get("LBM_B200_VARIANT_DIR") or OBJ, "liblbm_b200_" + _SUFFIX + ".so")
+else:
+    LIB = os.path.join(PKG, "liblbm_b200.so")
+STAMP = LIB + ".sha256"
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+FLAGS = ["-std=c++20", "-O3", *(["-lineinfo"] if os.environ.get("LBM_B200_LINEINFO") == "1" else []),
+         "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),
          *os.environ.get("LBM_B200_NVCC_DEFINES", "").split()]
 
@@ -72,16 +84,25 @@ def _unit_hash(unit) -> str:
     return h.hexdigest()
 
 
+def source_digest(digests=None) -> str:
+    """sha256 over every translation unit's (source, headers, flags) hash: identifies the sources a library was
+    built from (written next to the library as `<lib>.sha256`)."""
+    if digests is None:
+        digests = {u[0]: _unit_hash(u) for u in _units()}
+    return hashlib.sha256("".join(sorted(digests.values())).encode()).hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile (if sources changed) and return the path of the shared library."""
-    os.makedirs(OBJ, exist_ok=True)
     units = _units()
     digests = {u[0]: _unit_hash(u) for u in units}
-    stamp = os.path.join(OBJ, "source.sha256")
-    digest = hashlib.sha256("".join(sorted(digests.values())).encode()).hexdigest()
+    stamp = STAMP
+    digest = source_digest(digests)
     if (not force and os.path.exists(LIB) and os.path.exists(stamp)
             and open(stamp).read().strip() == digest):
         return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
 
     def compile_one(unit):
         name, src, defs = unit

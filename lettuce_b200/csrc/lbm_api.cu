@@ -58,9 +58,24 @@ static int launch_links(const StepParams<R> &p, const LinkArgs<R> &a, int coll, 
     return LBM_ERR_BAD_ARGUMENT;
 }
 
-template <class S, class R>
-static const char *step_variant_name(const StepParams<R> &, int, int, bool masked, int) {
-    return masked ? "scalar_masked+general_nodes" : "scalar";
+// how the bulk kernel of a masked run treats general nodes (lbm_step.cuh): lbm_step_desc::variant, else the
+// environment variable LBM_B200_MASKED_MODE (A/B measurements), else the default
+static int masked_mode(const lbm_step_desc *d) {
+    int m = d->variant;
+    if (m == 0) {
+        const char *e = getenv("LBM_B200_MASKED_MODE");
+        m = e ? atoi(e) : 0;
+    }
+    return (m == kMaskedLabelFirst || m == kMaskedOverwrite || m == kMaskedSpeculative) ? m : kMaskedSpeculative;
+}
+
+static const char *step_variant_name(const lbm_step_desc *d, bool masked) {
+    if (!masked) return "scalar";
+    switch (masked_mode(d)) {
+        case kMaskedLabelFirst: return "general_nodes+scalar_masked_label_first";
+        case kMaskedOverwrite: return "scalar_all_nodes+general_nodes_overwrite";
+    }
+    return "general_nodes+scalar_masked_speculative";
 }
 
 static int cuda_fail(int e) {
@@ -218,7 +233,7 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     if (sync) p.sync = *sync;
     p.energy_partials = energy_partials;
     const bool masked = d->n_ops > 1 || d->labels != nullptr;
-    return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, d->variant, st));
+    return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, masked_mode(d), st));
 }
 
 #define LBM_DISPATCH(stencil, dtype, ...)                                   \
@@ -281,7 +296,10 @@ static int pack_typed(const lbm_step_desc *d, const Dims &dm, const uint8_t *ncm
     int e = (int)cudaMallocAsync(&dev, sizeof host, st);
     if (e) return e;
     e = (int)cudaMemcpyAsync(dev, host, sizeof host, cudaMemcpyHostToDevice, st);
-    if (e) return e;
+    if (e) {
+        cudaFreeAsync(dev, st);
+        return e;
+    }
     const int64_t N = (int64_t)dm.n0 * dm.n1 * dm.n2;
     int64_t b = (N + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
@@ -578,14 +596,7 @@ int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, v
 const char *lbm_step_variant_name(const lbm_step_desc *desc) {
     Dims dm;
     if (validate_desc(desc, dm)) return "invalid";
-    const bool masked = desc->n_ops > 1 || desc->labels != nullptr;
-    LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype, {
-        StepParams<R> p;
-        fill_params<S, R>(desc, dm, nullptr, nullptr, p);
-        return (step_variant_name<S, R>(p, desc->ops[desc->collision_index].kind, desc->streaming, masked,
-                                        desc->variant));
-    });
-    return "invalid";
+    return step_variant_name(desc, desc->n_ops > 1 || desc->labels != nullptr);
 }
 
 int lbm_pack_masks(const lbm_step_desc *desc, const uint8_t *d_ncm, const uint8_t *d_nsm, uint8_t *d_labels,

@@ -264,16 +264,14 @@ __device__ void node_pipeline(const StepParams<R> &p, int x, int y, int z, int l
     }
 }
 
-template <class S, class R, int COLL, bool PULL, bool PUSH>
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool AFTER>
 __device__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
     constexpr int Q = S::Q;
     R f[Q];
     node_pipeline<S, R, COLL, PULL>(p, x, y, z, label, f);
-#if defined(LBM_GENERAL_AFTER_BULK)
-    // EXPERIMENT: this kernel was launched BEHIND the bulk kernel, which updated every node as if it were plain
-    // fluid; wait for it to finish before overwriting the slots that belong to the general nodes
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
+    // kMaskedOverwrite: this kernel was launched BEHIND the bulk kernel, which updated every node as if it were
+    // plain fluid; wait for it to finish before overwriting the slots that belong to the general nodes
+    if constexpr (AFTER) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // scatter with the destination-side frozen-slot rule (_simulation.py:252-255):
     // slot (q, dst) takes the streamed value unless it is frozen, in which case the
@@ -367,12 +365,21 @@ LBM_D R node_update(const StepParams<R> &p, int x, int y, int z) {
     }
 }
 
-#if defined(LBM_SPECULATIVE_MASKED_LOADS)
-// EXPERIMENT (not the default build; -DLBM_SPECULATIVE_MASKED_LOADS=1): node_update for masked runs with the label
-// byte loaded TOGETHER with the populations instead of in front of them.  The default masked kernel does
-// LDG(label) -> EXIT? -> LDG x q, i.e. two dependent memory round trips per node; here all q+1 loads are in flight
-// at once and the exit follows them (ptxas keeps that order: checked with cuobjdump).  The loads of the few nodes
-// that belong to the general-nodes kernel are wasted.
+// How the bulk kernel of a masked run treats the nodes that belong to general_nodes_kernel (template parameter
+// MODE of step_scalar_kernel; selected at run time, lbm_step_desc::variant / LBM_B200_MASKED_MODE):
+//   kUnmasked         no masks at all
+//   kMaskedLabelFirst LDG(label) -> EXIT? -> LDG x q: two dependent memory round trips per node
+//   kMaskedSpeculative label byte loaded TOGETHER with the populations, exit after the loads have landed: one
+//                     round trip; the loads of the few general nodes are wasted
+//   kMaskedOverwrite  no label test: the bulk kernel is the unmasked kernel and treats every node as plain fluid;
+//                     general_nodes_kernel, launched BEHIND it with programmatic dependent launch, gathers and
+//                     collides concurrently and overwrites the general nodes' slots after griddepcontrol.wait.
+//                     Every slot the bulk kernel writes wrongly (from or into a general node) has a general node
+//                     as its rightful writer: nodes that stream into a frozen slot carry the general bit, frozen
+//                     slots are rewritten by their owner.
+enum : int { kUnmasked = 0, kMaskedLabelFirst = 1, kMaskedSpeculative = 2, kMaskedOverwrite = 3 };
+
+// node_update for kMaskedSpeculative (ptxas keeps the order LDG x q, LDG.U8, EXIT?, STG x q: checked with cuobjdump).
 template <class S, class R, int COLL, bool PULL, bool PUSH>
 LBM_D void node_update_speculative(const StepParams<R> &p, int x, int y, int z) {
     constexpr int Q = S::Q;
@@ -406,36 +413,32 @@ LBM_D void node_update_speculative(const StepParams<R> &p, int x, int y, int z) 
         p.tbl.st[k][q][rd + zd] = f[q];
     });
 }
-#endif
 
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool MASKED>
+template <class S, class R, int COLL, bool PULL, bool PUSH, int MODE>
 __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
     step_scalar_kernel(const __grid_constant__ StepParams<R> p) {
+    // kMaskedOverwrite: release general_nodes_kernel (launched behind this grid) right away
+    if constexpr (MODE == kMaskedOverwrite) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x = blockIdx.z;
-    if (z >= p.n2 || y >= p.n1) return;
-    if (MASKED) {
-        // Boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
-        // bit 7 and are left to general_nodes_kernel; every output slot still has exactly one writer.
-#if defined(LBM_GENERAL_AFTER_BULK)
-        // EXPERIMENT (not the default build; -DLBM_GENERAL_AFTER_BULK=1): no label test at all.  The bulk kernel
-        // treats every node as plain fluid -- it is then the unmasked kernel, no label traffic, no dependent load --
-        // and general_nodes_kernel, launched behind it with programmatic dependent launch, gathers and collides
-        // concurrently and overwrites the slots of the general nodes once this grid has finished.  Every slot the
-        // bulk kernel writes wrongly (from or into a general node) has a general node as its rightful writer:
-        // nodes that stream into a frozen slot carry the general bit, frozen slots are rewritten by their owner.
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
-        return;
-#endif
-#if defined(LBM_SPECULATIVE_MASKED_LOADS)
-        node_update_speculative<S, R, COLL, PULL, PUSH>(p, x, y, z);
-        return;
-#endif
-        if (p.labels[(int64_t)x * p.n1 * p.n2 + (int64_t)y * p.n2 + z] != p.collision_index) return;
+    if (z < p.n2 && y < p.n1) {
+        // Masked runs: boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
+        // bit 7 and belong to general_nodes_kernel; every output slot ends up with exactly one final writer.
+        if constexpr (MODE == kMaskedLabelFirst) {
+            if (p.labels[(int64_t)x * p.n1 * p.n2 + (int64_t)y * p.n2 + z] == p.collision_index)
+                node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+        } else if constexpr (MODE == kMaskedSpeculative) {
+            node_update_speculative<S, R, COLL, PULL, PUSH>(p, x, y, z);
+        } else {
+            node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+        }
     }
-    node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+    // general_nodes_kernel runs IN FRONT of this grid in these two modes and released it with
+    // griddepcontrol.launch_dependents; a dependent grid has to execute griddepcontrol.wait so that the next
+    // launch on the stream is ordered behind BOTH kernels (free when the sparse kernel has long finished)
+    if constexpr (MODE == kMaskedLabelFirst || MODE == kMaskedSpeculative)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // Bulk kernel that also reduces the kinetic energy of the state it writes (unmasked, non-pushing steps): the
@@ -507,19 +510,21 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
 // (boundaries, frozen slots).  Runs next to step_scalar_kernel<MASKED> on the same
 // stream; the two kernels write disjoint slots of the output buffer.
 // ---------------------------------------------------------------------------
-template <class S, class R, int COLL, bool PULL, bool PUSH>
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool AFTER>
 __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constant__ StepParams<R> p) {
-#if !defined(LBM_GENERAL_AFTER_BULK)
-    // let the bulk kernel (launched with programmatic stream serialization) start right away
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
+    // launched in front of the bulk kernel: let it (programmatic stream serialization) start right away
+    if constexpr (!AFTER) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n_general) return;
+    if (i >= p.n_general) {
+        // every thread of a dependent grid passes the wait, so that grid completion implies the bulk grid's
+        if constexpr (AFTER) asm volatile("griddepcontrol.wait;" ::: "memory");
+        return;
+    }
     const int n = p.general_nodes[i];
     const int z = n % p.n2;
     const int y = (n / p.n2) % p.n1;
     const int x = n / (p.n1 * p.n2);
-    general_node<S, R, COLL, PULL, PUSH>(p, x, y, z, p.labels[n] & 0x7f);
+    general_node<S, R, COLL, PULL, PUSH, AFTER>(p, x, y, z, p.labels[n] & 0x7f);
 }
 
 // ---------------------------------------------------------------------------

@@ -87,6 +87,8 @@ class _PlaneOutlet(Boundary):
     the direction axis), its inward `neighbor` plane and the outgoing velocity set
     {q : e_q . direction = 1} (anti_bounce_back_outlet.py:38-55)."""
 
+    in_place = True
+
     def __init__(self, direction, flow):
         self.direction = _check_direction(direction)
         e = np.asarray(flow.stencil.e)

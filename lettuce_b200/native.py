@@ -529,6 +529,50 @@ class Engine:
         flow.f, flow.f_next = bufs[cur], bufs[1 - cur]
 
 
+class _OneOperator:
+    """The minimal simulation-shaped object `Engine` needs to run ONE operator over the whole lattice."""
+
+    def __init__(self, flow, op, is_collision: bool):
+        from ._simulation import StreamingStrategy        # late: _simulation imports this module
+        from .ext.collision import NoCollision
+        self.flow = flow
+        self.streaming_strategy = StreamingStrategy.NO_STREAMING
+        if is_collision:
+            self.transformer, self.collision_index = [op], 0
+            self.no_collision_mask = self.no_streaming_mask = None
+        else:
+            # label 1 everywhere: the boundary acts on every node, as `boundary(flow)` does in the reference
+            # before Simulation._collide blends it in by label (lettuce/_simulation.py:258-305)
+            self.transformer, self.collision_index = [NoCollision(), op], 0
+            shape = [int(n) for n in flow.f.shape]
+            self.no_collision_mask = torch.ones(shape[1:], dtype=torch.uint8, device=flow.f.device)
+            self.no_streaming_mask = torch.zeros(shape, dtype=torch.uint8, device=flow.f.device)
+        self.collision = self.transformer[self.collision_index]
+
+
+def apply_operator(op, flow, is_collision: bool) -> torch.Tensor:
+    """`op(flow)` of the reference's operator contract (Collision.__call__, lettuce/_simulation.py:17-28;
+    Boundary.__call__, lettuce/_flow.py:31-52): the operator applied to EVERY node of `flow.f`, returned as a new
+    tensor -- one NO_STREAMING launch of the step kernel into a scratch buffer (no torch arithmetic).  Boundaries run
+    through the general-nodes kernel with the whole lattice labelled as theirs."""
+    key = (id(flow.f.untyped_storage()), tuple(flow.f.shape), flow.f.dtype, bool(is_collision))
+    cached = getattr(op, "_b200_call_engine", None)
+    if cached is None or cached[0] != key or cached[1].flow is not flow:
+        cached = (key, Engine(_OneOperator(flow, op, is_collision)))
+        try:
+            op._b200_call_engine = cached
+        except AttributeError:
+            pass
+    eng = cached[1]
+    eng.refresh_parameters()
+    f = flow.f
+    _require_cuda(f, "flow.f")
+    out = torch.empty_like(f)
+    with torch.cuda.device(f.device):
+        check(eng.lib.lbm_step(C.byref(eng.desc), f.data_ptr(), out.data_ptr(), _stream_ptr(f.device)), "lbm_step")
+    return out
+
+
 def describe(simulation):
     """The transformer list of `simulation` as the engine would see it: a list of dicts with the native op
     kind and its parameters.  Works on CPU simulations and on the reference's own `lettuce.Simulation`."""

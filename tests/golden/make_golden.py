@@ -387,7 +387,49 @@ def ebb_cases():
         save(name, **out)
 
 
+def kbc_fp32_floor_case():
+    """How far the REFERENCE's own torch fp32 path is from its own fp64 path for KBC, on exactly the inputs of the
+    GPU parity tests (tests/test_gpu_parity.py: test_tgv_matches_live_oracle's KBC cases and the cylinder_d2q9_kbc
+    golden).  KBC's stabiliser gamma (kbc_collision.py:152) is a ratio of two sums that shrink to rounding level
+    in smooth flow, so any fp32 evaluation is noise-limited; these floors pin the tolerance of the fp32 KBC tests to
+    the reference instead of a hand-written table.  Keys: tgv_<stencil>_<strategy>, cylinder_<strategy>."""
+    out = {}
+    steps = 10
+    for stencil, res, re in (("D2Q9", [48, 40], 800.0), ("D3Q27", [20, 24, 28], 1600.0)):
+        for sname in STRATS:
+            fs = {}
+            for dtype in (torch.float64, torch.float32):
+                ctx = lt.Context(device="cpu", dtype=dtype, use_native=False)
+                flow = lt.TaylorGreenVortex(ctx, list(res), re, 0.05, stencil=STENCILS[stencil]())
+                if dtype == torch.float64:
+                    # same construction as the test: fp64 initial state, seeded 1e-3 perturbation, rounded to fp32
+                    rng = np.random.default_rng(11)
+                    f0 = npy(flow.f) * (1.0 + 1e-3 * (rng.random(tuple(flow.f.shape)) - 0.5))
+                    f0 = f0.astype(np.float32).astype(np.float64)
+                flow.f = ctx.convert_to_tensor(f0)
+                sim = lt.Simulation(flow, lt.KBCCollision(), [], STRATS[sname])
+                sim(steps)
+                fs[dtype] = npy(flow.f).astype(np.float64)
+            out[f"tgv_{stencil}_{sname}"] = np.float64(np.max(np.abs(fs[torch.float32] - fs[torch.float64])
+                                                              / np.abs(fs[torch.float64])))
+    g = np.load(os.path.join(HERE, "cylinder_d2q9_kbc.npz"))
+    for key in [k for k in g.files if k.startswith("f_")]:
+        ctx = lt.Context(device="cpu", dtype=torch.float32, use_native=False)
+        flow = make_obstacle(ObstacleEqOut, ctx, [int(r) for r in g["res"]], lt.D2Q9())
+        flow.initialize()
+        flow.f = ctx.convert_to_tensor(g["f0"])
+        sim = lt.Simulation(flow, lt.KBCCollision(), [], STRATS[key[2:]])
+        sim(int(g["meta"][2]))
+        out["cylinder_" + key[2:]] = np.float64(np.max(np.abs(npy(flow.f).astype(np.float64) - g[key]) / np.abs(g[key])))
+    for k, v in out.items():
+        print(f"  {k}: {float(v):.3e}")
+    save("kbc_fp32_floor", **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["kbc_floor"]:
+        kbc_fp32_floor_case()
+        sys.exit(0)
     if sys.argv[1:] == ["ebb"]:
         ebb_cases()
         sys.exit(0)
@@ -430,3 +472,4 @@ if __name__ == "__main__":
     ebb_cases()
     more_flows_case()
     ebb_random_links_case()
+    kbc_fp32_floor_case()

@@ -147,9 +147,12 @@ def test_obstacle_matches_reference_golden(name, cls, dtype):
         assert np.array_equal(sim.no_collision_mask.cpu().numpy(), g["ncm"])
         assert np.array_equal(sim.no_streaming_mask.cpu().numpy(), g["nsm"])
         sim(int(steps))
-        # KBC's gamma is ill-conditioned where the flow is uniform (sum_h ~ rounding noise,
-        # kbc_collision.py:152); fp32 then only agrees to the size of the non-equilibrium part
-        tol = TOL[dtype] if not (coll == "kbc" and dtype == torch.float32) else 1e-4
+        tol = TOL[dtype]
+        if coll == "kbc" and dtype == torch.float32:
+            # KBC's gamma is ill-conditioned where the flow is uniform (sum_h ~ rounding noise,
+            # kbc_collision.py:152): bound = 5 x the distance of the reference's OWN fp32 path from its fp64 path
+            # on this input (tests/golden/kbc_fp32_floor.npz, written by make_golden.py from the reference)
+            tol = max(tol, 5.0 * float(load_golden("kbc_fp32_floor")["cylinder_" + key[2:]]))
         err = max_rel(get_f(flow), g[key])
         assert err < tol, (name, key, err)
         mass = float(lt.Mass(flow, no_mass_mask=flow.mask)(flow.f).cpu())
@@ -297,9 +300,9 @@ def test_equilibrium_boundary_broadcast_shapes():
 
 
 # ------------------------------------------------------------------ live oracle at larger sizes, all strategies
-REFERENCE_TORCH_FP32_KBC_FLOOR = {("D2Q9", "NO_STREAMING"): 1.061e-03, ("D2Q9", "POST_STREAMING"): 2.417e-04,
-                                  ("D2Q9", "PRE_STREAMING"): 1.056e-05, ("D3Q27", "NO_STREAMING"): 4.351e-05,
-                                  ("D3Q27", "POST_STREAMING"): 1.014e-05, ("D3Q27", "PRE_STREAMING"): 1.379e-05}
+# distance of the reference's own torch fp32 path from its fp64 path on exactly the KBC inputs below, after 10
+# steps: tests/golden/kbc_fp32_floor.npz, generated from the reference by tests/golden/make_golden.py
+REFERENCE_TORCH_FP32_KBC_FLOOR = {k: float(v) for k, v in load_golden("kbc_fp32_floor").items()}
 
 CASES = [("D3Q19", [20, 12, 28], "regularized", 1600.0), ("D3Q27", [12, 20, 24], "smagorinsky", 1600.0),
          ("D2Q9", [48, 40], "bgk", 1.0), ("D2Q9", [48, 40], "kbc", 800.0), ("D2Q9", [33, 47], "trt", 100.0),
@@ -344,7 +347,7 @@ def test_tgv_matches_live_oracle(stencil, res, coll, re, strategy, dtype):
         if dtype == torch.float32:
             # the reference's torch fp32 path itself, measured in the build container on exactly these inputs
             # (max relative difference to its own fp64 path after 10 steps)
-            floor = max(floor, REFERENCE_TORCH_FP32_KBC_FLOOR.get((stencil, strategy), 0.0))
+            floor = max(floor, REFERENCE_TORCH_FP32_KBC_FLOOR[f"tgv_{stencil}_{strategy}"])
         err = float(np.max(np.abs(get_f(flow).astype(hi) - truth) / np.abs(truth)))
         tol = max(tol, 5.0 * floor)
     assert err < tol, (stencil, coll, strategy, err, tol)
