@@ -11,7 +11,7 @@
  *   invoke(simulation) python shim (_template.py:35-39)           lettuce_b200.native.invoke()
  *   Simulation.__init__ mask build (_simulation.py:100-146)       lbm_pack_masks()
  *   Flow.rho / Flow.j / Flow.u (lettuce/_flow.py:157-193)         lbm_moments()
- *   reporter reductions (ext/_reporter/observable_reporter.py     lbm_reduce()
+ *   reporter reductions (ext/_reporter/observable_reporter.py     lbm_reduce(), lbm_step_moments()
  *     :27-68,140-158; util/utility.py:37-99 order=6)
  *   Simulation.__call__ with host-resident populations            lbm_run_host()
  *     (_simulation.py:311-323)
@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LBM_ABI_VERSION 3
+#define LBM_ABI_VERSION 4
 #define LBM_MAX_OPS 8 /* transformer list length: pre_boundaries + collision + post_boundaries */
 
 typedef enum lbm_status {
@@ -138,8 +138,9 @@ typedef struct lbm_step_desc {
     int32_t streaming; /* lbm_streaming */
     int32_t n_ops;     /* 1 <= n_ops <= LBM_MAX_OPS */
     int32_t collision_index; /* index of the collision entry in ops (= number of pre-boundaries) */
-    int32_t variant;   /* masked runs: 0 = library default, 1 = label-first, 2 = speculative loads, 3 = overwrite
-                          (how the bulk kernel skips general nodes; same results, see csrc/lbm_step.cuh) */
+    int32_t variant;   /* nodes per thread of the bulk kernel: 0 = library default, 1, or 2 (two neighbouring nodes as
+                          one float2 on the packed fp32 pipe; used where that kernel exists: fp32, even contiguous
+                          extent, PRE / POST streaming).  Both give bit-identical results (csrc/lbm_vec.cuh). */
     lbm_op ops[LBM_MAX_OPS];
     /* Masked runs (any boundary present): per-node label byte produced by
      * lbm_pack_masks() and one frozen-slot word per node (bit q set = slot (q,node) is
@@ -157,15 +158,26 @@ typedef struct lbm_step_desc {
  * f_out once.  f_in and f_out must not overlap.  Launches on `stream`, does not sync. */
 int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream);
 
-/* One time step that also returns the kinetic energy sum 0.5|u|^2 (lattice units) of the state it writes:
- * the IncompressibleKineticEnergy reporter (ext/_reporter/observable_reporter.py:34-42 with
- * lettuce/_flow.py:200-204) fused into the step kernel, so that a reporter with interval 1 costs no second pass
- * over the populations.  Available for steps without boundaries that do not stream after the collide phase
- * (NO_STREAMING, PRE_STREAMING); otherwise LBM_ERR_UNSUPPORTED (use lbm_step + lbm_reduce).  `d_scratch` needs
- * lbm_step_energy_scratch_bytes(desc) bytes (0 = not available for desc); *d_energy receives one double. */
-size_t lbm_step_energy_scratch_bytes(const lbm_step_desc *desc);
-int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
-                    size_t scratch_bytes, double *d_energy, void *stream);
+/* One time step with the reporters' moment reductions fused into the step kernels (a reporter with interval 1
+ * then costs no second pass over the populations): d_result[0] = sum over nodes of 0.5|u|^2 and d_result[1] = max
+ * over nodes of |u|^2, both in lattice units -- IncompressibleKineticEnergy and MaximumVelocity
+ * (ext/_reporter/observable_reporter.py:27-42 with lettuce/_flow.py:200-204).  Which state they describe depends
+ * on the streaming strategy (lbm_step_moments_state):
+ *   LBM_MOMENTS_OF_OUTPUT  NO_STREAMING, PRE_STREAMING: the state this step WRITES (the node's output is still in
+ *                          registers; collisions conserve rho and j)
+ *   LBM_MOMENTS_OF_INPUT   POST_STREAMING: the state this step READS, i.e. what the previous step left (a pushing
+ *                          step assembles its output node from several source nodes, but its input node is whole):
+ *                          the reduction for the report after step k rides on step k+1
+ *   LBM_MOMENTS_UNAVAILABLE DOUBLE_STREAMING (use lbm_step + lbm_reduce)
+ * Boundaries are allowed (the sparse general-nodes kernel contributes its nodes).  `d_scratch` needs
+ * lbm_step_moments_scratch_bytes(desc) bytes (0 = not available for desc).  Deterministic (no atomics). */
+typedef enum lbm_moments_state {
+    LBM_MOMENTS_UNAVAILABLE = 0, LBM_MOMENTS_OF_OUTPUT = 1, LBM_MOMENTS_OF_INPUT = 2
+} lbm_moments_state;
+int lbm_step_moments_state(const lbm_step_desc *desc);
+size_t lbm_step_moments_scratch_bytes(const lbm_step_desc *desc);
+int lbm_step_moments(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
+                     size_t scratch_bytes, double *d_result, void *stream);
 
 /* Link-wise bounce-back boundaries applied AFTER streaming -- the "efficient bounce-back" boundaries of the
  * reference's example project examples/advanced_projects/efficient_bounce_back_obstacle: its EbbSimulation runs
@@ -211,7 +223,8 @@ int lbm_step_links_n(const lbm_step_desc *desc, const lbm_links *links, int32_t 
  * (lettuce/_simulation.py:317-318) when no reporter is due.  The newest populations end up in
  * d_f_b if n is odd and in d_f_a if n is even.  On lattices of up to LBM_B200_GRAPH_MAX_NODES nodes
  * (environment variable, default 2^20, 0 = off) without boundaries, batches of >= 32 steps are replayed from
- * a cached CUDA graph of 32 steps (launch-latency bound regime); results are identical to n lbm_step calls. */
+ * a cached CUDA graph of 32 steps (launch-latency bound regime); results are identical to n lbm_step calls.
+ * Consecutive steps are chained with programmatic dependent launch (LBM_B200_PDL=0 switches that off). */
 int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *stream);
 
 /* Builds the per-node label byte and frozen-slot word from lettuce's masks
@@ -266,9 +279,12 @@ int lbm_reduce(const lbm_lattice *lat, int what, const void *d_in, const uint8_t
  * device pointers as for lbm_step; halo must be all NULL), downloads the final
  * populations into h_f_out and synchronises.  If h_energy is non-NULL it must hold
  * nsteps doubles and receives sum 0.5|u|^2 after every step (a reporter with
- * interval 1).  Device scratch is allocated and freed inside the call. */
+ * interval 1; reduced inside the step kernels, lbm_step_moments).  h_f_out may equal h_f.  The device work space
+ * (two population buffers + scratch) is kept for the next call with the same size on the same device;
+ * lbm_run_host_release() frees it. */
 int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int64_t nsteps,
                  double *h_energy);
+int lbm_run_host_release(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU x-slabs, one process per GPU (no counterpart in the reference, which is single-device:
@@ -298,20 +314,27 @@ typedef struct lbm_slab {
     /* peer-mapped addresses where this rank publishes the number of steps it has completed: slot 1 of
      * the lo neighbour's counter pair and slot 0 of the hi neighbour's */
     uint64_t *signal_lo, *signal_hi;
-    /* this rank's own counter block (in lbm_ipc_alloc memory, at least 4 words): [0] written by lo,
-     * [1] written by hi, [2],[3] scratch of the in-kernel lock step */
+    /* this rank's own counter block (in lbm_ipc_alloc memory, at least 8 words): [0] written by lo,
+     * [1] written by hi, [2]..[4] scratch of the in-kernel lock step */
     const uint64_t *wait_slots;
     uint64_t epoch;                /* steps completed before this call; identical on all ranks */
 } lbm_slab;
 
 /* n lock-stepped time steps on an x-slab.  Ranks publish the number of steps they have completed to both
  * neighbours and never run a boundary plane of step k+1 before both neighbours have completed step k,
- * which orders the peer reads/writes of consecutive steps.  Unmasked slabs do this INSIDE the step kernel
- * (boundary-plane CTAs are scheduled first, wait for the neighbour's counter, and the last of them
- * publishes this rank's counter; interior CTAs never wait); masked slabs use a 1-thread kernel per step.  desc->halo's population pointers
+ * which orders the peer reads/writes of consecutive steps.  This happens INSIDE the step kernels
+ * (boundary-plane CTAs are scheduled first, wait for the neighbour's counter, and the last of them -- or, with
+ * boundaries, the last CTA of the sparse general-nodes kernel -- publishes this rank's counter; interior CTAs never
+ * wait); slabs thinner than two boundary layers use a 1-thread kernel per step.  A spin on a peer counter gives up
+ * with a trap after LBM_B200_PEER_TIMEOUT_S seconds (default 600).  desc->halo's population pointers
  * are ignored (they are derived from `slab`); its label/frozen pointers are used as given. */
 int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
                     void *stream);
+
+/* ONE lock-stepped slab step (d_f_a -> d_f_b) with the fused reductions of lbm_step_moments over THIS rank's nodes
+ * (d_result[0] = sum 0.5|u|^2, d_result[1] = max |u|^2; the caller combines the ranks' values). */
+int lbm_slab_step_moments(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b,
+                          void *d_scratch, size_t scratch_bytes, double *d_result, void *stream);
 
 /* Introspection. */
 int lbm_abi_version(void);

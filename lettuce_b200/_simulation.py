@@ -140,40 +140,65 @@ class Simulation:
             k = min(k, interval - self.flow.i % interval)
         return max(k, 1)
 
-    def _energy_reporter_due(self, k: int) -> bool:
-        """True when, `k` steps from now, a reporter evaluates an observable that the step kernel can reduce on
-        the fly (`fused_with_step`, i.e. IncompressibleKineticEnergy of this flow) and the engine has that
-        kernel for this simulation (no boundaries, no stream after the collide phase)."""
+    def _fused_reporters_due(self, k: int):
+        """(any, all): `k` steps from now, does ANY due reporter evaluate an observable that the step kernels can
+        reduce on the fly (`fused_with_step`: IncompressibleKineticEnergy / MaximumVelocity of this flow), and are
+        ALL due reporters of that kind?"""
         if self._collide_and_stream is not native.invoke or not self.flow.f.is_cuda:
-            return False
-        for r in self.reporter:
-            obs = getattr(r, "observable", None)
-            if (getattr(obs, "fused_with_step", False) and getattr(obs, "flow", None) is self.flow
-                    and (self.flow.i + k) % max(int(r.interval), 1) == 0):
-                return native.engine_of(self).energy_fusable()
-        return False
+            return False, False
+        due = [r for r in self.reporter if (self.flow.i + k) % max(int(r.interval), 1) == 0]
+        fused = [r for r in due
+                 if getattr(getattr(r, "observable", None), "fused_with_step", False)
+                 and getattr(r.observable, "flow", None) is self.flow and getattr(r, "batchable", False)]
+        return bool(fused), bool(due) and len(fused) == len(due)
 
     def __call__(self, num_steps: int) -> float:
         """Run `num_steps` time steps; returns MLUPS (lettuce/_simulation.py:311-323).  The
-        device is synchronised before the clock is read."""
+        device is synchronised before the clock is read.
+
+        Steps between two due reports run as one library call (`lbm_step_n`).  Reports of observables the step
+        kernels can reduce themselves cost no second pass over the populations: with NO / PRE streaming the step
+        that writes the reported state reduces it; with POST streaming the step FOLLOWING the reported state does
+        (its input node is the reported node), so when only such reporters are due and more steps follow, that next
+        step is launched first and the reporters then receive the values it produced (`flow.i` still names the
+        reported step; `flow.f` is one step ahead for the duration of these reporter calls)."""
         self.context.synchronize()
         beg = timer()
         if self.flow.i == 0:
             self._report()
         remaining = int(num_steps)
+        ahead = 0                       # 1 when flow.f is already one step ahead of flow.i (see above)
         while remaining > 0:
             k = self._batch_length(remaining)
-            if self._energy_reporter_due(k):
-                if k > 1:
-                    native.invoke_n(self, k - 1)
-                native.engine_of(self).step_with_energy()
-            elif k == 1:
+            todo = k - ahead
+            engine = native.engine_of(self) if self._collide_and_stream is native.invoke else None
+            state = engine.moments_state() if engine is not None else native.MOMENTS_UNAVAILABLE
+            any_fused, all_fused = self._fused_reporters_due(k)
+            if todo > 0 and any_fused and state == native.MOMENTS_OF_OUTPUT:
+                if todo > 1:
+                    native.invoke_n(self, todo - 1)
+                engine.step_with_moments()
+            elif todo == 1 and engine is None:
                 self._collide_and_stream(self)
-            else:
-                native.invoke_n(self, k)
+            elif todo > 0:
+                if engine is None:
+                    for _ in range(todo):
+                        self._collide_and_stream(self)
+                else:
+                    native.invoke_n(self, todo)
             self.flow.i += k
-            self._report()
             remaining -= k
+            ahead = 0
+            if all_fused and state == native.MOMENTS_OF_INPUT and remaining > 0:
+                # the next step reduces the moments of the state being reported while it reads it
+                self.flow._b200_reported_moments = engine.step_with_moments()
+                ahead = 1
+                try:
+                    self._report()
+                finally:
+                    self.flow._b200_reported_moments = None
+            else:
+                self._report()
         self._flush_reporters()
         self.context.synchronize()
         end = timer()

@@ -71,7 +71,8 @@ def _headers_hash() -> "hashlib._Hash":
             if name.endswith((".cuh", ".h")):
                 with open(os.path.join(d, name), "rb") as fh:
                     h.update(name.encode() + b"\0" + fh.read())
-    h.update(" ".join(FLAGS).encode())
+    # (without the absolute include path: the digest must not depend on where the checkout lives)
+    h.update(" ".join(f for f in FLAGS if not f.startswith(ROOT)).encode())
     return h
 
 

@@ -20,24 +20,26 @@ int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, in
                   cudaStream_t st);
 size_t reduce_scratch_bytes();
 int launch_fold_sum(const double *partials, int n, double *stage, double *out, cudaStream_t st);
+size_t fold_pair_stage_bytes();
+int launch_fold_pair(const double *partials, int n, double *stage, double *out, cudaStream_t st);
 template <class S, class R>
 int launch_equilibrium(const R *rho, const int64_t *rs, const R *u, const int64_t *us, int n0, int n1, int n2, R *f,
                        cudaStream_t stream);
 
 // collision dispatch over the separately compiled (stencil, dtype, collision) units
 template <class S, class R>
-static int launch_step(const StepParams<R> &p, int coll, int streaming, bool masked, int variant, cudaStream_t stream) {
+static int launch_step(const StepParams<R> &p, int coll, int streaming, const LaunchOptions &opt, cudaStream_t stream) {
     switch (coll) {
-        case LBM_OP_NO_COLLISION: return launch_step_coll<S, R, LBM_OP_NO_COLLISION>(p, streaming, masked, variant, stream);
-        case LBM_OP_BGK: return launch_step_coll<S, R, LBM_OP_BGK>(p, streaming, masked, variant, stream);
-        case LBM_OP_TRT: return launch_step_coll<S, R, LBM_OP_TRT>(p, streaming, masked, variant, stream);
+        case LBM_OP_NO_COLLISION: return launch_step_coll<S, R, LBM_OP_NO_COLLISION>(p, streaming, opt, stream);
+        case LBM_OP_BGK: return launch_step_coll<S, R, LBM_OP_BGK>(p, streaming, opt, stream);
+        case LBM_OP_TRT: return launch_step_coll<S, R, LBM_OP_TRT>(p, streaming, opt, stream);
         case LBM_OP_KBC:
             // KBC exists for D2Q9 and D3Q27 only (kbc_collision.py:101,116)
             if constexpr (S::ID == LBM_D3Q19) return LBM_ERR_UNSUPPORTED;
-            else return launch_step_coll<S, R, LBM_OP_KBC>(p, streaming, masked, variant, stream);
-        case LBM_OP_REGULARIZED: return launch_step_coll<S, R, LBM_OP_REGULARIZED>(p, streaming, masked, variant, stream);
-        case LBM_OP_SMAGORINSKY: return launch_step_coll<S, R, LBM_OP_SMAGORINSKY>(p, streaming, masked, variant, stream);
-        case LBM_OP_BGK_FORCED: return launch_step_coll<S, R, LBM_OP_BGK_FORCED>(p, streaming, masked, variant, stream);
+            else return launch_step_coll<S, R, LBM_OP_KBC>(p, streaming, opt, stream);
+        case LBM_OP_REGULARIZED: return launch_step_coll<S, R, LBM_OP_REGULARIZED>(p, streaming, opt, stream);
+        case LBM_OP_SMAGORINSKY: return launch_step_coll<S, R, LBM_OP_SMAGORINSKY>(p, streaming, opt, stream);
+        case LBM_OP_BGK_FORCED: return launch_step_coll<S, R, LBM_OP_BGK_FORCED>(p, streaming, opt, stream);
     }
     return LBM_ERR_BAD_ARGUMENT;
 }
@@ -58,24 +60,33 @@ static int launch_links(const StepParams<R> &p, const LinkArgs<R> &a, int coll, 
     return LBM_ERR_BAD_ARGUMENT;
 }
 
-// how the bulk kernel of a masked run treats general nodes (lbm_step.cuh): lbm_step_desc::variant, else the
-// environment variable LBM_B200_MASKED_MODE (A/B measurements), else the default
-static int masked_mode(const lbm_step_desc *d) {
-    int m = d->variant;
-    if (m == 0) {
-        const char *e = getenv("LBM_B200_MASKED_MODE");
-        m = e ? atoi(e) : 0;
+// Nodes per thread of the bulk kernel: lbm_step_desc::variant (1 or 2), else the environment variable
+// LBM_B200_LANES (A/B measurements), else the default: two nodes per thread (packed fp32 arithmetic, lbm_vec.cuh)
+// wherever that kernel exists -- fp32, even contiguous extent, PRE / POST streaming.  Both give the same bits.
+static int chosen_lanes(const lbm_step_desc *d) {
+    const int n2 = d->lat.stencil == LBM_D2Q9 ? d->lat.ny : d->lat.nz;
+    if (!lanes2_available(d->lat.dtype, d->streaming, n2)) return 1;
+    int want = d->variant;
+    if (want != 1 && want != 2) {
+        const char *e = getenv("LBM_B200_LANES");
+        want = e ? atoi(e) : 0;
     }
-    return (m == kMaskedLabelFirst || m == kMaskedOverwrite || m == kMaskedSpeculative) ? m : kMaskedSpeculative;
+    if (want == 1 || want == 2) return want;
+    return 2;
 }
 
 static const char *step_variant_name(const lbm_step_desc *d, bool masked) {
-    if (!masked) return "scalar";
-    switch (masked_mode(d)) {
-        case kMaskedLabelFirst: return "general_nodes+scalar_masked_label_first";
-        case kMaskedOverwrite: return "scalar_all_nodes+general_nodes_overwrite";
-    }
-    return "general_nodes+scalar_masked_speculative";
+    if (chosen_lanes(d) == 2) return masked ? "step_kernel<2 nodes/thread, packed fp32> + general_nodes" :
+                                              "step_kernel<2 nodes/thread, packed fp32>";
+    return masked ? "step_kernel<1 node/thread> + general_nodes" : "step_kernel<1 node/thread>";
+}
+
+// spins on peer progress counters give up after this long (LBM_B200_PEER_TIMEOUT_S, default 600 s), in SM clocks
+static unsigned long long peer_timeout_cycles() {
+    const char *e = getenv("LBM_B200_PEER_TIMEOUT_S");
+    double s = e ? atof(e) : 600.0;
+    if (!(s > 0)) s = 600.0;
+    return (unsigned long long)(s * 2.0e9);
 }
 
 static int cuda_fail(int e) {
@@ -86,9 +97,7 @@ static int cuda_fail(int e) {
 }
 
 int cuda_fail_public(int e) { return cuda_fail(e); }
-int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream);
-int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync,
-                 double *energy_partials, void *stream);
+unsigned long long peer_timeout_cycles_public() { return peer_timeout_cycles(); }
 
 struct Dims {
     int n0, n1, n2, d, q;
@@ -226,14 +235,17 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
 }
 
 template <class S, class R>
-static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, const SlabSync *sync,
-                      double *energy_partials, cudaStream_t st) {
+static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, void *f_out, const StepExtras &x,
+                      cudaStream_t st) {
     StepParams<R> p;
     fill_params<S, R>(d, dm, f_in, f_out, p);
-    if (sync) p.sync = *sync;
-    p.energy_partials = energy_partials;
-    const bool masked = d->n_ops > 1 || d->labels != nullptr;
-    return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, masked, masked_mode(d), st));
+    if (x.sync) p.sync = *x.sync;
+    p.energy_partials = x.partials;
+    p.reduce_mode = x.partials ? x.reduce_mode : kReduceNone;
+    LaunchOptions opt;
+    opt.lanes = chosen_lanes(d);
+    opt.chained = x.chained;
+    return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, opt, st));
 }
 
 #define LBM_DISPATCH(stencil, dtype, ...)                                   \
@@ -349,20 +361,15 @@ const char *lbm_last_cuda_error(void) { return g_cuda_error; }
 int64_t lbm_launch_count(void) { return g_launch_count.load(); }
 
 int lbm_step(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *stream) {
-    return step_with_sync(desc, d_f_in, d_f_out, nullptr, stream);
+    return step_general(desc, d_f_in, d_f_out, StepExtras(), stream);
 }
 
 }  // extern "C"
 
 namespace lbm {
-// lbm_step plus the optional in-kernel slab lock step (used by lbm_slab_step_n)
-int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream) {
-    return step_general(desc, d_f_in, d_f_out, sync, nullptr, stream);
-}
-
-// lbm_step plus the optional in-kernel slab lock step (lbm_slab_step_n) or fused energy partials (lbm_step_energy)
-int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync,
-                 double *energy_partials, void *stream) {
+// lbm_step plus the optional in-kernel slab lock step (lbm_slab_step_n), fused reductions (lbm_step_moments) and
+// programmatic chaining behind the previous step (lbm_step_n)
+int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const StepExtras &x, void *stream) {
     Dims dm;
     int rc = validate_desc(desc, dm);
     if (rc) return rc;
@@ -371,37 +378,63 @@ int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, c
     const char *a = (const char *)d_f_in, *b = (const char *)d_f_out;
     if (a < b + bytes && b < a + bytes) return LBM_ERR_ALIASING;
     LBM_DISPATCH(desc->lat.stencil, desc->lat.dtype,
-                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, sync, energy_partials, (cudaStream_t)stream)));
+                 return (step_typed<S, R>(desc, dm, d_f_in, d_f_out, x, (cudaStream_t)stream)));
     return LBM_ERR_BAD_ARGUMENT;
+}
+
+// partial pairs a step with fused reductions may write (either bulk geometry)
+static int max_reduce_slots(const lbm_step_desc *desc, const Dims &dm) {
+    const int a = reduce_slots_for(dm.n0, dm.n1, dm.n2, 1, desc->n_general);
+    const int b = reduce_slots_for(dm.n0, dm.n1, dm.n2, 2, desc->n_general);
+    return a > b ? a : b;
+}
+
+// one step with fused reductions into (partials, stage) -> d_result[2]; shared by lbm_step_moments and the slab entry
+int step_moments_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync,
+                         void *d_scratch, size_t scratch_bytes, double *d_result, bool chained, void *stream) {
+    if (!d_scratch || !d_result) return LBM_ERR_BAD_ARGUMENT;
+    const int state = lbm_step_moments_state(desc);
+    if (state == LBM_MOMENTS_UNAVAILABLE) return LBM_ERR_UNSUPPORTED;
+    const size_t need = lbm_step_moments_scratch_bytes(desc);
+    if (need == 0 || scratch_bytes < need) return LBM_ERR_BAD_ARGUMENT;
+    Dims dm;
+    int rc = validate_desc(desc, dm);
+    if (rc) return rc;
+    StepExtras x;
+    x.sync = sync;
+    x.partials = (double *)d_scratch;
+    x.reduce_mode = state == LBM_MOMENTS_OF_OUTPUT ? kReduceOutput : kReduceInput;
+    x.chained = chained;
+    rc = step_general(desc, d_f_in, d_f_out, x, stream);
+    if (rc) return rc;
+    const int slots = reduce_slots_for(dm.n0, dm.n1, dm.n2, chosen_lanes(desc), desc->n_general);
+    return cuda_fail(launch_fold_pair((const double *)d_scratch, slots, (double *)d_scratch + 2 * (size_t)max_reduce_slots(desc, dm),
+                                      d_result, (cudaStream_t)stream));
 }
 }  // namespace lbm
 
 extern "C" {
 
-static bool energy_fusable(const lbm_step_desc *desc) {
-    return desc && desc->n_ops == 1 && !desc->labels && !(desc->streaming & LBM_POST_STREAMING);
+int lbm_step_moments_state(const lbm_step_desc *desc) {
+    if (!desc) return LBM_MOMENTS_UNAVAILABLE;
+    switch (desc->streaming) {
+        case LBM_NO_STREAMING:
+        case LBM_PRE_STREAMING: return LBM_MOMENTS_OF_OUTPUT;   // the node's output is still in registers
+        case LBM_POST_STREAMING: return LBM_MOMENTS_OF_INPUT;   // the node's input is the previous step's output
+    }
+    return LBM_MOMENTS_UNAVAILABLE;                             // DOUBLE_STREAMING: neither
 }
 
-size_t lbm_step_energy_scratch_bytes(const lbm_step_desc *desc) {
+size_t lbm_step_moments_scratch_bytes(const lbm_step_desc *desc) {
     Dims dm;
-    if (!desc || lattice_dims(&desc->lat, dm) || !energy_fusable(desc)) return 0;
-    dim3 grid, block;
-    bulk_geometry(dm.n0, dm.n1, dm.n2, grid, block);
-    // one partial per CTA of the step kernel + the staging area of the two-stage fold
-    return sizeof(double) * (size_t)grid.x * grid.y * grid.z + reduce_scratch_bytes();
+    if (!desc || lattice_dims(&desc->lat, dm) || lbm_step_moments_state(desc) == LBM_MOMENTS_UNAVAILABLE) return 0;
+    // one (sum, max) pair per CTA of the step's kernels + the staging area of the two-stage fold
+    return 2 * sizeof(double) * (size_t)max_reduce_slots(desc, dm) + fold_pair_stage_bytes();
 }
 
-int lbm_step_energy(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
-                    size_t scratch_bytes, double *d_energy, void *stream) {
-    if (!d_scratch || !d_energy) return LBM_ERR_BAD_ARGUMENT;
-    if (!energy_fusable(desc)) return LBM_ERR_UNSUPPORTED;
-    const size_t need = lbm_step_energy_scratch_bytes(desc);
-    if (need == 0 || scratch_bytes < need) return LBM_ERR_BAD_ARGUMENT;
-    const int rc = step_general(desc, d_f_in, d_f_out, nullptr, (double *)d_scratch, stream);
-    if (rc) return rc;
-    const int n_partials = (int)((need - reduce_scratch_bytes()) / sizeof(double));
-    return cuda_fail(launch_fold_sum((const double *)d_scratch, n_partials, (double *)d_scratch + n_partials, d_energy,
-                                     (cudaStream_t)stream));
+int lbm_step_moments(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
+                     size_t scratch_bytes, double *d_result, void *stream) {
+    return step_moments_general(desc, d_f_in, d_f_out, nullptr, d_scratch, scratch_bytes, d_result, false, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -427,6 +460,11 @@ std::mutex g_graph_mutex;
 GraphSlot g_graph_slots[kGraphSlots];
 uint64_t g_graph_clock = 0;
 
+bool pdl_enabled() {                   // LBM_B200_PDL=0 switches the programmatic chaining of steps off (A/B)
+    const char *e = getenv("LBM_B200_PDL");
+    return !(e && e[0] == '0');
+}
+
 int64_t graph_max_nodes() {           // read per call: cheap, and a host program may switch it at run time
     const char *e = getenv("LBM_B200_GRAPH_MAX_NODES");
     return e ? (int64_t)atoll(e) : (int64_t)1 << 20;
@@ -434,7 +472,7 @@ int64_t graph_max_nodes() {           // read per call: cheap, and a host progra
 
 // captures kGraphSteps steps on a private stream (the caller's may be the legacy default stream, which cannot
 // be captured) and instantiates them; returns 0 or a cudaError / lbm_status
-int capture_steps(const lbm_step_desc *desc, void *a, void *b, cudaGraphExec_t *exec) {
+int capture_steps(const lbm_step_desc *desc, void *a, void *b, bool chained, cudaGraphExec_t *exec) {
     cudaStream_t cs = nullptr;
     int e = (int)cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
     if (e) return e;
@@ -445,7 +483,9 @@ int capture_steps(const lbm_step_desc *desc, void *a, void *b, cudaGraphExec_t *
     if (!e) {
         void *x = a, *y = b;
         for (int k = 0; k < kGraphSteps && !rc; ++k) {
-            rc = lbm_step(desc, x, y, cs);
+            lbm::StepExtras extras;
+            extras.chained = chained && k > 0;      // programmatic edges between consecutive steps
+            rc = lbm::step_general(desc, x, y, extras, cs);
             void *t = x; x = y; y = t;
         }
         e = (int)cudaStreamEndCapture(cs, &graph);
@@ -475,7 +515,11 @@ int64_t graph_steps(const lbm_step_desc *desc, void *a, void *b, int64_t n, cuda
     }
     if (!slot) {
         cudaGraphExec_t exec = nullptr;
-        const int e = capture_steps(desc, a, b, &exec);
+        int e = capture_steps(desc, a, b, pdl_enabled(), &exec);
+        if (e && pdl_enabled()) {
+            cudaGetLastError();                      // programmatic edges refused by this driver: plain capture
+            e = capture_steps(desc, a, b, false, &exec);
+        }
         if (e) {
             *status = lbm::cuda_fail_public(e);
             return -1;
@@ -585,8 +629,13 @@ int lbm_step_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, v
         if (done < 0) return rc;
         n -= done;                                   // kGraphSteps is even: a still holds the newest populations
     }
+    // consecutive steps are chained with programmatic dependent launch: step k+1's CTAs become resident while step
+    // k drains and wait (griddepcontrol.wait) for its completion before they read anything
+    const bool chain = pdl_enabled();
     for (int64_t k = 0; k < n; ++k) {
-        const int rc = lbm_step(desc, a, b, stream);
+        lbm::StepExtras extras;
+        extras.chained = chain && k > 0;
+        const int rc = lbm::step_general(desc, a, b, extras, stream);
         if (rc) return rc;
         void *t = a; a = b; b = t;
     }
@@ -667,6 +716,37 @@ int lbm_reduce(const lbm_lattice *lat, int what, const void *d_in, const uint8_t
     return LBM_ERR_BAD_ARGUMENT;
 }
 
+// device work space of lbm_run_host, kept between calls (allocating and freeing 2 x the lattice costs more than
+// the steps of a short run)
+namespace {
+struct HostRunWorkspace {
+    int device = -1;
+    size_t bytes = 0, scratch_bytes = 0;
+    void *a = nullptr, *b = nullptr, *scratch = nullptr;
+    double *d_e = nullptr;
+    cudaStream_t stream = nullptr;
+    void release() {
+        if (device >= 0) {
+            int cur = -1;
+            cudaGetDevice(&cur);
+            cudaSetDevice(device);
+            if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+            cudaFree(a); cudaFree(b); cudaFree(scratch); cudaFree(d_e);
+            if (cur >= 0) cudaSetDevice(cur);
+        }
+        *this = HostRunWorkspace();
+    }
+};
+HostRunWorkspace g_host_ws;
+std::mutex g_host_ws_mutex;
+}  // namespace
+
+int lbm_run_host_release(void) {
+    std::lock_guard<std::mutex> lock(g_host_ws_mutex);
+    g_host_ws.release();
+    return LBM_OK;
+}
+
 int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int64_t nsteps, double *h_energy) {
     Dims dm;
     int rc = validate_desc(desc, dm);
@@ -675,44 +755,64 @@ int lbm_run_host(const lbm_step_desc *desc, const void *h_f, void *h_f_out, int6
     const lbm_halo &h = desc->halo;
     if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return LBM_ERR_BAD_ARGUMENT;
     const size_t bytes = (size_t)dm.q * dm.n0 * dm.n1 * dm.n2 * (desc->lat.dtype == LBM_F32 ? 4 : 8);
-    cudaStream_t st = nullptr;
-    void *a = nullptr, *b = nullptr, *scratch = nullptr;
-    double *d_e = nullptr;
-    int e = (int)cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    const size_t fused_bytes = lbm_step_moments_scratch_bytes(desc);
+    const size_t scratch_bytes = fused_bytes > reduce_scratch_bytes() ? fused_bytes : reduce_scratch_bytes();
+    int device = -1;
+    int e = (int)cudaGetDevice(&device);
     if (e) return cuda_fail(e);
-    auto cleanup = [&](int code) {
+    std::lock_guard<std::mutex> lock(g_host_ws_mutex);
+    HostRunWorkspace &ws = g_host_ws;
+    if (ws.device != device || ws.bytes != bytes || ws.scratch_bytes < scratch_bytes) {
+        ws.release();
+        ws.device = device;
+        if ((e = (int)cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking)) ||
+            (e = (int)cudaMalloc(&ws.a, bytes)) || (e = (int)cudaMalloc(&ws.b, bytes)) ||
+            (e = (int)cudaMalloc(&ws.scratch, scratch_bytes)) || (e = (int)cudaMalloc(&ws.d_e, 2 * sizeof(double)))) {
+            ws.release();
+            return cuda_fail(e);
+        }
+        ws.bytes = bytes;
+        ws.scratch_bytes = scratch_bytes;
+    }
+    cudaStream_t st = ws.stream;
+    void *a = ws.a, *b = ws.b;
+    auto fail = [&](int code) {
         cudaStreamSynchronize(st);
-        if (a) cudaFree(a);
-        if (b) cudaFree(b);
-        if (scratch) cudaFree(scratch);
-        if (d_e) cudaFree(d_e);
-        cudaStreamDestroy(st);
         return code;
     };
-    // non-pushing steps without boundaries reduce the energy inside the step kernel (lbm_step_energy)
-    const size_t fused_bytes = h_energy ? lbm_step_energy_scratch_bytes(desc) : 0;
-    const size_t scratch_bytes = fused_bytes > reduce_scratch_bytes() ? fused_bytes : reduce_scratch_bytes();
-    if ((e = (int)cudaMalloc(&a, bytes)) || (e = (int)cudaMalloc(&b, bytes)) ||
-        (e = (int)cudaMalloc(&scratch, scratch_bytes)) || (e = (int)cudaMalloc(&d_e, sizeof(double))))
-        return cleanup(cuda_fail(e));
-    if ((e = (int)cudaMemcpyAsync(a, h_f, bytes, cudaMemcpyHostToDevice, st))) return cleanup(cuda_fail(e));
+    if ((e = (int)cudaMemcpyAsync(a, h_f, bytes, cudaMemcpyHostToDevice, st))) return fail(cuda_fail(e));
+    // Every step's kinetic energy is reduced inside the step kernels (lbm_step_moments).  Steps that describe the
+    // state they WRITE deliver the value of step k with step k; steps that describe the state they READ
+    // (POST_STREAMING) deliver it with step k + 1, and the last one comes from a stand-alone reduction.
+    const int state = h_energy ? lbm_step_moments_state(desc) : LBM_MOMENTS_UNAVAILABLE;
     for (int64_t k = 0; k < nsteps; ++k) {
-        rc = fused_bytes ? lbm_step_energy(desc, a, b, scratch, scratch_bytes, d_e, st) : lbm_step(desc, a, b, st);
-        if (rc) return cleanup(rc);
+        const bool fused = state == LBM_MOMENTS_OF_OUTPUT || (state == LBM_MOMENTS_OF_INPUT && k > 0);
+        rc = fused ? step_moments_general(desc, a, b, nullptr, ws.scratch, ws.scratch_bytes, ws.d_e, k > 0, st)
+                   : lbm_step(desc, a, b, st);
+        if (rc) return fail(rc);
         void *t = a; a = b; b = t;
-        if (h_energy) {
-            if (!fused_bytes) {
-                rc = lbm_reduce(&desc->lat, LBM_SUM_HALF_U2, a, nullptr, scratch, d_e, st);
-                if (rc) return cleanup(rc);
-            }
-            // result of this step read back to the host (reporter with interval 1)
-            if ((e = (int)cudaMemcpyAsync(h_energy + k, d_e, sizeof(double), cudaMemcpyDeviceToHost, st)))
-                return cleanup(cuda_fail(e));
+        if (!h_energy) continue;
+        int64_t slot = k;                       // which step's energy ws.d_e holds now
+        if (state == LBM_MOMENTS_OF_INPUT) {
+            if (k == 0) continue;
+            slot = k - 1;
+        } else if (state == LBM_MOMENTS_UNAVAILABLE) {
+            rc = lbm_reduce(&desc->lat, LBM_SUM_HALF_U2, a, nullptr, ws.scratch, ws.d_e, st);
+            if (rc) return fail(rc);
         }
+        // result of that step read back to the host (reporter with interval 1)
+        if ((e = (int)cudaMemcpyAsync(h_energy + slot, ws.d_e, sizeof(double), cudaMemcpyDeviceToHost, st)))
+            return fail(cuda_fail(e));
     }
-    if ((e = (int)cudaMemcpyAsync(h_f_out, a, bytes, cudaMemcpyDeviceToHost, st))) return cleanup(cuda_fail(e));
+    if (h_energy && state == LBM_MOMENTS_OF_INPUT && nsteps > 0) {
+        rc = lbm_reduce(&desc->lat, LBM_SUM_HALF_U2, a, nullptr, ws.scratch, ws.d_e, st);
+        if (rc) return fail(rc);
+        if ((e = (int)cudaMemcpyAsync(h_energy + nsteps - 1, ws.d_e, sizeof(double), cudaMemcpyDeviceToHost, st)))
+            return fail(cuda_fail(e));
+    }
+    if ((e = (int)cudaMemcpyAsync(h_f_out, a, bytes, cudaMemcpyDeviceToHost, st))) return fail(cuda_fail(e));
     e = (int)cudaStreamSynchronize(st);
-    return cleanup(e ? cuda_fail(e) : LBM_OK);
+    return e ? cuda_fail(e) : LBM_OK;
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
-// lbm_core.cuh -- velocity sets, equilibrium and collision operators as
-// compile-time-unrolled device code.  Everything here works on a register array
-// `R f[Q]` holding the populations of ONE lattice node.
+// lbm_core.cuh -- velocity sets, equilibrium and collision operators as compile-time-unrolled code on a register
+// array `V f[Q]` holding the populations of ONE lattice node (V = float, double) or of TWO neighbouring nodes
+// (V = float2, Blackwell's packed fp32 arithmetic; see lbm_vec.cuh).  Written once, with explicit round-to-nearest
+// operations, so that every instantiation yields the same bits per node; compiles for the device and the host.
 //
 // Semantics follow lettuce's torch path (the parity oracle), cited per function.
 #pragma once
@@ -8,11 +9,9 @@
 #include <stdint.h>
 
 #include "../../include/lbm_b200.h"
+#include "lbm_vec.cuh"
 
 namespace lbm {
-
-#define LBM_HD __host__ __device__ __forceinline__
-#define LBM_D __device__ __forceinline__
 
 // ---------------------------------------------------------------------------
 // Velocity sets.  Internally every lattice is three-dimensional with extents
@@ -74,95 +73,11 @@ struct D3Q27 {
 constexpr double kCs = 0.57735026918962584;  // 1/sqrt(3) rounded to double
 constexpr double kCs2 = kCs * kCs;
 
-// ---------------------------------------------------------------------------
-// moments (lettuce/_flow.py:157-193)
-// ---------------------------------------------------------------------------
-template <class S, class R>
-LBM_D void moments(const R (&f)[S::Q], R &rho, R (&j)[3]) {
-    rho = R(0);
-    j[0] = j[1] = j[2] = R(0);
-#pragma unroll
-    for (int q = 0; q < S::Q; ++q) {
-        rho += f[q];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (S::e(q, a) == 1) j[a] += f[q];
-            if (S::e(q, a) == -1) j[a] -= f[q];
-        }
-    }
-}
-
-// feq_q = w_q rho ((2 e.u - u.u)/(2 cs^2) + (e.u/cs^2)^2/2 + 1)
-// (lettuce/ext/_equilibrium/quadratic_equilibrium.py:11-24)
-template <class S, class R>
-struct Equilibrium {
-    R rho, u[3], base;  // base = 1 - u.u/(2 cs^2)
-    LBM_D Equilibrium(R rho_, const R (&u_)[3]) : rho(rho_) {
-        u[0] = u_[0]; u[1] = u_[1]; u[2] = u_[2];
-        const R uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-        base = R(1) - uu * R(1.0 / (2.0 * kCs2));
-    }
-    template <int q>
-    LBM_D R get() const {
-        R eu = R(0);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (S::e(q, a) == 1) eu += u[a];
-            if (S::e(q, a) == -1) eu -= u[a];
-        }
-        // 1 + eu/cs2 + eu^2/(2 cs2^2) - uu/(2 cs2)
-        const R poly = base + eu * (R(1.0 / kCs2) + eu * R(0.5 / (kCs2 * kCs2)));
-        return R(S::w(q)) * rho * poly;
-    }
-    // feq of q and of its opposite: they share the even part base + (e.u)^2/(2 cs^4)
-    template <int q>
-    LBM_D void pair(R &fq, R &fo) const {
-        R eu = R(0);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (S::e(q, a) == 1) eu += u[a];
-            if (S::e(q, a) == -1) eu -= u[a];
-        }
-        const R wr = R(S::w(q)) * rho;
-        const R even = base + (eu * eu) * R(0.5 / (kCs2 * kCs2));
-        const R odd = eu * R(1.0 / kCs2);
-        fq = wr * (even + odd);
-        fo = wr * (even - odd);
-    }
-#if defined(LBM_KBC_PACKED)
-    // (feq_q, feq_opposite(q)) as one float2: wr * (even + odd * (1, -1))
-    template <int q>
-    LBM_D float2 pair2(const float2 pm) const {
-        R eu = R(0);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (S::e(q, a) == 1) eu += u[a];
-            if (S::e(q, a) == -1) eu -= u[a];
-        }
-        const float wr = float(R(S::w(q)) * rho);
-        const float even = float(base + (eu * eu) * R(0.5 / (kCs2 * kCs2)));
-        const float odd = float(eu * R(1.0 / kCs2));
-        return __fmul2_rn(make_float2(wr, wr), __ffma2_rn(make_float2(odd, odd), pm, make_float2(even, even)));
-    }
-#endif
-    // feq_q + feq_opposite(q)
-    template <int q>
-    LBM_D R pair_sum() const {
-        R eu = R(0);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (S::e(q, a) == 1) eu += u[a];
-            if (S::e(q, a) == -1) eu -= u[a];
-        }
-        return (R(2.0 * S::w(q)) * rho) * (base + (eu * eu) * R(0.5 / (kCs2 * kCs2)));
-    }
-};
-
 // compile-time loop helper: body.template operator()<q>() for q in [0, Q)
 template <int Q, int q = 0>
 struct ForQ {
     template <class F>
-    LBM_D static void run(F &&fn) {
+    LBM_HD static void run(F &&fn) {
         fn.template operator()<q>();
         ForQ<Q, q + 1>::run(fn);
     }
@@ -170,321 +85,343 @@ struct ForQ {
 template <int Q>
 struct ForQ<Q, Q> {
     template <class F>
-    LBM_D static void run(F &&) {}
+    LBM_HD static void run(F &&) {}
 };
 
-template <class S, class R>
-LBM_D void equilibrium_all(R rho, const R (&u)[3], R (&feq)[S::Q]) {
-    Equilibrium<S, R> eq(rho, u);
+// running sum whose first term is taken as is (no "0 + x"); every branch below is resolved at compile time
+// once the loops over q are unrolled
+template <class V>
+struct Acc {
+    V v;
+    bool set = false;
+    LBM_HD void add(V t) {
+        v = set ? vadd(v, t) : t;
+        set = true;
+    }
+    LBM_HD void sub(V t) {
+        v = set ? vsub(v, t) : vneg(t);
+        set = true;
+    }
+    LBM_HD void add_signed(int sign, V t) {
+        if (sign > 0) add(t);
+        if (sign < 0) sub(t);
+    }
+    LBM_HD V get() const { return set ? v : vset<V>(0.0); }
+};
+
+// e_q . u as a sum of +-u_a
+template <class S, class V, int q>
+LBM_HD V e_dot(const V (&u)[3]) {
+    Acc<V> eu;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) eu.add_signed(S::e(q, a), u[a]);
+    return eu.get();
+}
+
+// ---------------------------------------------------------------------------
+// moments (lettuce/_flow.py:157-193): rho = sum_q f_q, j = sum_q e_q f_q
+// ---------------------------------------------------------------------------
+template <class S, class V>
+LBM_HD void moments(const V (&f)[S::Q], V &rho, V (&j)[3]) {
+    Acc<V> r, m[3];
+    ForQ<S::Q>::run([&]<int q>() {
+        r.add(f[q]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) m[a].add_signed(S::e(q, a), f[q]);
+    });
+    rho = r.get();
+    j[0] = m[0].get(); j[1] = m[1].get(); j[2] = m[2].get();
+}
+
+// rho and u = j / rho of one node (Flow.u without force correction)
+template <class S, class V>
+LBM_HD void density_velocity(const V (&f)[S::Q], V &rho, V (&u)[3]) {
+    V j[3];
+    moments<S, V>(f, rho, j);
+    const V inv = vrecip(rho);
+    u[0] = vmul(j[0], inv); u[1] = vmul(j[1], inv); u[2] = vmul(j[2], inv);
+}
+
+// feq_q = w_q rho ((2 e.u - u.u)/(2 cs^2) + (e.u/cs^2)^2/2 + 1)
+//       = w_q rho (base + e.u (1/cs^2 + e.u / (2 cs^4))),  base = 1 - u.u/(2 cs^2)
+// (lettuce/ext/_equilibrium/quadratic_equilibrium.py:11-24)
+template <class S, class V>
+struct Equilibrium {
+    V rho, u[3], base;
+    LBM_HD Equilibrium(V rho_, const V (&u_)[3]) : rho(rho_) {
+        u[0] = u_[0]; u[1] = u_[1]; u[2] = u_[2];
+        const V uu = vfma(u[2], u[2], vfma(u[1], u[1], vmul(u[0], u[0])));
+        base = vfma(uu, vset<V>(-1.0 / (2.0 * kCs2)), vset<V>(1.0));
+    }
+    template <int q>
+    LBM_HD V wrho() const { return vmul(vset<V>(S::w(q)), rho); }
+    template <int q>
+    LBM_HD V get() const {
+        if constexpr (q == 0) {
+            return vmul(wrho<0>(), base);
+        } else {
+            const V eu = e_dot<S, V, q>(u);
+            const V poly = vfma(eu, vfma(eu, vset<V>(0.5 / (kCs2 * kCs2)), vset<V>(1.0 / kCs2)), base);
+            return vmul(wrho<q>(), poly);
+        }
+    }
+    // even part of q and its opposite: base + (e.u)^2 / (2 cs^4); feq_q + feq_opposite = 2 w rho even
+    template <int q>
+    LBM_HD V even(V eu) const { return vfma(vmul(eu, eu), vset<V>(0.5 / (kCs2 * kCs2)), base); }
+    // feq of q and of its opposite, sharing the even part: w rho (even +- e.u / cs^2)
+    template <int q>
+    LBM_HD void pair(V &fq, V &fo) const {
+        const V eu = e_dot<S, V, q>(u);
+        const V wr = wrho<q>();
+        const V a = vmul(wr, even<q>(eu));
+        const V b = vmul(vmul(wr, vset<V>(1.0 / kCs2)), eu);
+        fq = vadd(a, b);
+        fo = vsub(a, b);
+    }
+};
+
+template <class S, class V>
+LBM_HD void equilibrium_all(V rho, const V (&u)[3], V (&feq)[S::Q]) {
+    Equilibrium<S, V> eq(rho, u);
     ForQ<S::Q>::run([&]<int q>() { feq[q] = eq.template get<q>(); });
 }
 
 // ---------------------------------------------------------------------------
-// collisions.  COLL is an lbm_op_kind collision value.
+// collisions.  COLL is an lbm_op_kind collision value; a and b are the operator's scalars
+// (collision_scalars below), the same for every lane.
 // ---------------------------------------------------------------------------
-template <class S, class R, int COLL>
+template <class S, class V, int COLL>
 struct Collide;
 
-template <class S, class R>
-struct Collide<S, R, LBM_OP_NO_COLLISION> {
-    LBM_D static void apply(R (&)[S::Q], R, R) {}
+template <class S, class V>
+struct Collide<S, V, LBM_OP_NO_COLLISION> {
+    LBM_HD static void apply(V (&)[S::Q], scalar_t<V>, scalar_t<V>) {}
 };
 
-// f - (f - feq)/tau   (lettuce/ext/_collision/bgk_collision.py:17-22)
-template <class S, class R>
-struct Collide<S, R, LBM_OP_BGK> {
-    LBM_D static void apply(R (&f)[S::Q], R inv_tau, R) {
-        R rho, j[3];
-        moments<S, R>(f, rho, j);
-        const R inv_rho = R(1) / rho;
-        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
-        Equilibrium<S, R> eq(rho, u);
-        ForQ<S::Q>::run([&]<int q>() { f[q] = f[q] - inv_tau * (f[q] - eq.template get<q>()); });
+// f - (f - feq)/tau   (lettuce/ext/_collision/bgk_collision.py:17-22); a = 1/tau
+template <class S, class V>
+struct Collide<S, V, LBM_OP_BGK> {
+    LBM_HD static void apply(V (&f)[S::Q], scalar_t<V> inv_tau, scalar_t<V>) {
+        V rho, u[3];
+        density_velocity<S, V>(f, rho, u);
+        Equilibrium<S, V> eq(rho, u);
+        const V omega = vsplat<V>(inv_tau);
+        ForQ<S::Q>::run([&]<int q>() { f[q] = vfma(omega, vsub(eq.template get<q>(), f[q]), f[q]); });
     }
 };
 
 // f - [ (f+ - feq+)/tau+ + (f- - feq-)/tau- ]   (lettuce/ext/_collision/trt_collision.py:16-27)
 // a = 1/(2 tau+), b = 1/(2 tau-)
-template <class S, class R>
-struct Collide<S, R, LBM_OP_TRT> {
-    LBM_D static void apply(R (&f)[S::Q], R a, R b) {
-        R rho, j[3];
-        moments<S, R>(f, rho, j);
-        const R inv_rho = R(1) / rho;
-        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
-        Equilibrium<S, R> eq(rho, u);
+template <class S, class V>
+struct Collide<S, V, LBM_OP_TRT> {
+    LBM_HD static void apply(V (&f)[S::Q], scalar_t<V> a_, scalar_t<V> b_) {
+        V rho, u[3];
+        density_velocity<S, V>(f, rho, u);
+        Equilibrium<S, V> eq(rho, u);
+        const V a = vsplat<V>(a_), b = vsplat<V>(b_);
         ForQ<S::Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
             if constexpr (q == 0) {
-                const R fe = eq.template get<0>();
-                f[0] = f[0] - ((f[0] + f[0]) - (fe + fe)) * a;
+                const V d = vsub(f[0], eq.template get<0>());
+                f[0] = vfnma(vadd(d, d), a, f[0]);
             } else if constexpr (q < o) {
-                const R fq = f[q], fo = f[o];
-                const R eq_q = eq.template get<q>(), eq_o = eq.template get<o>();
-                const R even = ((fq + fo) - (eq_q + eq_o)) * a;
-                const R odd = ((fq - fo) - (eq_q - eq_o)) * b;
-                f[q] = fq - (even + odd);
-                f[o] = fo - (even - odd);
+                V eq_q, eq_o;
+                eq.template pair<q>(eq_q, eq_o);
+                const V fq = f[q], fo = f[o];
+                const V even = vmul(vsub(vadd(fq, fo), vadd(eq_q, eq_o)), a);
+                const V odd = vmul(vsub(vsub(fq, fo), vsub(eq_q, eq_o)), b);
+                f[q] = vsub(fq, vadd(even, odd));
+                f[o] = vsub(fo, vsub(even, odd));
             }
         });
     }
 };
 
-// dh / feq inside KBC's entropic sums.  gamma is the ratio of two sums that are dominated by
-// rounding noise in smooth flow (see tests/test_gpu_parity.py), so fp32 uses the 2-ulp fast
-// approximate reciprocal (one MUFU.RCP, ~1 ulp; feq is O(1e-3..1), far from the denormal range)
-// instead of 27 IEEE divisions with their slow-path calls per node.
-LBM_D float kbc_div(float a, float b) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-    return a * r;
-}
-// fp64: reciprocal seed (MUFU.RCP64H, ~20 bits) refined by two Newton steps to full precision; avoids the
-// IEEE division's slow-path subroutine 27 times per node.
-LBM_D double kbc_div(double a, double b) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    r = fma(fma(-b, r, 1.0), r, r);
-    r = fma(fma(-b, r, 1.0), r, r);
-    return a * r;
-}
-
 // Entropic KBC in the closed form of SURVEY.md Appendix A.3
-// (lettuce/ext/_collision/kbc_collision.py:22-160).  beta = 1/(2 tau).
+// (lettuce/ext/_collision/kbc_collision.py:22-160).  a = beta = 1/(2 tau).
 //
 // Register plan: only f itself lives in registers.  Moments come from opposite-pair sums and
 // differences, feq is re-evaluated per opposite pair where it is needed (the pair shares the even
 // part; the second moments need only that part), and delta_s is one of ten scalars derived from
-// the six second moments.
-template <class S, class R>
-struct Collide<S, R, LBM_OP_KBC> {
-    // shear part of population q from the precomputed moment combinations (kbc_collision.py:44-94)
+// the six second moments.  In fp32 this is ~550 operations per node on the fp32 pipe: the one-node kernel is bound
+// by that pipe (sm_100 issues a scalar FFMA every second cycle); the two-node float2 instantiation halves it.
+template <class S, class V>
+struct Collide<S, V, LBM_OP_KBC> {
+    // shear part of population q from the precomputed moment combinations (kbc_collision.py:44-94):
+    // index into c[] and sign; index < 0: no shear part
+    LBM_HD static constexpr int ds_index(int q) {
+        if (q == 0) return 0;
+        if (S::D == 2) return q <= 4 ? (q & 1 ? 1 : 2) : 3;      // c[1] (x axis: 1,3), c[2] (y axis: 2,4), c[3] = Pxy/4
+        return q <= 6 ? (q + 1) / 2 : (q <= 10 ? 4 : (q <= 14 ? 5 : (q <= 18 ? 6 : -1)));
+    }
+    LBM_HD static constexpr int ds_sign(int q) {
+        if (S::D == 2) return (q == 6 || q == 8) ? -1 : 1;
+        return (q == 9 || q == 10 || q == 13 || q == 14 || q == 17 || q == 18) ? -1 : 1;
+    }
     template <int q>
-    LBM_D static R ds_of(const R (&c)[7]) {
-        if constexpr (q == 0) return c[0];
-        if constexpr (S::D == 2) {
-            // c[1] = (T+N)/4 (x axis pops 1,3), c[2] = (T-N)/4 (y axis pops 2,4), c[3] = Pxy/4
-            if constexpr (q == 1 || q == 3) return c[1];
-            else if constexpr (q == 2 || q == 4) return c[2];
-            else if constexpr (q == 5 || q == 7) return c[3];
-            else return -c[3];
-        } else {
-            if constexpr (q <= 2) return c[1];
-            else if constexpr (q <= 4) return c[2];
-            else if constexpr (q <= 6) return c[3];
-            else if constexpr (q <= 8) return c[4];
-            else if constexpr (q <= 10) return -c[4];
-            else if constexpr (q <= 12) return c[5];
-            else if constexpr (q <= 14) return -c[5];
-            else if constexpr (q <= 16) return c[6];
-            else if constexpr (q <= 18) return -c[6];
-            else return R(0);
-        }
+    LBM_HD static V ds_of(const V (&c)[7]) {
+        static_assert(ds_index(q) >= 0);
+        return ds_sign(q) > 0 ? c[ds_index(q)] : vneg(c[ds_index(q)]);
     }
 
-    LBM_D static void apply(R (&f)[S::Q], R beta, R) {
+    LBM_HD static void apply(V (&f)[S::Q], scalar_t<V> beta_, scalar_t<V>) {
         constexpr int Q = S::Q;
         // Pass 1a: density and momentum from opposite-pair sums and differences (even moments only see
         // f_q + f_o, odd ones only f_q - f_o).
-        R rho = f[0], j[3] = {R(0), R(0), R(0)};
+        Acc<V> r, m[3];
+        r.add(f[0]);
         ForQ<Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
             if constexpr (q != 0 && q < o) {
-                constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-                const R d = f[q] - f[o];
-                rho += f[q] + f[o];
-                if constexpr (e0 == 1) j[0] += d;
-                if constexpr (e0 == -1) j[0] -= d;
-                if constexpr (e1 == 1) j[1] += d;
-                if constexpr (e1 == -1) j[1] -= d;
-                if constexpr (e2 == 1) j[2] += d;
-                if constexpr (e2 == -1) j[2] -= d;
+                r.add(vadd(f[q], f[o]));
+                const V d = vsub(f[q], f[o]);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) m[a].add_signed(S::e(q, a), d);
             }
         });
-        const R inv_rho = R(1) / rho;
-        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
-        Equilibrium<S, R> eq(rho, u);
+        const V rho = r.get();
+        const V inv_rho = vrecip(rho);
+        const V u[3] = {vmul(m[0].get(), inv_rho), vmul(m[1].get(), inv_rho), vmul(m[2].get(), inv_rho)};
+        Equilibrium<S, V> eq(rho, u);
         // Pass 1b: raw second moments of f - feq.  They are even in e, so per opposite pair only
-        // (f_q + f_o) - (feq_q + feq_o) is needed, and feq_q + feq_o = 2 w rho (base + (e.u)^2/(2 cs^4)) costs
-        // three operations.  (Subtracting the closed-form equilibrium stress from the moments of f instead
-        // is cheaper still but loses a digit: the differences are taken between O(rho/3) numbers.)
-        R P00 = 0, P11 = 0, P22 = 0, P01 = 0, P02 = 0, P12 = 0;
+        // (f_q + f_o) - (feq_q + feq_o) is needed, and feq_q + feq_o = 2 w rho (base + (e.u)^2/(2 cs^4)).
+        // (Subtracting the closed-form equilibrium stress from the moments of f instead is cheaper still but
+        // loses a digit: the differences are taken between O(rho/3) numbers.)
+        Acc<V> P00, P11, P22, P01, P02, P12;
         ForQ<Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
             if constexpr (q != 0 && q < o) {
                 constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-                const R s = (f[q] + f[o]) - eq.template pair_sum<q>();
-                if constexpr (e0 != 0) P00 += s;
-                if constexpr (e1 != 0) P11 += s;
-                if constexpr (e2 != 0) P22 += s;
-                if constexpr (e0 * e1 == 1) P01 += s;
-                if constexpr (e0 * e1 == -1) P01 -= s;
-                if constexpr (e0 * e2 == 1) P02 += s;
-                if constexpr (e0 * e2 == -1) P02 -= s;
-                if constexpr (e1 * e2 == 1) P12 += s;
-                if constexpr (e1 * e2 == -1) P12 -= s;
+                const V eu = e_dot<S, V, q>(u);
+                const V s = vfnma(vmul(vset<V>(2.0 * S::w(q)), rho), eq.template even<q>(eu), vadd(f[q], f[o]));
+                if constexpr (e0 != 0) P00.add(s);
+                if constexpr (e1 != 0) P11.add(s);
+                if constexpr (e2 != 0) P22.add(s);
+                P01.add_signed(e0 * e1, s);
+                P02.add_signed(e0 * e2, s);
+                P12.add_signed(e1 * e2, s);
             }
         });
-        R c[7];
+        V c[7];
         if constexpr (S::D == 2) {
-            const R T = P00 + P22, N = P00 - P22;        // internal axis 2 is y
-            c[0] = -T;
-            c[1] = R(0.25) * (T + N);
-            c[2] = R(0.25) * (T - N);
-            c[3] = R(0.25) * P02;
-            c[4] = c[5] = c[6] = R(0);
+            const V T = vadd(P00.get(), P22.get()), N = vsub(P00.get(), P22.get());        // internal axis 2 is y
+            c[0] = vneg(T);
+            c[1] = vmul(vset<V>(0.25), vadd(T, N));
+            c[2] = vmul(vset<V>(0.25), vsub(T, N));
+            c[3] = vmul(vset<V>(0.25), P02.get());
+            c[4] = c[5] = c[6] = vset<V>(0.0);
         } else {
-            const R T = P00 + P11 + P22, Nxz = P00 - P22, Nyz = P11 - P22;
-            c[0] = -T;
-            c[1] = (R(2) * Nxz - Nyz + T) * R(1.0 / 6.0);
-            c[2] = (R(2) * Nyz - Nxz + T) * R(1.0 / 6.0);
-            c[3] = (-Nxz - Nyz + T) * R(1.0 / 6.0);
-            c[4] = R(0.25) * P12;
-            c[5] = R(0.25) * P02;
-            c[6] = R(0.25) * P01;
+            const V T = vadd(vadd(P00.get(), P11.get()), P22.get());
+            const V Nxz = vsub(P00.get(), P22.get()), Nyz = vsub(P11.get(), P22.get());
+            const V sixth = vset<V>(1.0 / 6.0);
+            c[0] = vneg(T);
+            c[1] = vmul(vadd(vsub(vadd(Nxz, Nxz), Nyz), T), sixth);      // (2 Nxz - Nyz + T) / 6
+            c[2] = vmul(vadd(vsub(vadd(Nyz, Nyz), Nxz), T), sixth);      // (2 Nyz - Nxz + T) / 6
+            c[3] = vmul(vsub(T, vadd(Nxz, Nyz)), sixth);                 // (-Nxz - Nyz + T) / 6
+            c[4] = vmul(vset<V>(0.25), P12.get());
+            c[5] = vmul(vset<V>(0.25), P02.get());
+            c[6] = vmul(vset<V>(0.25), P01.get());
         }
-#if defined(LBM_KBC_PACKED)
-        // EXPERIMENT (not the default build): passes 2 and 3 with Blackwell's packed fp32 arithmetic
-        // (FADD2 / FMUL2 / FFMA2 on sm_100): an opposite pair (q, o) is one float2.  Per lane the operations and
-        // their rounding are those of the scalar code below, except that <dh|dh> is accumulated per lane.
-        if constexpr (sizeof(R) == 4) {
-            float sum_s = 0.f;
-            float2 sum_h2 = make_float2(0.f, 0.f);
-            const float2 pm = make_float2(1.f, -1.f);
-            {
-                const float fe = eq.template get<0>();
-                const float ds = ds_of<0>(c), dh = (f[0] - fe) - ds;
-                const float r = kbc_div(dh, fe);
-                sum_s += ds * r;
-                sum_h2.x += dh * r;
-            }
-            ForQ<Q>::run([&]<int q>() {
-                constexpr int o = S::opp(q);
-                if constexpr (q != 0 && q < o) {
-                    const float2 EQ = eq.template pair2<q>(pm);
-                    const float ds = ds_of<q>(c);
-                    const float2 F = make_float2(f[q], f[o]);
-                    const float2 DH = __fadd2_rn(__ffma2_rn(EQ, make_float2(-1.f, -1.f), F), make_float2(-ds, -ds));
-                    float2 RC;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(RC.x) : "f"(EQ.x));
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(RC.y) : "f"(EQ.y));
-                    const float2 RR = __fmul2_rn(DH, RC);
-                    sum_s += ds * (RR.x + RR.y);
-                    sum_h2 = __ffma2_rn(DH, RR, sum_h2);
-                }
-            });
-            const float sum_h = sum_h2.x + sum_h2.y;
-            const float inv_beta = 1.f / beta;
-            float gamma = inv_beta - (2.f - inv_beta) * (sum_s / sum_h);
-            if (!(gamma >= 1e-15f)) gamma = 2.f;
-            const float a = 1.f - beta * gamma, na = beta * gamma, b = beta * (gamma - 2.f);
-            f[0] = a * f[0] + (na * eq.template get<0>() + b * ds_of<0>(c));
-            ForQ<Q>::run([&]<int q>() {
-                constexpr int o = S::opp(q);
-                if constexpr (q != 0 && q < o) {
-                    const float2 EQ = eq.template pair2<q>(pm);
-                    const float bds = b * ds_of<q>(c);
-                    const float2 F = make_float2(f[q], f[o]);
-                    const float2 OUT = __ffma2_rn(make_float2(a, a), F,
-                                                  __ffma2_rn(make_float2(na, na), EQ, make_float2(bds, bds)));
-                    f[q] = OUT.x;
-                    f[o] = OUT.y;
-                }
-            });
-            return;
-        }
-#endif
         // Pass 2: entropic stabiliser gamma = 1/beta - (2 - 1/beta) <ds|dh>/<dh|dh>, weights 1/feq,
-        // with dh = (f - feq) - ds.  f itself stays in the registers.
-        R sum_s = 0, sum_h = 0;
+        // with dh = (f - feq) - ds.  f itself stays in the registers.  gamma is the ratio of two sums that are
+        // dominated by rounding noise in smooth flow (tests/test_gpu_parity.py), hence vdiv_fast for the 27 weights.
+        V sum_s, sum_h;
+        {
+            const V fe = eq.template get<0>();
+            const V ds = ds_of<0>(c), dh = vsub(vsub(f[0], fe), ds);
+            const V w = vdiv_fast(dh, fe);
+            sum_s = vmul(ds, w);
+            sum_h = vmul(dh, w);
+        }
         ForQ<Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
-            if constexpr (q == 0) {
-                const R fe = eq.template get<0>();
-                const R ds = ds_of<0>(c), dh = (f[0] - fe) - ds;
-                const R r = kbc_div(dh, fe);
-                sum_s += ds * r;
-                sum_h += dh * r;
-            } else if constexpr (q < o) {
-                R eq_q, eq_o;
+            if constexpr (q != 0 && q < o) {
+                V eq_q, eq_o;
                 eq.template pair<q>(eq_q, eq_o);
-                const R ds = ds_of<q>(c);          // even in e: same for q and its opposite
-                const R dh_q = (f[q] - eq_q) - ds, dh_o = (f[o] - eq_o) - ds;
-                const R r_q = kbc_div(dh_q, eq_q), r_o = kbc_div(dh_o, eq_o);
-                sum_s += ds * (r_q + r_o);
-                sum_h += dh_q * r_q + dh_o * r_o;
+                if constexpr (ds_index(q) >= 0) {
+                    const V ds = ds_of<q>(c);          // even in e: same for q and its opposite
+                    const V dh_q = vsub(vsub(f[q], eq_q), ds), dh_o = vsub(vsub(f[o], eq_o), ds);
+                    const V w_q = vdiv_fast(dh_q, eq_q), w_o = vdiv_fast(dh_o, eq_o);
+                    sum_s = vfma(ds, vadd(w_q, w_o), sum_s);
+                    sum_h = vfma(dh_q, w_q, vfma(dh_o, w_o, sum_h));
+                } else {                               // corner populations of D3Q27 carry no shear part
+                    const V dh_q = vsub(f[q], eq_q), dh_o = vsub(f[o], eq_o);
+                    sum_h = vfma(dh_q, vdiv_fast(dh_q, eq_q), vfma(dh_o, vdiv_fast(dh_o, eq_o), sum_h));
+                }
             }
         });
-        const R inv_beta = R(1) / beta;
-        R gamma = inv_beta - (R(2) - inv_beta) * (sum_s / sum_h);
+        const V beta = vsplat<V>(beta_);
+        const V inv_beta = vsplat<V>(scalar_t<V>(1) / beta_);
+        V gamma = vfnma(vsub(vset<V>(2.0), inv_beta), vdiv(sum_s, sum_h), inv_beta);
         // kbc_collision.py:154-157: gamma < 1e-15 -> 2 ; NaN -> 2
-        if (!(gamma >= R(1e-15))) gamma = R(2);
-        // Pass 3: f' = f - beta (2 ds + gamma dh) = a f + (1 - a) feq + b ds,  a = 1 - beta gamma, b = beta (gamma - 2)
-        const R a = R(1) - beta * gamma, na = beta * gamma, b = beta * (gamma - R(2));
+        gamma = vkeep_ge(gamma, scalar_t<V>(1e-15), scalar_t<V>(2));
+        // Pass 3: f' = f - beta (2 ds + gamma dh) = a f + na feq + b ds,  na = beta gamma, a = 1 - na,
+        // b = beta (gamma - 2); per opposite pair na feq = G +- H with G = na w rho even, H = na w rho e.u / cs^2
+        const V na = vmul(beta, gamma), a = vsub(vset<V>(1.0), na), b = vmul(beta, vsub(gamma, vset<V>(2.0)));
+        const V nrho = vmul(na, rho);
+        f[0] = vfma(a, f[0], vfma(vmul(vset<V>(S::w(0)), nrho), eq.base, vmul(b, ds_of<0>(c))));
         ForQ<Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
-            if constexpr (q == 0) {
-                f[0] = a * f[0] + (na * eq.template get<0>() + b * ds_of<0>(c));
-            } else if constexpr (q < o) {
-                R eq_q, eq_o;
-                eq.template pair<q>(eq_q, eq_o);
-                const R bds = b * ds_of<q>(c);
-                f[q] = a * f[q] + (na * eq_q + bds);
-                f[o] = a * f[o] + (na * eq_o + bds);
+            if constexpr (q != 0 && q < o) {
+                const V eu = e_dot<S, V, q>(u);
+                const V nwr = vmul(vset<V>(S::w(q)), nrho);
+                V g;
+                if constexpr (ds_index(q) >= 0) g = vfma(nwr, eq.template even<q>(eu), vmul(b, ds_of<q>(c)));
+                else g = vmul(nwr, eq.template even<q>(eu));
+                const V h = vmul(vmul(nwr, vset<V>(1.0 / kCs2)), eu);
+                f[q] = vfma(a, f[q], vadd(g, h));
+                f[o] = vfma(a, f[o], vsub(g, h));
             }
         });
     }
 };
 
-// raw second moments P_ab = sum_q g_q e_qa e_qb of (f - feq), with f <- f - feq done in place
-template <class S, class R>
-struct NonEqMoments {
-    R P00 = 0, P11 = 0, P22 = 0, P01 = 0, P02 = 0, P12 = 0;
-    LBM_D void accumulate(const R (&g)[S::Q]) {
+// raw second moments P_ab = sum_q g_q e_qa e_qb of a set of populations g
+template <class S, class V>
+struct SecondMoments {
+    V P00, P11, P22, P01, P02, P12;
+    LBM_HD explicit SecondMoments(const V (&g)[S::Q]) {
+        Acc<V> a00, a11, a22, a01, a02, a12;
         ForQ<S::Q>::run([&]<int q>() {
             constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            if constexpr (e0 != 0) P00 += g[q];
-            if constexpr (e1 != 0) P11 += g[q];
-            if constexpr (e2 != 0) P22 += g[q];
-            if constexpr (e0 * e1 == 1) P01 += g[q];
-            if constexpr (e0 * e1 == -1) P01 -= g[q];
-            if constexpr (e0 * e2 == 1) P02 += g[q];
-            if constexpr (e0 * e2 == -1) P02 -= g[q];
-            if constexpr (e1 * e2 == 1) P12 += g[q];
-            if constexpr (e1 * e2 == -1) P12 -= g[q];
+            if constexpr (e0 != 0) a00.add(g[q]);
+            if constexpr (e1 != 0) a11.add(g[q]);
+            if constexpr (e2 != 0) a22.add(g[q]);
+            a01.add_signed(e0 * e1, g[q]);
+            a02.add_signed(e0 * e2, g[q]);
+            a12.add_signed(e1 * e2, g[q]);
         });
+        P00 = a00.get(); P11 = a11.get(); P22 = a22.get();
+        P01 = a01.get(); P02 = a02.get(); P12 = a12.get();
     }
 };
 
 // Regularized LBM (Latt & Chopard 2006): f = feq + (1 - 1/tau) w_q (Q_q : Pi_neq) / (2 cs^4),
 // Q_q = e_q e_q - cs^2 I  (lettuce/ext/_collision/regularized_collision.py:17-43).  a = 1 - 1/tau.
-template <class S, class R>
-struct Collide<S, R, LBM_OP_REGULARIZED> {
-    LBM_D static void apply(R (&f)[S::Q], R a, R) {
-        R rho, j[3];
-        moments<S, R>(f, rho, j);
-        const R inv_rho = R(1) / rho;
-        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
-        Equilibrium<S, R> eq(rho, u);
-        R feq[S::Q];
+template <class S, class V>
+struct Collide<S, V, LBM_OP_REGULARIZED> {
+    LBM_HD static void apply(V (&f)[S::Q], scalar_t<V> a, scalar_t<V>) {
+        V rho, u[3];
+        density_velocity<S, V>(f, rho, u);
+        Equilibrium<S, V> eq(rho, u);
+        V feq[S::Q];
         ForQ<S::Q>::run([&]<int q>() {
             feq[q] = eq.template get<q>();
-            f[q] -= feq[q];
+            f[q] = vsub(f[q], feq[q]);
         });
-        NonEqMoments<S, R> m;
-        m.accumulate(f);
-        const R trace = (m.P00 + m.P11 + m.P22) * R(kCs2);
-        const R scale = a * R(1.0 / (2.0 * kCs2 * kCs2));
+        const SecondMoments<S, V> m(f);
+        const V trace = vmul(vadd(vadd(m.P00, m.P11), m.P22), vset<V>(kCs2));
+        const V scale = vsplat<V>(a * scalar_t<V>(1.0 / (2.0 * kCs2 * kCs2)));
         ForQ<S::Q>::run([&]<int q>() {
             constexpr int e0 = S::e(q, 0), e1 = S::e(q, 1), e2 = S::e(q, 2);
-            R qpi = -trace;
-            if constexpr (e0 != 0) qpi += m.P00;
-            if constexpr (e1 != 0) qpi += m.P11;
-            if constexpr (e2 != 0) qpi += m.P22;
-            if constexpr (e0 * e1 != 0) qpi += R(2 * e0 * e1) * m.P01;
-            if constexpr (e0 * e2 != 0) qpi += R(2 * e0 * e2) * m.P02;
-            if constexpr (e1 * e2 != 0) qpi += R(2 * e1 * e2) * m.P12;
-            f[q] = feq[q] + scale * (R(S::w(q)) * qpi);
+            V qpi = vneg(trace);
+            if constexpr (e0 != 0) qpi = vadd(qpi, m.P00);
+            if constexpr (e1 != 0) qpi = vadd(qpi, m.P11);
+            if constexpr (e2 != 0) qpi = vadd(qpi, m.P22);
+            if constexpr (e0 * e1 != 0) qpi = vfma(vset<V>(2 * e0 * e1), m.P01, qpi);
+            if constexpr (e0 * e2 != 0) qpi = vfma(vset<V>(2 * e0 * e2), m.P02, qpi);
+            if constexpr (e1 * e2 != 0) qpi = vfma(vset<V>(2 * e1 * e2), m.P12, qpi);
+            f[q] = vfma(scale, vmul(vset<V>(S::w(q)), qpi), feq[q]);
         });
     }
 };
@@ -492,31 +429,31 @@ struct Collide<S, R, LBM_OP_REGULARIZED> {
 // Smagorinsky LES on BGK (lettuce/ext/_collision/smagorinsky_collision.py:22-40, force = None): strain from the
 // non-equilibrium second moments, two fixed-point iterations for tau_eff, then BGK with tau_eff.
 // a = tau, b = smagorinsky constant.
-template <class S, class R>
-struct Collide<S, R, LBM_OP_SMAGORINSKY> {
-    LBM_D static void apply(R (&f)[S::Q], R tau, R constant) {
-        R rho, j[3];
-        moments<S, R>(f, rho, j);
-        const R inv_rho = R(1) / rho;
-        const R u[3] = {j[0] * inv_rho, j[1] * inv_rho, j[2] * inv_rho};
-        Equilibrium<S, R> eq(rho, u);
-        R fn[S::Q];
-        ForQ<S::Q>::run([&]<int q>() { fn[q] = f[q] - eq.template get<q>(); });
-        NonEqMoments<S, R> m;
-        m.accumulate(fn);
+template <class S, class V>
+struct Collide<S, V, LBM_OP_SMAGORINSKY> {
+    LBM_HD static void apply(V (&f)[S::Q], scalar_t<V> tau_, scalar_t<V> constant_) {
+        using T = scalar_t<V>;
+        V rho, u[3];
+        density_velocity<S, V>(f, rho, u);
+        Equilibrium<S, V> eq(rho, u);
+        V fn[S::Q];
+        ForQ<S::Q>::run([&]<int q>() { fn[q] = vsub(f[q], eq.template get<q>()); });
+        const SecondMoments<S, V> m(fn);
         // S_shear = Pi_neq / (2 rho cs^2); sum over ALL a,b of S_ab^2 (off-diagonals count twice)
-        const R k = R(1) / (R(2.0 * kCs2) * rho);
-        const R ss0 = k * k * (m.P00 * m.P00 + m.P11 * m.P11 + m.P22 * m.P22 +
-                               R(2) * (m.P01 * m.P01 + m.P02 * m.P02 + m.P12 * m.P12));
-        const R nu = (tau - R(0.5)) / R(3);
-        R tau_eff = tau;
+        const V k = vrecip(vmul(vset<V>(2.0 * kCs2), rho));
+        const V diag = vfma(m.P22, m.P22, vfma(m.P11, m.P11, vmul(m.P00, m.P00)));
+        const V off = vfma(m.P12, m.P12, vfma(m.P02, m.P02, vmul(m.P01, m.P01)));
+        const V ss0 = vmul(vmul(k, k), vfma(vset<V>(2.0), off, diag));
+        const V nu = vsplat<V>((tau_ - T(0.5)) / T(3));
+        const V c2 = vsplat<V>(constant_ * constant_);
+        V tau_eff = vsplat<V>(tau_);
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const R ss = ss0 / (tau_eff * tau_eff);
-            tau_eff = (nu + constant * constant * ss) * R(3) + R(0.5);
+            const V ss = vdiv(ss0, vmul(tau_eff, tau_eff));
+            tau_eff = vfma(vfma(c2, ss, nu), vset<V>(3.0), vset<V>(0.5));
         }
-        const R inv_tau = R(1) / tau_eff;
-        ForQ<S::Q>::run([&]<int q>() { f[q] = f[q] - inv_tau * fn[q]; });
+        const V inv_tau = vrecip(tau_eff);
+        ForQ<S::Q>::run([&]<int q>() { f[q] = vfnma(inv_tau, fn[q], f[q]); });
     }
 };
 
@@ -529,25 +466,24 @@ struct ForceArgs {
     R ueq_scale, src_scale;
 };
 
-template <class S, class R>
-LBM_D void collide_bgk_forced(R (&f)[S::Q], R inv_tau, const ForceArgs<R> &fa) {
-    R rho, j[3];
-    moments<S, R>(f, rho, j);
-    const R inv_rho = R(1) / rho;
-    const R k = fa.ueq_scale * inv_rho;
-    const R u[3] = {j[0] * inv_rho + k * fa.a[0], j[1] * inv_rho + k * fa.a[1], j[2] * inv_rho + k * fa.a[2]};
-    Equilibrium<S, R> eq(rho, u);
-    const R ua = u[0] * fa.a[0] + u[1] * fa.a[1] + u[2] * fa.a[2];
+template <class S, class V>
+LBM_HD void collide_bgk_forced(V (&f)[S::Q], scalar_t<V> inv_tau, const ForceArgs<scalar_t<V>> &fa) {
+    V rho, j[3];
+    moments<S, V>(f, rho, j);
+    const V inv_rho = vrecip(rho);
+    const V k = vmul(vsplat<V>(fa.ueq_scale), inv_rho);
+    const V acc[3] = {vsplat<V>(fa.a[0]), vsplat<V>(fa.a[1]), vsplat<V>(fa.a[2])};
+    const V u[3] = {vfma(k, acc[0], vmul(j[0], inv_rho)), vfma(k, acc[1], vmul(j[1], inv_rho)),
+                    vfma(k, acc[2], vmul(j[2], inv_rho))};
+    Equilibrium<S, V> eq(rho, u);
+    const V ua = vfma(u[2], acc[2], vfma(u[1], acc[1], vmul(u[0], acc[0])));
+    const V omega = vsplat<V>(inv_tau), src_scale = vsplat<V>(fa.src_scale);
     ForQ<S::Q>::run([&]<int q>() {
-        R eu = R(0), ea = R(0);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (S::e(q, c) == 1) { eu += u[c]; ea += fa.a[c]; }
-            if (S::e(q, c) == -1) { eu -= u[c]; ea -= fa.a[c]; }
-        }
+        const V eu = e_dot<S, V, q>(u), ea = e_dot<S, V, q>(acc);
         // (e - u).a / cs^2 + (e.u)(e.a) / cs^4
-        const R src = (ea - ua) * R(1.0 / kCs2) + eu * ea * R(1.0 / (kCs2 * kCs2));
-        f[q] = f[q] - inv_tau * (f[q] - eq.template get<q>()) + fa.src_scale * (R(S::w(q)) * src);
+        const V src = vfma(vmul(eu, ea), vset<V>(1.0 / (kCs2 * kCs2)), vmul(vsub(ea, ua), vset<V>(1.0 / kCs2)));
+        const V relaxed = vfma(omega, vsub(eq.template get<q>(), f[q]), f[q]);
+        f[q] = vfma(src_scale, vmul(vset<V>(S::w(q)), src), relaxed);
     });
 }
 

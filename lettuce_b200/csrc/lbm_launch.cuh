@@ -10,20 +10,62 @@ namespace lbm {
 
 extern std::atomic<int64_t> g_launch_count;  // kernels launched by this library (lbm_launch_count)
 
-// launch geometry of the bulk kernels: threadIdx.x along the contiguous axis, blocks of up to 256 threads
-// filled with rows, one grid layer per x-plane
-inline void bulk_geometry(int n0, int n1, int n2, dim3 &grid, dim3 &block) {
+constexpr int kSparseThreads = 128;          // general_nodes_kernel
+
+// launch geometry of the bulk kernel: threadIdx.x along the contiguous axis (`lanes` nodes per thread), blocks of up
+// to `threads` threads filled with rows, one grid layer per x-plane
+inline void bulk_geometry(int n0, int n1, int n2, int lanes, int threads, dim3 &grid, dim3 &block) {
+    const int zthreads = (n2 + lanes - 1) / lanes;
     int tz = 32;
-    while (tz < n2 && tz < 256) tz <<= 1;
-    int ty = 256 / tz;
+    while (tz < zthreads && tz < threads) tz <<= 1;
+    int ty = threads / tz;
     while (ty > 1 && ty / 2 >= n1) ty >>= 1;
     block = dim3(tz, ty, 1);
-    grid = dim3((n2 + tz - 1) / tz, (n1 + ty - 1) / ty, n0);
+    grid = dim3((zthreads + tz - 1) / tz, (n1 + ty - 1) / ty, n0);
 }
+
+// threads per CTA of the bulk kernel (bulk_threads<> in lbm_step.cuh: 256 for one node per thread, 128 for two)
+inline int bulk_threads_for(int lanes) { return lanes == 2 ? 128 : 256; }
+
+inline int sparse_blocks(int64_t n_general) { return (int)((n_general + kSparseThreads - 1) / kSparseThreads); }
+
+// number of (sum, max) partial pairs a step with fused reductions writes: one per bulk CTA + one per sparse CTA
+inline int reduce_slots_for(int n0, int n1, int n2, int lanes, int64_t n_general) {
+    dim3 grid, block;
+    bulk_geometry(n0, n1, n2, lanes, bulk_threads_for(lanes), grid, block);
+    return (int)(grid.x * grid.y * grid.z) + sparse_blocks(n_general);
+}
+
+struct LaunchOptions {
+    int lanes;        // 1, or 2 (fp32, even n2, PRE / POST streaming): nodes per thread of the bulk kernel
+    bool chained;     // the previous launch on the stream is a step kernel of this library: launch behind it with
+                      // programmatic stream serialization (it released its dependents, see step_kernel)
+};
+
+// true when the two-nodes-per-thread kernel exists for this request (instantiated for float, PRE and POST streaming)
+inline bool lanes2_available(int dtype, int streaming, int n2) {
+    return dtype == LBM_F32 && (streaming == LBM_PRE_STREAMING || streaming == LBM_POST_STREAMING) && n2 % 2 == 0;
+}
+
+// everything a step launch can carry besides the descriptor (lbm_api.cu: step_general)
+struct StepExtras {
+    const SlabSync *sync = nullptr;     // in-kernel slab lock step
+    double *partials = nullptr;         // fused reductions: 2 * reduce_slots doubles ...
+    int reduce_mode = kReduceNone;      // ... of the written (kReduceOutput) or the read (kReduceInput) state
+    bool chained = false;               // launch behind the previous step kernel with programmatic serialization
+};
+// lbm_step plus the optional in-kernel slab lock step (lbm_slab_step_n), fused reductions (lbm_step_moments) and
+// programmatic chaining behind the previous step (lbm_step_n); returns an lbm_status
+int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const StepExtras &x, void *stream);
+// one step with fused reductions: partials + fold -> d_result[2] (lbm_step_moments, lbm_slab_step_moments)
+int step_moments_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync,
+                         void *d_scratch, size_t scratch_bytes, double *d_result, bool chained, void *stream);
+int cuda_fail_public(int e);                       // cudaError -> lbm_status, message kept for lbm_last_cuda_error
+unsigned long long peer_timeout_cycles_public();   // LBM_B200_PEER_TIMEOUT_S in SM clocks
 
 // returns cudaError_t as int (0 = success) or a negative lbm_status; defined in lbm_step_inst.cu
 template <class S, class R, int COLL>
-int launch_step_coll(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream);
+int launch_step_coll(const StepParams<R> &p, int streaming, const LaunchOptions &opt, cudaStream_t stream);
 
 // link-wise post-streaming boundary (lbm_apply_links): gather kernel, then scatter kernel
 inline int link_blocks(int64_t n) { return (int)((n + kLinkThreads - 1) / kLinkThreads); }

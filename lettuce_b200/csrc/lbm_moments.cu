@@ -286,4 +286,59 @@ int launch_fold_sum(const double *partials, int n, double *stage, double *out, c
     return (int)cudaGetLastError();
 }
 
+// (sum, max) partial pairs of a step with fused reductions (StepParams::energy_partials: sums in [0, n), maxima in
+// [n, 2n)) -> out[0] = sum in a fixed order, out[1] = max.  Two stages above 16 partials per thread, as above.
+__global__ void fold_pair_stage_kernel(const double *__restrict__ partials, int n, double *stage) {
+    double s = 0.0, m = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        s += partials[i];
+        m = fmax(m, partials[n + i]);
+    }
+    block_fold_store<false>(s, stage);
+    __syncthreads();
+    block_fold_store<true>(m, stage + gridDim.x);
+}
+
+__global__ void fold_pair_final_kernel(const double *__restrict__ partials, int n, double *out) {
+    double s = 0.0, m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s += partials[i];
+        m = fmax(m, partials[n + i]);
+    }
+    __shared__ double sm[2][kReduceThreads / 32];
+    s = warp_fold<false>(s);
+    m = warp_fold<true>(m);
+    if ((threadIdx.x & 31) == 0) {
+        sm[0][threadIdx.x >> 5] = s;
+        sm[1][threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kReduceThreads / 32; ++w) {
+            a += sm[0][w];
+            b = fmax(b, sm[1][w]);
+        }
+        out[0] = a;
+        out[1] = b;
+    }
+}
+
+size_t fold_pair_stage_bytes() { return 2 * sizeof(double) * (size_t)kReduceBlocks; }
+
+int launch_fold_pair(const double *partials, int n, double *stage, double *out, cudaStream_t st) {
+    if (n > 16 * kReduceThreads) {
+        const int g = grid_for(n / 4);
+        fold_pair_stage_kernel<<<g, kReduceThreads, 0, st>>>(partials, n, stage);
+        ++g_launch_count;
+        const int e = (int)cudaGetLastError();
+        if (e) return e;
+        partials = stage;
+        n = g;
+    }
+    fold_pair_final_kernel<<<1, kReduceThreads, 0, st>>>(partials, n, out);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
 }  // namespace lbm

@@ -8,26 +8,20 @@
 
 namespace lbm {
 
-int cuda_fail_public(int e);
-int step_with_sync(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, const SlabSync *sync, void *stream);
-
 // One thread: publish `epoch` to both neighbours, then wait until both neighbours have published it.
 // Everything this rank's step kernel wrote (also into peer memory) is complete when this kernel starts
 // (stream order); the system-scope fences order the counter against those writes for the peers.
 __global__ void peer_signal_wait_kernel(unsigned long long *sig_lo, unsigned long long *sig_hi,
-                                        const unsigned long long *wait_slots, unsigned long long epoch) {
+                                        const unsigned long long *wait_slots, unsigned long long epoch,
+                                        unsigned long long timeout_cycles) {
     if (threadIdx.x != 0) return;
     __threadfence_system();
     *(volatile unsigned long long *)sig_lo = epoch;
     *(volatile unsigned long long *)sig_hi = epoch;
     __threadfence_system();
-    const volatile unsigned long long *w = wait_slots;
-    const long long t0 = clock64();
-    while (w[0] < epoch || w[1] < epoch) {
-        // a neighbour that never arrives (crashed rank) must not hang the GPU: ~20 s at 2 GHz, then fault
-        if (clock64() - t0 > 40000000000LL) __trap();
-        __nanosleep(200);
-    }
+    // a neighbour that never arrives (crashed rank) must not hang the GPU for ever (LBM_B200_PEER_TIMEOUT_S)
+    spin_until(wait_slots + 0, epoch, timeout_cycles);
+    spin_until(wait_slots + 1, epoch, timeout_cycles);
     __threadfence_system();
 }
 
@@ -35,14 +29,11 @@ __global__ void peer_signal_wait_kernel(unsigned long long *sig_lo, unsigned lon
 // completed on this rank's stream the neighbours have also finished the last step's boundary planes --
 // their pushes into this rank's planes have landed and their pulls from them are done -- before a
 // reporter reads, or the caller overwrites, the populations.
-__global__ void peer_wait_kernel(const unsigned long long *wait_slots, unsigned long long epoch) {
+__global__ void peer_wait_kernel(const unsigned long long *wait_slots, unsigned long long epoch,
+                                 unsigned long long timeout_cycles) {
     if (threadIdx.x != 0) return;
-    const volatile unsigned long long *w = wait_slots;
-    const long long t0 = clock64();
-    while (w[0] < epoch || w[1] < epoch) {
-        if (clock64() - t0 > 40000000000LL) __trap();
-        __nanosleep(200);
-    }
+    spin_until(wait_slots + 0, epoch, timeout_cycles);
+    spin_until(wait_slots + 1, epoch, timeout_cycles);
     __threadfence_system();
 }
 
@@ -87,8 +78,9 @@ int lbm_ipc_free(void *d_ptr) {
     return cuda_fail_public((int)cudaFree(d_ptr));
 }
 
-int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
-                    void *stream) {
+// n lock-stepped steps; when d_result is given, the LAST one carries the fused reductions
+static int slab_steps(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
+                      void *d_scratch, size_t scratch_bytes, double *d_result, void *stream) {
     if (!desc || !slab || !d_f_a || !d_f_b || n < 0) return LBM_ERR_BAD_ARGUMENT;
     if (!slab->lo_a || !slab->lo_b || !slab->hi_a || !slab->hi_b || !slab->signal_lo || !slab->signal_hi ||
         !slab->wait_slots || slab->lo_nx < 1 || slab->hi_nx < 1)
@@ -100,13 +92,14 @@ int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a
     char *lo_in = (char *)slab->lo_a, *lo_out = (char *)slab->lo_b;
     char *hi_in = (char *)slab->hi_a, *hi_out = (char *)slab->hi_b;
     unsigned long long epoch = slab->epoch;
-    // Unmasked slabs thick enough for separate lo / hi boundary planes synchronise inside the step kernel
-    // (step_sync_kernel); everything else uses the one-thread signal/wait kernel after each step.
+    const unsigned long long timeout = peer_timeout_cycles_public();
+    // Slabs thick enough for separate lo / hi boundary layers synchronise inside the step kernels; thinner ones use
+    // the one-thread signal/wait kernel after each step.
     const int w = (desc->streaming == LBM_DOUBLE_STREAMING) ? 2 : 1;
-    const bool fused = desc->n_ops == 1 && desc->lat.nx >= 2 * w;
-    unsigned long long *counters = (unsigned long long *)slab->wait_slots;   // [0],[1] peers; [2],[3] scratch
+    const bool fused = desc->lat.nx >= 2 * w;
+    unsigned long long *counters = (unsigned long long *)slab->wait_slots;   // [0],[1] peers; [2]..[4] scratch
     if (fused) {
-        const int e = (int)cudaMemsetAsync(counters + 2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream);
+        const int e = (int)cudaMemsetAsync(counters + 2, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream);
         if (e) return cuda_fail_public(e);
     }
     for (int64_t k = 0; k < n; ++k) {
@@ -117,27 +110,34 @@ int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a
         d.halo.in_hi = hi_in;
         d.halo.out_hi = hi_out;
         d.halo.in_hi_qstride = d.halo.out_hi_qstride = (int64_t)slab->hi_nx * plane;
+        const bool reduce = d_result != nullptr && k == n - 1;
+        SlabSync sync = {};
         if (fused) {
-            SlabSync sync;
             sync.sig_lo = (unsigned long long *)slab->signal_lo;
             sync.sig_hi = (unsigned long long *)slab->signal_hi;
             sync.wait = counters;
             sync.done = counters + 2;
             sync.wait_value = epoch;          // neighbours have completed the previous step
             sync.signal_value = epoch + 1;
-            sync.ctas_per_side = 0;           // filled in by the launcher
+            sync.timeout_cycles = timeout;
+            sync.ctas_per_side = 0;           // filled in by the launcher, like publish
             sync.on = 1;
-            const int rc = step_with_sync(&d, a, b, &sync, stream);
-            if (rc) return rc;
-            ++epoch;
+        }
+        int rc;
+        if (reduce) {
+            rc = step_moments_general(&d, a, b, fused ? &sync : nullptr, d_scratch, scratch_bytes, d_result, false, stream);
         } else {
-            const int rc = lbm_step(&d, a, b, stream);
-            if (rc) return rc;
-            ++epoch;
+            StepExtras x;
+            x.sync = fused ? &sync : nullptr;
+            rc = step_general(&d, a, b, x, stream);
+        }
+        if (rc) return rc;
+        ++epoch;
+        if (!fused) {
             peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)slab->signal_lo,
                                                                         (unsigned long long *)slab->signal_hi,
                                                                         (const unsigned long long *)slab->wait_slots,
-                                                                        epoch);
+                                                                        epoch, timeout);
             ++g_launch_count;
             const int e = (int)cudaGetLastError();
             if (e) return cuda_fail_public(e);
@@ -147,12 +147,24 @@ int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a
         c = hi_in; hi_in = hi_out; hi_out = c;
     }
     if (fused && n > 0) {
-        peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long *)slab->wait_slots, epoch);
+        peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long *)slab->wait_slots, epoch,
+                                                             timeout);
         ++g_launch_count;
         const int e = (int)cudaGetLastError();
         if (e) return cuda_fail_public(e);
     }
     return LBM_OK;
+}
+
+int lbm_slab_step_n(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b, int64_t n,
+                    void *stream) {
+    return slab_steps(desc, slab, d_f_a, d_f_b, n, nullptr, 0, nullptr, stream);
+}
+
+int lbm_slab_step_moments(const lbm_step_desc *desc, const lbm_slab *slab, void *d_f_a, void *d_f_b,
+                          void *d_scratch, size_t scratch_bytes, double *d_result, void *stream) {
+    if (!d_scratch || !d_result) return LBM_ERR_BAD_ARGUMENT;
+    return slab_steps(desc, slab, d_f_a, d_f_b, 1, d_scratch, scratch_bytes, d_result, stream);
 }
 
 }  // extern "C"

@@ -5,17 +5,28 @@
 // post-collision value to x + e_q (stream-after-collide); the four StreamingStrategy values are the four
 // (PULL, PUSH) combinations.
 //
-//   step_scalar_kernel   bulk kernel, one node per thread (`node_update`); in masked runs it skips every
-//                        node whose label byte is not the plain collision label
-//   general_nodes_kernel sparse kernel over the precomputed list of those skipped nodes (boundaries,
-//                        frozen slots): `general_node` restates Appendix A.2 of SURVEY.md node by node;
-//                        launched right before the bulk kernel, which overlaps it (programmatic
-//                        dependent launch); the two kernels write disjoint slots
-//   step_sync_kernel     bulk kernel for multi-GPU slabs with the in-kernel lock step (SlabSync)
-//   step_energy_kernel   bulk kernel that also reduces the kinetic energy of its output (reporter fusion)
+//   step_kernel          bulk kernel over EVERY node (`node_update`), one node per thread or two neighbours per
+//                        thread as a float2 on the packed fp32 pipe.  Run-time options: the in-kernel lock step of
+//                        multi-GPU slabs (SlabSync) and the reporters' moment reductions (sum 0.5|u|^2, max |u|^2)
+//                        of the state the step writes or reads.
+//   general_nodes_kernel masked runs: sparse kernel over the precomputed list of general nodes (boundaries, frozen
+//                        slots): `general_node` restates Appendix A.2 of SURVEY.md node by node.  The bulk kernel
+//                        treats every node as plain fluid; this kernel, launched BEHIND it with programmatic
+//                        dependent launch, gathers and collides next to it and overwrites the general nodes' slots
+//                        once the bulk grid has completed (griddepcontrol.wait).  Every slot the bulk kernel writes
+//                        wrongly (from or into a general node) has a general node as its rightful writer: nodes
+//                        that stream into a frozen slot carry the general bit, frozen slots are rewritten by their
+//                        owner.  (Measured against two variants with a label test in the bulk kernel -- label first,
+//                        and label loaded together with the populations -- this one was fastest on every masked
+//                        configuration: profiles/r2_masked_modes.md.)
 //   link_gather_kernel / link_scatter_kernel
 //                        link-wise bounce-back boundaries applied AFTER streaming (fullway / halfway / linearly
 //                        interpolated, momentum-exchange force), sparse over the list of boundary links
+//
+// Consecutive steps are chained with programmatic dependent launch (lbm_step_n): every step kernel first waits
+// for the grid in front of it to COMPLETE (griddepcontrol.wait, a no-op after an ordinary launch), then releases
+// the kernel behind it (griddepcontrol.launch_dependents), so the next kernel's CTAs are resident and past their
+// index arithmetic when the data dependency resolves; nothing reads populations before the previous step is done.
 //
 // Planes x = -1 and x = n0 resolve to the wrapped plane of the same buffer (single GPU) or to a
 // peer-mapped plane of the neighbour rank's buffer (in_plane / out_plane).
@@ -42,10 +53,13 @@ struct OpDev {
 struct SlabSync {
     unsigned long long *sig_lo, *sig_hi;   // peer-mapped: neighbour's wait slot for this rank
     const unsigned long long *wait;        // local: [0] written by lo neighbour, [1] by hi neighbour
-    unsigned long long *done;              // local: [0],[1] finished boundary CTAs per side (zeroed per call)
+    unsigned long long *done;              // local: [0],[1] finished boundary CTAs per side, [2] finished CTAs of the
+                                           // sparse kernel (zeroed per call)
     unsigned long long wait_value, signal_value;
+    unsigned long long timeout_cycles;     // a spin on a peer counter gives up (trap) after this many clocks
     unsigned int ctas_per_side;
     int on;
+    int publish;                           // 0: the sparse kernel behind this grid publishes the counters
 };
 
 // Per-population base pointers of the bulk kernel, built on the host (fill_params).  Entry [k][q] already
@@ -78,7 +92,11 @@ struct StepParams {
     R ca, cb;  // scalars of the collision entry
     ForceArgs<R> force;  // LBM_OP_BGK_FORCED only
     SlabSync sync;
-    double *energy_partials;  // step_energy_kernel: one partial sum of 0.5|u|^2 per CTA
+    // fused moment reductions (kReduceNone / kReduceOutput / kReduceInput): one (sum 0.5|u|^2, max |u|^2) pair per
+    // CTA, sums in [0, reduce_slots), maxima in [reduce_slots, 2 reduce_slots); the sparse kernel's CTAs use the
+    // slots from reduce_sparse_offset on
+    double *energy_partials;
+    int reduce_mode, reduce_slots, reduce_sparse_offset, _pad_reduce;
     AddrTables<R> tbl;
     OpDev<R> ops[LBM_MAX_OPS];
 };
@@ -118,12 +136,14 @@ LBM_D const uint8_t *label_plane(const StepParams<R> &p, int x) {
 
 LBM_D int wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
 
-// the collision entry of the transformer list applied to one node
-template <class S, class R, int COLL>
-LBM_D void collide_node(const StepParams<R> &p, R (&f)[S::Q]) {
-    if constexpr (COLL == LBM_OP_BGK_FORCED) collide_bgk_forced<S, R>(f, p.ca, p.force);
-    else Collide<S, R, COLL>::apply(f, p.ca, p.cb);
+// the collision entry of the transformer list applied to the node (V = R) or the two nodes (V = float2) held in f
+template <class S, class V, int COLL>
+LBM_D void collide_lanes(const StepParams<scalar_t<V>> &p, V (&f)[S::Q]) {
+    if constexpr (COLL == LBM_OP_BGK_FORCED) collide_bgk_forced<S, V>(f, p.ca, p.force);
+    else Collide<S, V, COLL>::apply(f, p.ca, p.cb);
 }
+template <class S, class R, int COLL>
+LBM_D void collide_node(const StepParams<R> &p, R (&f)[S::Q]) { collide_lanes<S, R, COLL>(p, f); }
 
 // ---------------------------------------------------------------------------
 // general path pieces
@@ -264,18 +284,11 @@ __device__ void node_pipeline(const StepParams<R> &p, int x, int y, int z, int l
     }
 }
 
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool AFTER>
-__device__ void general_node(const StepParams<R> &p, int x, int y, int z, int label) {
+// scatter of a general node's populations with the destination-side frozen-slot rule (_simulation.py:252-255):
+// slot (q, dst) takes the streamed value unless it is frozen, in which case the node's own value stays.
+template <class S, class R, bool PUSH>
+__device__ void scatter_general(const StepParams<R> &p, int x, int y, int z, const R (&f)[S::Q]) {
     constexpr int Q = S::Q;
-    R f[Q];
-    node_pipeline<S, R, COLL, PULL>(p, x, y, z, label, f);
-    // kMaskedOverwrite: this kernel was launched BEHIND the bulk kernel, which updated every node as if it were
-    // plain fluid; wait for it to finish before overwriting the slots that belong to the general nodes
-    if constexpr (AFTER) asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    // scatter with the destination-side frozen-slot rule (_simulation.py:252-255):
-    // slot (q, dst) takes the streamed value unless it is frozen, in which case the
-    // node's own value stays.
     const int64_t row = (int64_t)y * p.n2 + z;
     if (!PUSH) {
         const auto pl = out_plane(p, x);
@@ -310,192 +323,214 @@ __device__ void general_node(const StepParams<R> &p, int x, int y, int z, int la
 }
 
 // ---------------------------------------------------------------------------
-// scalar kernel: one node per thread, threadIdx.x along the contiguous axis.
+// bulk kernel: LANES nodes per thread (1, or 2 neighbours along the contiguous axis as one float2 on the packed
+// fp32 pipe), threadIdx.x along the contiguous axis.
 // ---------------------------------------------------------------------------
-template <class S, class R, int COLL>
+
+// moment reductions fused into the step (StepParams::reduce_mode): of the state the step WRITES (steps that do not
+// push: the node's output is still in registers, and collisions conserve rho and j) or of the state it READS (steps
+// that only push: the input node is the previous step's output node)
+enum : int { kReduceNone = 0, kReduceOutput = 1, kReduceInput = 2 };
+
+template <class R, int LANES>
+struct LaneVec {
+    using type = R;
+};
+template <>
+struct LaneVec<float, 2> {
+    using type = float2;
+};
+
+template <class S, class R, int COLL, int LANES>
+constexpr int bulk_threads() {
+    return LANES == 2 ? 128 : 256;
+}
+template <class S, class R, int COLL, int LANES>
 constexpr int min_blocks_per_sm() {
-    // fp32 KBC on D3Q27: cap at 85 registers (3 CTAs of 256 threads); the push variant otherwise
-    // hoists 27 store addresses into 108 registers.
-#ifndef LBM_KBC_MIN_BLOCKS
-#define LBM_KBC_MIN_BLOCKS 3
-#endif
-    return (sizeof(R) == 4 && COLL == LBM_OP_KBC && S::Q == 27) ? LBM_KBC_MIN_BLOCKS : 0;  // 0 = no constraint
+    // fp32 KBC on D3Q27, one node per thread: cap at 85 registers (3 CTAs of 256 threads); the push variant
+    // otherwise hoists 27 store addresses into 108 registers.  Two nodes per thread: 128 registers, 4 CTAs of 128.
+    if (sizeof(R) == 4 && COLL == LBM_OP_KBC && S::Q == 27) return LANES == 2 ? 4 : 3;
+    return 0;  // no constraint
 }
 
-// one node: gather, collide, scatter.  An address is a block-uniform table entry (AddrTables, read from the
-// constant bank) plus one 32-bit node index per thread, chosen from nine precomputed (row, column)
-// combinations: one IMAD.WIDE per access.
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool ENERGY = false>
-LBM_D R node_update(const StepParams<R> &p, int x, int y, int z) {
-    constexpr int Q = S::Q;
-    // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
-    const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
-    const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
-    const int xoff = x * (p.n1 * p.n2);
-    const int rowm = xoff + ym * p.n2, row0 = xoff + y * p.n2, rowp = xoff + yp * p.n2;
-    const int k = (x == 0 ? 1 : 0) | (x == p.n0 - 1 ? 2 : 0);
-
-    R f[Q];
-    ForQ<Q>::run([&]<int q>() {
-        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
-        const int rs = (!PULL || e1 == 0) ? row0 : (e1 == 1 ? rowm : rowp);
-        const int zs = (!PULL || e2 == 0) ? z : (e2 == 1 ? zm : zp);
-        f[q] = __ldg(p.tbl.ld[k][q] + (rs + zs));
-    });
-
-    collide_node<S, R, COLL>(p, f);
-
-    ForQ<Q>::run([&]<int q>() {
-        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
-        const int rd = (!PUSH || e1 == 0) ? row0 : (e1 == 1 ? rowp : rowm);
-        const int zd = (!PUSH || e2 == 0) ? z : (e2 == 1 ? zp : zm);
-        p.tbl.st[k][q][rd + zd] = f[q];
-    });
-    if constexpr (ENERGY) {
-        // without a push the node's output IS f: its kinetic energy 0.5 |j|^2 / rho^2 (Flow.incompressible_energy,
-        // lettuce/_flow.py:200-204) comes from the registers, no second pass over the populations
-        static_assert(!PUSH, "the output state of a pushing step is assembled from several nodes");
-        R rho, j[3];
-        moments<S, R>(f, rho, j);
-        const R inv = R(1) / rho;
-        const R u0 = j[0] * inv, u1 = j[1] * inv, u2 = j[2] * inv;
-        return R(0.5) * (u0 * u0 + u1 * u1 + u2 * u2);
-    } else {
-        return R(0);
-    }
-}
-
-// How the bulk kernel of a masked run treats the nodes that belong to general_nodes_kernel (template parameter
-// MODE of step_scalar_kernel; selected at run time, lbm_step_desc::variant / LBM_B200_MASKED_MODE):
-//   kUnmasked         no masks at all
-//   kMaskedLabelFirst LDG(label) -> EXIT? -> LDG x q: two dependent memory round trips per node
-//   kMaskedSpeculative label byte loaded TOGETHER with the populations, exit after the loads have landed: one
-//                     round trip; the loads of the few general nodes are wasted
-//   kMaskedOverwrite  no label test: the bulk kernel is the unmasked kernel and treats every node as plain fluid;
-//                     general_nodes_kernel, launched BEHIND it with programmatic dependent launch, gathers and
-//                     collides concurrently and overwrites the general nodes' slots after griddepcontrol.wait.
-//                     Every slot the bulk kernel writes wrongly (from or into a general node) has a general node
-//                     as its rightful writer: nodes that stream into a frozen slot carry the general bit, frozen
-//                     slots are rewritten by their owner.
-enum : int { kUnmasked = 0, kMaskedLabelFirst = 1, kMaskedSpeculative = 2, kMaskedOverwrite = 3 };
-
-// node_update for kMaskedSpeculative (ptxas keeps the order LDG x q, LDG.U8, EXIT?, STG x q: checked with cuobjdump).
-template <class S, class R, int COLL, bool PULL, bool PUSH>
-LBM_D void node_update_speculative(const StepParams<R> &p, int x, int y, int z) {
-    constexpr int Q = S::Q;
-    const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
-    const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + 1 == p.n2) ? 0 : z + 1;
-    const int xoff = x * (p.n1 * p.n2);
-    const int rowm = xoff + ym * p.n2, row0 = xoff + y * p.n2, rowp = xoff + yp * p.n2;
-    const int k = (x == 0 ? 1 : 0) | (x == p.n0 - 1 ? 2 : 0);
-    const uint8_t lab = __ldg(p.labels + (row0 + z));
-    R f[Q];
-    ForQ<Q>::run([&]<int q>() {
-        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
-        const int rs = (!PULL || e1 == 0) ? row0 : (e1 == 1 ? rowm : rowp);
-        const int zs = (!PULL || e2 == 0) ? z : (e2 == 1 ? zm : zp);
-        f[q] = __ldg(p.tbl.ld[k][q] + (rs + zs));
-    });
-    // ptxas sinks loads below an exit on whose path they are unused, which would restore the two round trips.  The
-    // exit therefore also tests a condition on the loaded bits that never holds for real populations (all nine /
-    // nineteen / twenty-seven values having every bit set, a NaN pattern): the loads must land first.
-    unsigned long long bits = ~0ull;
-    ForQ<Q>::run([&]<int q>() {
-        if constexpr (sizeof(R) == 4) bits &= (unsigned long long)__float_as_uint(f[q]) | 0xffffffff00000000ull;
-        else bits &= (unsigned long long)__double_as_longlong(f[q]);
-    });
-    if (lab != p.collision_index || bits == ~0ull) return;
-    collide_node<S, R, COLL>(p, f);
-    ForQ<Q>::run([&]<int q>() {
-        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
-        const int rd = (!PUSH || e1 == 0) ? row0 : (e1 == 1 ? rowp : rowm);
-        const int zd = (!PUSH || e2 == 0) ? z : (e2 == 1 ? zp : zm);
-        p.tbl.st[k][q][rd + zd] = f[q];
-    });
-}
-
-template <class S, class R, int COLL, bool PULL, bool PUSH, int MODE>
-__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
-    step_scalar_kernel(const __grid_constant__ StepParams<R> p) {
-    // kMaskedOverwrite: release general_nodes_kernel (launched behind this grid) right away
-    if constexpr (MODE == kMaskedOverwrite) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
-    if (z < p.n2 && y < p.n1) {
-        // Masked runs: boundary nodes, nodes with a frozen slot and nodes streaming into a frozen slot carry
-        // bit 7 and belong to general_nodes_kernel; every output slot ends up with exactly one final writer.
-        if constexpr (MODE == kMaskedLabelFirst) {
-            if (p.labels[(int64_t)x * p.n1 * p.n2 + (int64_t)y * p.n2 + z] == p.collision_index)
-                node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
-        } else if constexpr (MODE == kMaskedSpeculative) {
-            node_update_speculative<S, R, COLL, PULL, PUSH>(p, x, y, z);
-        } else {
-            node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+// 0.5 |u|^2 of the node(s) in f, per lane, accumulated into (sum, max of |u|^2)
+template <class S, class V>
+LBM_D void accumulate_kinetic(const V (&f)[S::Q], const bool (&take)[2], double &sum, double &mx) {
+    V rho, u[3];
+    density_velocity<S, V>(f, rho, u);
+    const V uu = vfma(u[2], u[2], vfma(u[1], u[1], vmul(u[0], u[0])));
+#pragma unroll
+    for (int l = 0; l < VecTraits<V>::lanes; ++l) {
+        if (take[l]) {
+            const double v = (double)vlane(uu, l);
+            sum += 0.5 * v;
+            mx = fmax(mx, v);
         }
     }
-    // general_nodes_kernel runs IN FRONT of this grid in these two modes and released it with
-    // griddepcontrol.launch_dependents; a dependent grid has to execute griddepcontrol.wait so that the next
-    // launch on the stream is ordered behind BOTH kernels (free when the sparse kernel has long finished)
-    if constexpr (MODE == kMaskedLabelFirst || MODE == kMaskedSpeculative)
-        asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-// Bulk kernel that also reduces the kinetic energy of the state it writes (unmasked, non-pushing steps): the
-// IncompressibleKineticEnergy reporter (observable_reporter.py:34-42) fused into the step.  Warp shuffles, one
-// shared-memory exchange, one partial per CTA; a fixed-order fold kernel follows (deterministic, no atomics).
-template <class S, class R, int COLL, bool PULL>
-__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
-    step_energy_kernel(const __grid_constant__ StepParams<R> p) {
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
-    double e = 0.0;
-    if (z < p.n2 && y < p.n1) e = (double)node_update<S, R, COLL, PULL, false, true>(p, x, y, z);
+// LANES nodes (x, y, z .. z+LANES-1): gather, collide, scatter.  An address is a block-uniform table entry
+// (AddrTables, read from the constant bank) plus one 32-bit node index per thread, chosen from nine precomputed
+// (row, column) combinations: one IMAD.WIDE per access.  With two lanes, populations that do not move along the
+// contiguous axis are loaded / stored as one aligned 64-bit access; the others as two 32-bit ones.
+//
+// Masked runs update EVERY node here and general_nodes_kernel overwrites its nodes afterwards.  `single_writer`
+// (block-uniform; the cut planes of a multi-GPU slab) makes the general nodes skip their stores instead: a wrong store
+// into the NEIGHBOUR's memory could land after the neighbour's sparse kernel has written the right value there
+// (nothing orders the two ranks' kernels within a step), so across a cut every slot keeps exactly one writer.
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES>
+LBM_D void node_update(const StepParams<R> &p, int x, int y, int z, bool single_writer, double &e_sum, double &e_max) {
+    constexpr int Q = S::Q;
+    using V = typename LaneVec<R, LANES>::type;
+    // neighbour rows / columns with periodic wrap (torch.roll, _simulation.py:241-243)
+    const int ym = (y == 0 ? p.n1 : y) - 1, yp = (y + 1 == p.n1) ? 0 : y + 1;
+    const int zm = (z == 0 ? p.n2 : z) - 1, zp = (z + LANES == p.n2) ? 0 : z + LANES;   // left of lane 0, right of the last
+    const int xoff = x * (p.n1 * p.n2);
+    const int rowm = xoff + ym * p.n2, row0 = xoff + y * p.n2, rowp = xoff + yp * p.n2;
+    const int k = (x == 0 ? 1 : 0) | (x == p.n0 - 1 ? 2 : 0);
+
+    // the labels are needed to keep the general nodes out of a fused reduction (the sparse kernel contributes
+    // those) and for single_writer
+    bool mine[2] = {true, true};
+    if ((p.reduce_mode != kReduceNone || single_writer) && p.labels != nullptr) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-    __shared__ double warp_sum[8];
-    const int t = threadIdx.y * blockDim.x + threadIdx.x, nwarps = (blockDim.x * blockDim.y + 31) >> 5;
-    if ((t & 31) == 0) warp_sum[t >> 5] = e;
-    __syncthreads();
-    if (t == 0) {
-        double s = 0.0;
-        for (int w = 0; w < nwarps; ++w) s += warp_sum[w];
-        p.energy_partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+        for (int l = 0; l < LANES; ++l) mine[l] = !(__ldg(p.labels + (row0 + z + l)) & kLabelGeneral);
+    }
+
+    V f[Q];
+    ForQ<Q>::run([&]<int q>() {
+        constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+        const int rs = (!PULL || e1 == 0) ? row0 : (e1 == 1 ? rowm : rowp);
+        const R *src = p.tbl.ld[k][q] + rs;
+        if constexpr (LANES == 1) {
+            const int zs = (!PULL || e2 == 0) ? z : (e2 == 1 ? zm : zp);
+            f[q] = __ldg(src + zs);
+        } else {
+            if constexpr (!PULL || e2 == 0) f[q] = __ldg(reinterpret_cast<const float2 *>(src + z));
+            else if constexpr (e2 == 1) f[q] = make_float2(__ldg(src + zm), __ldg(src + z));          // from z-1, z
+            else f[q] = make_float2(__ldg(src + (z + 1)), __ldg(src + zp));                          // from z+1, z+2
+        }
+    });
+    if (p.reduce_mode == kReduceInput) accumulate_kinetic<S, V>(f, mine, e_sum, e_max);
+
+    collide_lanes<S, V, COLL>(p, f);
+
+    if (single_writer && !(mine[0] && mine[LANES - 1])) {
+        // a general node on a cut plane: only the other lane's node (if it is plain fluid) stores, lane by lane
+#pragma unroll
+        for (int l = 0; l < LANES; ++l) {
+            if (!mine[l]) continue;
+            const int zl = z + l;
+            const int zlp = zl + 1 == p.n2 ? 0 : zl + 1, zlm = (zl == 0 ? p.n2 : zl) - 1;
+            ForQ<Q>::run([&]<int q>() {
+                constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+                const int rd = (!PUSH || e1 == 0) ? row0 : (e1 == 1 ? rowp : rowm);
+                const int zd = (!PUSH || e2 == 0) ? zl : (e2 == 1 ? zlp : zlm);
+                p.tbl.st[k][q][rd + zd] = vlane(f[q], l);
+            });
+        }
+    } else {
+        ForQ<Q>::run([&]<int q>() {
+            constexpr int e1 = S::e(q, 1), e2 = S::e(q, 2);
+            const int rd = (!PUSH || e1 == 0) ? row0 : (e1 == 1 ? rowp : rowm);
+            R *dst = p.tbl.st[k][q] + rd;
+            if constexpr (LANES == 1) {
+                const int zd = (!PUSH || e2 == 0) ? z : (e2 == 1 ? zp : zm);
+                dst[zd] = f[q];
+            } else {
+                if constexpr (!PUSH || e2 == 0) {
+                    *reinterpret_cast<float2 *>(dst + z) = f[q];
+                } else if constexpr (e2 == 1) {        // to z+1, z+2
+                    dst[z + 1] = f[q].x;
+                    dst[zp] = f[q].y;
+                } else {                               // to z-1, z
+                    dst[zm] = f[q].x;
+                    dst[z] = f[q].y;
+                }
+            }
+        });
+    }
+    if (p.reduce_mode == kReduceOutput) accumulate_kinetic<S, V>(f, mine, e_sum, e_max);
+}
+
+// Slab lock step (multi-GPU): W boundary planes per side take part (2 when the step both pulls and pushes, because
+// plane 1 then reads slots the neighbour pushed into plane 0 and pushes into plane 0 itself); their CTAs are
+// scheduled FIRST so that the progress counters go out early and the neighbour's next step never stalls.
+template <bool PULL, bool PUSH>
+LBM_D int sync_plane(const SlabSync &s, int zb, int n0) {
+    constexpr int W = (PULL && PUSH) ? 2 : 1;
+    return zb < W ? zb : (zb < 2 * W ? n0 - 2 * W + zb : zb - W);   // host guarantees n0 >= 2 W
+}
+
+LBM_D void spin_until(const volatile unsigned long long *w, unsigned long long value, unsigned long long limit) {
+    const long long t0 = clock64();
+    while (*w < value) {
+        // a neighbour that never arrives must not hang the GPU for ever: after `limit` cycles the kernel gives up
+        // with a trap (sticky error on this rank, reported by the next CUDA call); LBM_B200_PEER_TIMEOUT_S
+        if ((unsigned long long)(clock64() - t0) > limit) __trap();
+        __nanosleep(100);
     }
 }
 
-// Slab variant of the bulk kernel (unmasked, multi-GPU): identical arithmetic, plus the in-kernel lock
-// step.  W boundary planes per side take part (2 when the step both pulls and pushes, because plane 1
-// then reads slots the neighbour pushed into plane 0 and pushes into plane 0 itself); their CTAs are
-// scheduled FIRST so that the progress counters go out early and the neighbour's next step never stalls.
-template <class S, class R, int COLL, bool PULL, bool PUSH>
-__global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
-    step_sync_kernel(const __grid_constant__ StepParams<R> p) {
+// one partial (sum, max) per CTA: warp shuffles, one shared-memory exchange; deterministic (no atomics)
+LBM_D void store_cta_partials(double e_sum, double e_max, double *partials, int slot, int n_slots) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
+        e_max = fmax(e_max, __shfl_down_sync(0xffffffffu, e_max, o));
+    }
+    __shared__ double warp_part[2][8];
+    const int t = threadIdx.y * blockDim.x + threadIdx.x, nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+    if ((t & 31) == 0) {
+        warp_part[0][t >> 5] = e_sum;
+        warp_part[1][t >> 5] = e_max;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0, m = 0.0;
+        for (int w = 0; w < nwarps; ++w) {
+            s += warp_part[0][w];
+            m = fmax(m, warp_part[1][w]);
+        }
+        partials[slot] = s;
+        partials[n_slots + slot] = m;
+    }
+}
+
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES>
+__global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_blocks_per_sm<S, R, COLL, LANES>()))
+    step_kernel(const __grid_constant__ StepParams<R> p) {
+    // (no-op unless THIS grid was launched programmatically behind the previous step: then the grid in front has to
+    // be complete, and its writes visible, before anything below reads populations)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // The kernel behind this one on the stream may have been launched with programmatic stream serialization
+    // (masked runs: general_nodes_kernel; chained steps of lbm_step_n: the next step): it may become resident once
+    // every CTA of this grid has got here, i.e. once the previous step is known to be complete.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool sync = p.sync.on != 0;
+    const int x = sync ? sync_plane<PULL, PUSH>(p.sync, blockIdx.z, p.n0) : (int)blockIdx.z;
     constexpr int W = (PULL && PUSH) ? 2 : 1;
-    const int zb = blockIdx.z;
-    const int x = zb < W ? zb : (zb < 2 * W ? p.n0 - 2 * W + zb : zb - W);   // host guarantees n0 >= 2 W
-    const bool lo = x < W, hi = x >= p.n0 - W;
+    const bool lo = sync && x < W, hi = sync && x >= p.n0 - W;
     const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
     if (lo || hi) {
+        // boundary-plane CTAs wait for the neighbour's progress counter before they touch peer memory
         if (leader) {
-            const volatile unsigned long long *w = p.sync.wait + (lo ? 0 : 1);
-            const long long t0 = clock64();
-            while (*w < p.sync.wait_value) {
-                if (clock64() - t0 > 40000000000LL) __trap();   // a dead neighbour must not hang the GPU
-                __nanosleep(100);
-            }
+            spin_until(p.sync.wait + (lo ? 0 : 1), p.sync.wait_value, p.sync.timeout_cycles);
             __threadfence_system();
         }
         __syncthreads();
     }
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (z < p.n2 && y < p.n1) node_update<S, R, COLL, PULL, PUSH>(p, x, y, z);
+    double e_sum = 0.0, e_max = 0.0;
+    if (z < p.n2 && y < p.n1)
+        node_update<S, R, COLL, PULL, PUSH, LANES>(p, x, y, z, (lo || hi) && p.labels != nullptr, e_sum, e_max);
     if (lo || hi) {
+        // ... and the last of them to finish publishes this rank's counter (unless the sparse kernel of a masked
+        // step still has to touch the boundary planes: then IT publishes, general_nodes_kernel)
         __threadfence_system();   // this thread's loads from / stores to the neighbour are performed
         __syncthreads();
-        if (leader) {
+        if (leader && p.sync.publish) {
             const unsigned long long old = atomicAdd(p.sync.done + (lo ? 0 : 1), 1ULL);
             if ((old + 1) % p.sync.ctas_per_side == 0) {
                 __threadfence_system();
@@ -503,28 +538,72 @@ __global__ void __launch_bounds__(256, min_blocks_per_sm<S, R, COLL>())
             }
         }
     }
+    if (p.reduce_mode != kReduceNone)
+        store_cta_partials(e_sum, e_max, p.energy_partials,
+                           (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, p.reduce_slots);
 }
 
 // ---------------------------------------------------------------------------
 // sparse kernel: one thread per node of the precomputed list of general nodes
-// (boundaries, frozen slots).  Runs next to step_scalar_kernel<MASKED> on the same
-// stream; the two kernels write disjoint slots of the output buffer.
+// (boundaries, frozen slots), launched behind step_kernel on the same stream.
 // ---------------------------------------------------------------------------
-template <class S, class R, int COLL, bool PULL, bool PUSH, bool AFTER>
+template <class S, class R, int COLL, bool PULL, bool PUSH>
 __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constant__ StepParams<R> p) {
-    // launched in front of the bulk kernel: let it (programmatic stream serialization) start right away
-    if constexpr (!AFTER) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n_general) {
-        // every thread of a dependent grid passes the wait, so that grid completion implies the bulk grid's
-        if constexpr (AFTER) asm volatile("griddepcontrol.wait;" ::: "memory");
-        return;
+    // Launched programmatically behind the bulk kernel, which released this grid only after the previous step
+    // had completed: the input populations are final.  The next step's bulk kernel may become resident right away
+    // (it waits for THIS grid's completion before it reads anything).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    constexpr int Q = S::Q;
+    if (p.sync.on) {
+        // slabs: the gather below may read the neighbours' planes before the bulk kernel's boundary CTAs have seen
+        // the neighbours' progress counters
+        if (threadIdx.x == 0) {
+            spin_until(p.sync.wait + 0, p.sync.wait_value, p.sync.timeout_cycles);
+            spin_until(p.sync.wait + 1, p.sync.wait_value, p.sync.timeout_cycles);
+            __threadfence_system();
+        }
+        __syncthreads();
     }
-    const int n = p.general_nodes[i];
-    const int z = n % p.n2;
-    const int y = (n / p.n2) % p.n1;
-    const int x = n / (p.n1 * p.n2);
-    general_node<S, R, COLL, PULL, PUSH, AFTER>(p, x, y, z, p.labels[n] & 0x7f);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < p.n_general;
+    int x = 0, y = 0, z = 0;
+    R f[Q];
+    double e_sum = 0.0, e_max = 0.0;
+    const bool take[2] = {true, false};
+    if (active) {
+        const int n = p.general_nodes[i];
+        z = n % p.n2;
+        y = (n / p.n2) % p.n1;
+        x = n / (p.n1 * p.n2);
+        if (p.reduce_mode == kReduceInput) {        // the node as the previous step left it (steps that only push)
+            gather_node<S, R, false>(p, x, y, z, f);
+            accumulate_kinetic<S, R>(f, take, e_sum, e_max);
+        }
+        node_pipeline<S, R, COLL, PULL>(p, x, y, z, p.labels[n] & 0x7f, f);
+    }
+    // the bulk kernel updated every node as if it were plain fluid: wait for it to finish before overwriting the
+    // slots that belong to the general nodes (every thread passes the wait, so that completion of this grid
+    // implies completion of the bulk grid)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (active) {
+        scatter_general<S, R, PUSH>(p, x, y, z, f);
+        if (p.reduce_mode == kReduceOutput) accumulate_kinetic<S, R>(f, take, e_sum, e_max);
+    }
+    if (p.sync.on) {
+        // the last CTA to finish publishes this rank's progress to both neighbours (the bulk kernel did not)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long old = atomicAdd(p.sync.done + 2, 1ULL);
+            if ((old + 1) % gridDim.x == 0) {
+                __threadfence_system();
+                *(volatile unsigned long long *)p.sync.sig_lo = p.sync.signal_value;
+                *(volatile unsigned long long *)p.sync.sig_hi = p.sync.signal_value;
+            }
+        }
+    }
+    if (p.reduce_mode != kReduceNone)
+        store_cta_partials(e_sum, e_max, p.energy_partials, p.reduce_sparse_offset + blockIdx.x, p.reduce_slots);
 }
 
 // ---------------------------------------------------------------------------

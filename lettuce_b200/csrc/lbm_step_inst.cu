@@ -16,9 +16,6 @@ namespace lbm {
 
 namespace {
 
-// One node per thread.  (A 2- and 4-nodes-per-thread variant for D2Q9 was measured on B200 -- C4, 4096x1024 fp32,
-// PRE: 65.8 GLUPS with one node per thread, 64.6 with two, 55.5 with four -- and removed: occupancy pays, more
-// loads in flight per thread do not.)
 // launches `kernel` behind the previous launch on `stream` with programmatic stream serialization: it may start
 // as soon as the previous grid has executed griddepcontrol.launch_dependents (or exited) in every CTA
 template <class R>
@@ -39,85 +36,60 @@ int launch_dependent(void (*kernel)(const StepParams<R>), dim3 grid, dim3 block,
     return e;
 }
 
-template <class S, class R, int COLL, bool PULL, bool PUSH, int MODE>
-int launch_scalar(const StepParams<R> &p, cudaStream_t stream) {
-    constexpr bool MASKED = MODE != kUnmasked;
+// One time step: the bulk kernel over every node and, in masked runs, the sparse kernel behind it (released by the
+// bulk kernel once the previous step is known to be complete; it gathers and collides next to the bulk kernel and
+// stores after the bulk grid has completed).  One node per thread measured fastest for D2Q9 in round 1 when the
+// two nodes were computed with scalar arithmetic (4096x1024 fp32: 65.8 GLUPS vs 64.6); LANES = 2 here means the
+// packed float2 arithmetic of lbm_vec.cuh, which halves the fp32 issue slots.
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES>
+int launch_lanes(const StepParams<R> &p_in, const LaunchOptions &opt, cudaStream_t stream) {
+    StepParams<R> p = p_in;
     dim3 grid, block;
-    bulk_geometry(p.n0, p.n1, p.n2, grid, block);
-    void (*bulk)(const StepParams<R>) = step_scalar_kernel<S, R, COLL, PULL, PUSH, MODE>;
-    if (p.energy_partials) {       // lbm_step_energy: step + kinetic energy of the output in one kernel
-        if constexpr (!MASKED && !PUSH) {
-            if (p.sync.on) return LBM_ERR_UNSUPPORTED;
-            step_energy_kernel<S, R, COLL, PULL><<<grid, block, 0, stream>>>(p);
-            ++g_launch_count;
-            return (int)cudaGetLastError();
-        } else {
-            return LBM_ERR_UNSUPPORTED;
-        }
+    bulk_geometry(p.n0, p.n1, p.n2, LANES, bulk_threads<S, R, COLL, LANES>(), grid, block);
+    const bool sparse = p.labels != nullptr && p.n_general > 0;
+    const int bulk_ctas = (int)(grid.x * grid.y * grid.z);
+    if (p.reduce_mode != kReduceNone) {
+        if (PULL && PUSH) return LBM_ERR_UNSUPPORTED;      // the output node is assembled from several source nodes
+        p.reduce_sparse_offset = bulk_ctas;
+        p.reduce_slots = bulk_ctas + (sparse ? sparse_blocks(p.n_general) : 0);
     }
-    if constexpr (!MASKED) {
-        if (p.sync.on) {       // multi-GPU slab with in-kernel lock step (lbm_slab_step_n)
-            StepParams<R> ps = p;
-            ps.sync.ctas_per_side = grid.x * grid.y * ((PULL && PUSH) ? 2 : 1);
-            step_sync_kernel<S, R, COLL, PULL, PUSH><<<grid, block, 0, stream>>>(ps);
-            ++g_launch_count;
-            return (int)cudaGetLastError();
-        }
+    if (p.sync.on) {
+        p.sync.ctas_per_side = grid.x * grid.y * ((PULL && PUSH) ? 2 : 1);
+        p.sync.publish = sparse ? 0 : 1;
     }
-    if (p.sync.on) return LBM_ERR_UNSUPPORTED;
-    if (MASKED && p.n_general > 0) {
-        const dim3 sgrid((p.n_general + 127) / 128), sblock(128);
-        if constexpr (MODE == kMaskedOverwrite) {
-            // bulk kernel over every node first; the sparse kernel is released by the bulk kernel's first
-            // instruction, gathers and collides next to it and stores once the bulk grid has completed
-            bulk<<<grid, block, 0, stream>>>(p);
-            ++g_launch_count;
-            const int e = (int)cudaGetLastError();
-            if (e) return e;
-            return launch_dependent<R>(general_nodes_kernel<S, R, COLL, PULL, PUSH, true>, sgrid, sblock, p, stream);
-        } else {
-            // The sparse kernel is a chain of dependent loads on a handful of CTAs (~10 us at 15 k nodes); it
-            // and the bulk kernel write disjoint slots, so the bulk kernel is launched with programmatic
-            // dependent launch right behind it and overlaps it completely (the sparse kernel releases its
-            // dependents in its first instruction; the bulk kernel waits for it in its LAST instruction).
-            general_nodes_kernel<S, R, COLL, PULL, PUSH, false><<<sgrid, sblock, 0, stream>>>(p);
-            ++g_launch_count;
-            const int e = (int)cudaGetLastError();
-            if (e) return e;
-            return launch_dependent<R>(bulk, grid, block, p, stream);
-        }
+    void (*bulk)(const StepParams<R>) = step_kernel<S, R, COLL, PULL, PUSH, LANES>;
+    int e;
+    if (opt.chained) {
+        e = launch_dependent<R>(bulk, grid, block, p, stream);
+    } else {
+        bulk<<<grid, block, 0, stream>>>(p);
+        ++g_launch_count;
+        e = (int)cudaGetLastError();
     }
-    bulk<<<grid, block, 0, stream>>>(p);
-    ++g_launch_count;
-    return (int)cudaGetLastError();
+    if (e || !sparse) return e;
+    return launch_dependent<R>(general_nodes_kernel<S, R, COLL, PULL, PUSH>, dim3(sparse_blocks(p.n_general)),
+                               dim3(kSparseThreads), p, stream);
 }
 
-template <class S, class R, int COLL, int MODE>
-int by_streaming(const StepParams<R> &p, int streaming, cudaStream_t stream) {
-    switch (streaming) {
-        case LBM_NO_STREAMING: return launch_scalar<S, R, COLL, false, false, MODE>(p, stream);
-        case LBM_POST_STREAMING: return launch_scalar<S, R, COLL, false, true, MODE>(p, stream);
-        case LBM_PRE_STREAMING: return launch_scalar<S, R, COLL, true, false, MODE>(p, stream);
-        case LBM_DOUBLE_STREAMING: return launch_scalar<S, R, COLL, true, true, MODE>(p, stream);
+template <class S, class R, int COLL, bool PULL, bool PUSH>
+int by_lanes(const StepParams<R> &p, const LaunchOptions &opt, cudaStream_t stream) {
+    if constexpr (sizeof(R) == 4 && (PULL != PUSH)) {
+        if (opt.lanes == 2 && p.n2 % 2 == 0) return launch_lanes<S, R, COLL, PULL, PUSH, 2>(p, opt, stream);
     }
-    return LBM_ERR_BAD_ARGUMENT;
-}
-
-template <class S, class R, int COLL>
-int by_mask(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream) {
-    if (!masked) return by_streaming<S, R, COLL, kUnmasked>(p, streaming, stream);
-    switch (variant) {
-        case kMaskedLabelFirst: return by_streaming<S, R, COLL, kMaskedLabelFirst>(p, streaming, stream);
-        case kMaskedOverwrite: return by_streaming<S, R, COLL, kMaskedOverwrite>(p, streaming, stream);
-        default: return by_streaming<S, R, COLL, kMaskedSpeculative>(p, streaming, stream);
-    }
+    return launch_lanes<S, R, COLL, PULL, PUSH, 1>(p, opt, stream);
 }
 
 }  // namespace
 
 template <class S, class R, int COLL>
-int launch_step_coll(const StepParams<R> &p, int streaming, bool masked, int variant, cudaStream_t stream) {
-    return by_mask<S, R, COLL>(p, streaming, masked, variant, stream);
+int launch_step_coll(const StepParams<R> &p, int streaming, const LaunchOptions &opt, cudaStream_t stream) {
+    switch (streaming) {
+        case LBM_NO_STREAMING: return by_lanes<S, R, COLL, false, false>(p, opt, stream);
+        case LBM_POST_STREAMING: return by_lanes<S, R, COLL, false, true>(p, opt, stream);
+        case LBM_PRE_STREAMING: return by_lanes<S, R, COLL, true, false>(p, opt, stream);
+        case LBM_DOUBLE_STREAMING: return by_lanes<S, R, COLL, true, true>(p, opt, stream);
+    }
+    return LBM_ERR_BAD_ARGUMENT;
 }
 
 template <class S, class R, int COLL>
@@ -138,6 +110,6 @@ template int launch_links_coll<LBM_INST_STENCIL, LBM_INST_REAL, LBM_INST_COLL>(c
                                                                                cudaStream_t);
 
 template int launch_step_coll<LBM_INST_STENCIL, LBM_INST_REAL, LBM_INST_COLL>(const StepParams<LBM_INST_REAL> &, int,
-                                                                              bool, int, cudaStream_t);
+                                                                              const LaunchOptions &, cudaStream_t);
 
 }  // namespace lbm

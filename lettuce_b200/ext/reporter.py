@@ -30,25 +30,28 @@ class Observable(ABC):
 
 
 class MaximumVelocity(Observable):
-    """max |u| in physical units (observable_reporter.py:27-31)"""
+    """max |u| in physical units (observable_reporter.py:27-31).  `fused_with_step`: see IncompressibleKineticEnergy."""
+    fused_with_step = True
 
     def __call__(self, f=None):
         f = self.flow.f if f is None else f
-        return self.flow.units.convert_velocity_to_pu(native.reduce(self.flow.stencil, native.MAX_U, f))
+        fused = native.fused_moments(self.flow, f)            # reduced inside a step kernel?
+        u_max = torch.sqrt(fused[1]) if fused is not None else native.reduce(self.flow.stencil, native.MAX_U, f)
+        return self.flow.units.convert_velocity_to_pu(u_max)
 
 
 class IncompressibleKineticEnergy(Observable):
     """sum 0.5 |u|^2 dx^d in physical units (observable_reporter.py:34-42).  `fused_with_step`: when a reporter
-    of this observable is due, `Simulation.__call__` runs the step before it through `lbm_step_energy`, which
-    reduces the energy of the state it writes inside the step kernel (no second pass over the populations)."""
+    of this observable is due, `Simulation.__call__` lets a step kernel reduce it (`lbm_step_moments`: the step that
+    writes the reported state, or with POST_STREAMING the step that follows it) -- no second pass over the
+    populations."""
     fused_with_step = True
 
     def __call__(self, f=None):
         f = self.flow.f if f is None else f
         units = self.flow.units
-        e_lu = native.fused_energy_lu(self.flow, f)           # reduced inside the step kernel that wrote f?
-        if e_lu is None:
-            e_lu = native.reduce(self.flow.stencil, native.SUM_HALF_U2, f)
+        fused = native.fused_moments(self.flow, f)            # reduced inside a step kernel?
+        e_lu = fused[0] if fused is not None else native.reduce(self.flow.stencil, native.SUM_HALF_U2, f)
         return units.convert_incompressible_energy_to_pu(e_lu) * units.convert_length_to_pu(1.0) ** self.flow.stencil.d
 
 

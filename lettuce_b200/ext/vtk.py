@@ -123,6 +123,11 @@ class VTKReporter(Reporter):
         self._pending = None
         atexit.register(self.wait)
 
+    def flush(self):
+        """called by Simulation.__call__ before it returns: the last due file is on disk (the reference writes
+        synchronously, vtk_reporter.py) and a failed write raises here"""
+        self.wait()
+
     def wait(self):
         """block until the file of the last due step is on disk (re-raises a failed write)"""
         pending, self._pending = self._pending, None

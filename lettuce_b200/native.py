@@ -36,6 +36,8 @@ NO_STREAMING, POST_STREAMING, PRE_STREAMING, DOUBLE_STREAMING = 0, 1, 2, 3
 # holds by construction.
 LAZY_POST_MIN_STEPS = int(os.environ.get("LBM_B200_LAZY_POST_MIN", "0"))
 SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED, ENSTROPHY = range(6)
+# lbm_step_moments_state: which state the reductions fused into a step describe
+MOMENTS_UNAVAILABLE, MOMENTS_OF_OUTPUT, MOMENTS_OF_INPUT = 0, 1, 2
 
 
 class LbmOp(C.Structure):
@@ -80,10 +82,12 @@ class LbmLinks(C.Structure):
                 ("force_scratch", C.c_void_p), ("force", C.c_void_p)]
 
 
-EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_step_links_n", "lbm_ipc_alloc", "lbm_ipc_open", "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n",
-           "lbm_step", "lbm_step_n", "lbm_step_energy", "lbm_step_energy_scratch_bytes", "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes", "lbm_reduce",
-           "lbm_run_host", "lbm_abi_version", "lbm_status_string", "lbm_last_cuda_error",
-           "lbm_launch_count", "lbm_step_variant_name"]
+EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_step_links_n", "lbm_ipc_alloc", "lbm_ipc_open",
+           "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n", "lbm_slab_step_moments",
+           "lbm_step", "lbm_step_n", "lbm_step_moments", "lbm_step_moments_state", "lbm_step_moments_scratch_bytes",
+           "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes",
+           "lbm_reduce", "lbm_run_host", "lbm_run_host_release", "lbm_abi_version", "lbm_status_string",
+           "lbm_last_cuda_error", "lbm_launch_count", "lbm_step_variant_name"]
 
 _lib = None
 
@@ -102,10 +106,15 @@ def lib() -> C.CDLL:
     L.lbm_step.restype = i32
     L.lbm_step_n.argtypes = [C.POINTER(LbmStepDesc), vp, vp, i64, vp]
     L.lbm_step_n.restype = i32
-    L.lbm_step_energy_scratch_bytes.argtypes = [C.POINTER(LbmStepDesc)]
-    L.lbm_step_energy_scratch_bytes.restype = C.c_size_t
-    L.lbm_step_energy.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, C.c_size_t, vp, vp]
-    L.lbm_step_energy.restype = i32
+    L.lbm_step_moments_state.argtypes = [C.POINTER(LbmStepDesc)]
+    L.lbm_step_moments_state.restype = i32
+    L.lbm_step_moments_scratch_bytes.argtypes = [C.POINTER(LbmStepDesc)]
+    L.lbm_step_moments_scratch_bytes.restype = C.c_size_t
+    L.lbm_step_moments.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, C.c_size_t, vp, vp]
+    L.lbm_step_moments.restype = i32
+    L.lbm_slab_step_moments.argtypes = [C.POINTER(LbmStepDesc), C.POINTER(LbmSlab), vp, vp, vp, C.c_size_t, vp, vp]
+    L.lbm_slab_step_moments.restype = i32
+    L.lbm_run_host_release.restype = i32
     L.lbm_links_scratch_doubles.argtypes = [i64]
     L.lbm_links_scratch_doubles.restype = i64
     L.lbm_apply_links.argtypes = [C.POINTER(LbmStepDesc), C.POINTER(LbmLinks), vp, vp, vp]
@@ -421,37 +430,49 @@ class Engine:
                                f"({list(f.shape)} {f.dtype} {f.device}); create a new Simulation")
         return f, g
 
-    def energy_fusable(self) -> bool:
-        """True when `step_with_energy` exists for this simulation: single-GPU engine, no boundaries, no
-        stream after the collide phase (NO_STREAMING / PRE_STREAMING)."""
-        cached = getattr(self, "_energy_fusable", None)      # depends on the lattice, the streaming mode and masks only
+    def moments_state(self) -> int:
+        """Which state the reductions fused into a step describe for this simulation (`lbm_step_moments_state`):
+        MOMENTS_OF_OUTPUT (NO / PRE streaming), MOMENTS_OF_INPUT (POST streaming: the report after step k rides on
+        step k + 1) or MOMENTS_UNAVAILABLE (DOUBLE streaming)."""
+        cached = getattr(self, "_moments_state", None)       # depends on the streaming mode only
         if cached is None:
-            cached = type(self) is Engine and int(self.lib.lbm_step_energy_scratch_bytes(C.byref(self.desc))) > 0
-            self._energy_fusable = cached
+            cached = int(self.lib.lbm_step_moments_state(C.byref(self.desc)))
+            self._moments_state = cached
         return cached
 
-    def step_with_energy(self) -> torch.Tensor:
-        """One time step that also returns sum 0.5|u|^2 (lattice units, 0-d float64 CUDA tensor) of the new
-        state, reduced inside the step kernel (`lbm_step_energy`).  Raises for steps with boundaries or a
-        post-collision stream; callers then use `step()` + the IncompressibleKineticEnergy observable.
-        The value is also left on the flow (`fused_energy_lu`) for the observable to pick up."""
-        if type(self) is not Engine:
-            raise RuntimeError("lbm_step_energy is a single-GPU entry point (slabs reduce with GlobalSum)")
+    def _moments_scratch(self) -> torch.Tensor:
+        need = int(self.lib.lbm_step_moments_scratch_bytes(C.byref(self.desc)))
+        if need == 0:
+            raise RuntimeError("lbm_step_moments is not available for this simulation (DOUBLE_STREAMING)")
+        if getattr(self, "_moments_buf", None) is None or self._moments_buf.numel() < need:
+            self._moments_buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._moments_buf
+
+    def _launch_step_with_moments(self, f, g, scratch, out):
+        check(self.lib.lbm_step_moments(C.byref(self.desc), f.data_ptr(), g.data_ptr(), scratch.data_ptr(),
+                                        scratch.numel(), out.data_ptr(), _stream_ptr(self.device)),
+              "lbm_step_moments")
+
+    def step_with_moments(self) -> torch.Tensor:
+        """One time step whose kernels also reduce (sum 0.5|u|^2, max |u|^2) in lattice units over this engine's
+        nodes -- a float64 CUDA tensor of two entries, no second pass over the populations (`lbm_step_moments`).
+        With MOMENTS_OF_OUTPUT the values describe the NEW state and are left on the flow for the observables to pick
+        up (`fused_moments`); with MOMENTS_OF_INPUT they describe the state the step started from."""
         self.refresh_parameters()
         f, g = self._buffers()
-        need = int(self.lib.lbm_step_energy_scratch_bytes(C.byref(self.desc)))
-        if need == 0:
-            raise RuntimeError("lbm_step_energy is not available for this simulation (boundaries or post-streaming)")
-        if getattr(self, "_energy_scratch", None) is None or self._energy_scratch.numel() < need:
-            self._energy_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        out = torch.empty((), dtype=torch.float64, device=self.device)
+        scratch = self._moments_scratch()
+        out = torch.empty(2, dtype=torch.float64, device=self.device)
+        self.flow._b200_moments = None
         with torch.cuda.device(self.device):
-            check(self.lib.lbm_step_energy(C.byref(self.desc), f.data_ptr(), g.data_ptr(),
-                                           self._energy_scratch.data_ptr(), need, out.data_ptr(),
-                                           _stream_ptr(self.device)), "lbm_step_energy")
-        self.flow.f, self.flow.f_next = g, f
-        self.flow._b200_energy = (g.data_ptr(), g._version, out)
+            self._launch_step_with_moments(f, g, scratch, out)
+        self._after_moments_step(f, g)
+        if self.moments_state() == MOMENTS_OF_OUTPUT:
+            new = self.flow.f
+            self.flow._b200_moments = (new.data_ptr(), new._version, out)
         return out
+
+    def _after_moments_step(self, f, g):
+        self.flow.f, self.flow.f_next = g, f
 
     def apply_links(self, boundary):
         """One post-streaming link boundary (ext/bounce_back.py) on the populations the last `step(1)` produced:
@@ -475,7 +496,7 @@ class Engine:
             raise RuntimeError("post-streaming boundaries need StreamingStrategy.POST_STREAMING")
         self.refresh_parameters()
         f, g = self._buffers()
-        self.flow._b200_energy = None
+        self.flow._b200_moments = None
         array = (LbmLinks * max(len(boundaries), 1))()
         for i, boundary in enumerate(boundaries):
             array[i] = boundary.link_descriptor(f)
@@ -504,7 +525,7 @@ class Engine:
         self.refresh_parameters()
         f, g = self._buffers()
         flow = self.flow
-        flow._b200_energy = None            # a fused energy (step_with_energy) describes the state before this step
+        flow._b200_moments = None           # fused moments (step_with_moments) describe the state before this step
         bufs, cur = [f, g], 0
         with torch.cuda.device(self.device):
             stream = _stream_ptr(self.device)
@@ -587,10 +608,15 @@ def describe(simulation):
                 streaming=int(eng.desc.streaming), collision_index=int(eng.desc.collision_index), ops=out)
 
 
-def fused_energy_lu(flow, f: torch.Tensor) -> Optional[torch.Tensor]:
-    """sum 0.5|u|^2 of `f` if the step that produced it already reduced it (`Engine.step_with_energy`) and `f`
-    has not been written through torch since; else None."""
-    cached = getattr(flow, "_b200_energy", None)
+def fused_moments(flow, f: torch.Tensor) -> Optional[torch.Tensor]:
+    """(sum 0.5|u|^2, max |u|^2) of `f` in lattice units over the engine's nodes if a step kernel already reduced them
+    (`Engine.step_with_moments`), else None.  Two cases: the step that WROTE `f` reduced its output and `f` has not
+    been written through torch since; or `Simulation.__call__` is reporting a state whose moments were reduced by the
+    step that followed it (`_b200_reported_moments`, set only around the reporter calls)."""
+    reported = getattr(flow, "_b200_reported_moments", None)
+    if reported is not None and f is flow.f:
+        return reported
+    cached = getattr(flow, "_b200_moments", None)
     if cached is None or f is not flow.f or cached[0] != f.data_ptr() or cached[1] != f._version:
         return None
     return cached[2]

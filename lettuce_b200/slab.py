@@ -249,14 +249,10 @@ class SlabEngine(native.Engine):
         self.t[self.cur].copy_(f)
         self.flow.f, self.flow.f_next = self.t[self.cur], self.t[1 - self.cur]
 
-    def step(self, n: int = 1):
-        if n <= 0:
-            return
-        flow = self.flow
-        if flow.f.data_ptr() != self.t[self.cur].data_ptr():
+    def _slab_struct(self) -> "native.LbmSlab":
+        if self.flow.f.data_ptr() != self.t[self.cur].data_ptr():
             raise RuntimeError("flow.f was replaced: slab populations must stay in the engine's IPC buffers "
                                "(use engine.load(tensor))")
-        self.refresh_parameters()
         a, b = ("a", "b") if self.cur == 0 else ("b", "a")
         s = native.LbmSlab()
         s.lo_a, s.lo_b, s.hi_a, s.hi_b = self.lo[a], self.lo[b], self.hi[a], self.hi[b]
@@ -265,6 +261,28 @@ class SlabEngine(native.Engine):
         s.signal_hi = self.hi["flags"]            # the hi neighbour's slot 0 = "written by my lo neighbour"
         s.wait_slots = self.flags.ptr.value
         s.epoch = self.epoch
+        return s
+
+    def _launch_step_with_moments(self, f, g, scratch, out):
+        """one lock-stepped step whose kernels reduce (sum 0.5|u|^2, max |u|^2) over THIS rank's nodes; GlobalSum /
+        GlobalMax combine the ranks"""
+        s = self._slab_struct()
+        native.check(self.lib.lbm_slab_step_moments(C.byref(self.desc), C.byref(s), f.data_ptr(), g.data_ptr(),
+                                                    scratch.data_ptr(), scratch.numel(), out.data_ptr(),
+                                                    native._stream_ptr(self.device)), "lbm_slab_step_moments")
+
+    def _after_moments_step(self, f, g):
+        self.epoch += 1
+        self.cur = 1 - self.cur
+        self.flow.f, self.flow.f_next = self.t[self.cur], self.t[1 - self.cur]
+
+    def step(self, n: int = 1):
+        if n <= 0:
+            return
+        flow = self.flow
+        self.refresh_parameters()
+        flow._b200_moments = None
+        s = self._slab_struct()
         with torch.cuda.device(self.device):
             native.check(self.lib.lbm_slab_step_n(C.byref(self.desc), C.byref(s), self.t[self.cur].data_ptr(),
                                                   self.t[1 - self.cur].data_ptr(), n, native._stream_ptr(self.device)),
@@ -421,6 +439,8 @@ class _GlobalReduce(Observable):
         super().__init__(observable.flow)
         self.observable = observable
         self.group = group
+        # the wrapped observable may take its rank-local value from a step kernel (lbm_slab_step_moments)
+        self.fused_with_step = bool(getattr(observable, "fused_with_step", False))
 
     def __call__(self, f=None):
         v = self.observable(f).clone()

@@ -146,7 +146,10 @@ def _reference_case(ref, case, device, dtype):
     g = flow.grid
     c = [0.25 * g[0].max()] + [0.5 * gi.max() for gi in g[1:]]
     flow.mask = sum((gi - ci) ** 2 for gi, ci in zip(g, c)) < 0.5 ** 2
-    flow.initialize()
+    if device == "cpu":
+        # (the reference's Obstacle.initial_pu mixes a CPU unit vector with the CUDA mask and raises on a CUDA
+        # context, lettuce/ext/_flows/obstacle.py:94-99; the CUDA arm takes the CPU arm's initial populations)
+        flow.initialize()
     tau = flow.units.relaxation_parameter_lu
     collision = ref.TRTCollision(tau) if "trt" in case else ref.BGKCollision(tau)
     return flow, ref.Simulation(flow, collision, [], ref.StreamingStrategy.POST_STREAMING)
@@ -163,7 +166,6 @@ def test_reference_simulation_steps_on_the_engine(ref, case, dtype):
     steps = 10
     flow_cpu, sim_cpu = _reference_case(ref, case, "cpu", dtype)
     flow_gpu, sim_gpu = _reference_case(ref, case, "cuda", dtype)
-    assert torch.equal(flow_gpu.f.cpu(), flow_cpu.f) or max_rel(flow_gpu.f.cpu().numpy(), flow_cpu.f.numpy()) < 1e-6
     flow_gpu.f = flow_cpu.f.to("cuda").contiguous()                 # identical initial state, bit for bit
     sim_gpu._collide_and_stream = native.invoke
     launches = native.launch_count()
@@ -242,7 +244,7 @@ def test_boundary_call_contract():
         assert torch.equal(flow.f.cpu(), torch.as_tensor(f0))
         # equilibrium boundary: feq(p, u) broadcast to the lattice (equilibrium_boundary_pu.py:79-84)
         vel = 0.05 * rng.standard_normal(d)
-        eq = lt.EquilibriumBoundaryPU(ctx, flow, torch.zeros(res, dtype=torch.bool), vel, 0.01)
+        eq = lt.EquilibriumBoundaryPU(ctx, flow, torch.zeros(res, dtype=torch.bool), vel, np.array(0.01))
         out = eq(flow).cpu().numpy()
         units = lo.Units(50.0, 0.1, characteristic_length_lu=res[0])
         rho = units.pressure_pu_to_density_lu(np.full([1] + [1] * d, 0.01))

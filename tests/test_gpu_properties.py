@@ -257,13 +257,14 @@ def test_convergence_orders():
 
 @pytest.mark.parametrize("stencil,res,coll,dtype", [("D3Q19", [24, 20, 36], "bgk", torch.float32),
                                                     ("D3Q27", [12, 16, 20], "kbc", torch.float64),
+                                                    ("D3Q27", [12, 16, 20], "kbc", torch.float32),
                                                     ("D2Q9", [40, 33], "trt", torch.float64),
                                                     # 4200 CTAs: the partials take the two-stage fold
                                                     ("D2Q9", [4200, 40], "bgk", torch.float64)])
-@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING"])
-def test_fused_step_energy_equals_reporter(stencil, res, coll, dtype, strategy):
-    """lbm_step_energy: same populations as lbm_step, and the energy it returns equals the
-    IncompressibleKineticEnergy reduction of the new state"""
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING", "POST_STREAMING"])
+def test_fused_step_moments_equal_the_reductions(stencil, res, coll, dtype, strategy):
+    """lbm_step_moments: same populations as lbm_step, and (sum 0.5|u|^2, max |u|^2) equal the stand-alone
+    reductions of the state they describe -- the new state (NO / PRE streaming) or the step's input (POST)"""
     from lettuce_b200 import native as nv
     c = ctx(dtype)
     mk = lambda: lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=STENCILS[stencil]())
@@ -272,54 +273,141 @@ def test_fused_step_energy_equals_reporter(stencil, res, coll, dtype, strategy):
     fa, fb = mk(), mk()
     sa = lt.Simulation(fa, make(fa), [], lt.StreamingStrategy[strategy])
     sb = lt.Simulation(fb, make(fb), [], lt.StreamingStrategy[strategy])
+    eng = nv.engine_of(sb)
+    assert eng.moments_state() == (nv.MOMENTS_OF_INPUT if strategy == "POST_STREAMING" else nv.MOMENTS_OF_OUTPUT)
+    rel = 1e-12 if dtype == torch.float64 else 1e-6
     for _ in range(3):
+        before = fa.f.clone()
         nv.invoke(sa)
-        e = float(nv.engine_of(sb).step_with_energy().cpu())
+        got = eng.step_with_moments().cpu().tolist()
         assert torch.equal(fa.f, fb.f)
-        ref = float(nv.reduce(fa.stencil, nv.SUM_HALF_U2, fa.f).cpu())
-        assert e == pytest.approx(ref, rel=1e-12 if dtype == torch.float64 else 1e-6)
-    post = lt.Simulation(mk(), lt.NoCollision(), [])              # POST_STREAMING: not available
+        described = before if strategy == "POST_STREAMING" else fa.f
+        assert got[0] == pytest.approx(float(nv.reduce(fa.stencil, nv.SUM_HALF_U2, described).cpu()), rel=rel)
+        assert got[1] ** 0.5 == pytest.approx(float(nv.reduce(fa.stencil, nv.MAX_U, described).cpu()), rel=rel)
+    double = lt.Simulation(mk(), lt.NoCollision(), [], lt.StreamingStrategy.DOUBLE_STREAMING)   # not available
+    assert nv.engine_of(double).moments_state() == nv.MOMENTS_UNAVAILABLE
     with pytest.raises(RuntimeError):
-        nv.engine_of(post).step_with_energy()
+        nv.engine_of(double).step_with_moments()
+
+
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_step_moments_with_boundaries(strategy, dtype):
+    """masked runs: the bulk kernel leaves the general nodes out of its partial sums and the sparse kernel adds
+    them (inlet, pressure outlet, bounce-back cylinder)"""
+    from lettuce_b200 import native as nv
+    from test_gpu_parity import ObstacleEqOut, make_obstacle
+    c = ctx(dtype)
+    for stencil, res in ((lt.D2Q9, [96, 32]), (lt.D3Q27, [48, 24, 24])):
+        fa, fb = (make_obstacle(ObstacleEqOut, c, res, stencil()) for _ in range(2))
+        mk = lambda fl: lt.Simulation(fl, lt.BGKCollision(fl.units.relaxation_parameter_lu), [],
+                                      lt.StreamingStrategy[strategy])
+        sa, sb = mk(fa), mk(fb)
+        eng = nv.engine_of(sb)
+        assert int(eng.desc.n_general) > 0
+        rel = 1e-12 if dtype == torch.float64 else 1e-6
+        for _ in range(4):
+            before = fa.f.clone()
+            nv.invoke(sa)
+            got = eng.step_with_moments().cpu().tolist()
+            assert torch.equal(fa.f, fb.f)
+            described = before if strategy == "POST_STREAMING" else fa.f
+            assert got[0] == pytest.approx(float(nv.reduce(fa.stencil, nv.SUM_HALF_U2, described).cpu()), rel=rel)
+            assert got[1] ** 0.5 == pytest.approx(float(nv.reduce(fa.stencil, nv.MAX_U, described).cpu()), rel=rel)
 
 
 @pytest.mark.parametrize("interval", [1, 3])
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_energy_reporter_rides_on_the_step_kernel(interval, dtype):
-    """Simulation.__call__ runs the step before a due IncompressibleKineticEnergy reporter through
-    lbm_step_energy: same populations and same reporter values as a step-by-step run with the stand-alone
-    reduction, and no reduce kernel is launched (one step kernel per step + the small fold)"""
+def test_moment_reporters_ride_on_the_step_kernels(interval, strategy, dtype):
+    """Simulation.__call__ lets the step kernels reduce due IncompressibleKineticEnergy / MaximumVelocity reports
+    (PRE: the step that writes the state; POST: the step that follows it): same populations and same reporter
+    values as a step-by-step run with the stand-alone reductions, and no stand-alone reduction is launched except
+    for the report at step 0 and, with POST streaming, the last one"""
     from lettuce_b200 import native as nv
     c = ctx(dtype)
     res, steps = [40, 24, 36], 6
     mk = lambda: lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=lt.D3Q19())
     fa, fb = mk(), mk()
     rep = lt.ObservableReporter(lt.IncompressibleKineticEnergy(fa), interval=interval, out=None)
-    sa = lt.Simulation(fa, lt.BGKCollision(fa.units.relaxation_parameter_lu), [rep], lt.StreamingStrategy.PRE_STREAMING)
-    sb = lt.Simulation(fb, lt.BGKCollision(fb.units.relaxation_parameter_lu), [], lt.StreamingStrategy.PRE_STREAMING)
+    rep_u = lt.ObservableReporter(lt.MaximumVelocity(fa), interval=interval, out=None)
+    strat = lt.StreamingStrategy[strategy]
+    sa = lt.Simulation(fa, lt.BGKCollision(fa.units.relaxation_parameter_lu), [rep, rep_u], strat)
+    sb = lt.Simulation(fb, lt.BGKCollision(fb.units.relaxation_parameter_lu), [], strat)
     nv.engine_of(sa)
     before = nv.launch_count()
     sa(steps)
     launched = nv.launch_count() - before
-    energy_b = lt.IncompressibleKineticEnergy(fb)
-    expect = [[0, float(energy_b().cpu())]]
+    energy_b, umax_b = lt.IncompressibleKineticEnergy(fb), lt.MaximumVelocity(fb)
+    expect = [[0, float(energy_b().cpu()), float(umax_b().cpu())]]
     for i in range(1, steps + 1):
         nv.invoke(sb)
         if i % interval == 0:
-            expect.append([i, float(energy_b().cpu())])
+            expect.append([i, float(energy_b().cpu()), float(umax_b().cpu())])
     assert torch.equal(fa.f, fb.f)
-    assert [e[0] for e in rep.out] == [e[0] for e in expect]
-    for got, want in zip(rep.out, expect):
-        assert got[2] == pytest.approx(want[1], rel=1e-12 if dtype == torch.float64 else 1e-6)
-    # step 0 report: reduce + fold; then `steps` step kernels and one fold per due report (tiny lattice: one stage)
-    assert launched == 2 + steps + steps // interval
-    # the cached value is dropped as soon as the populations move on or are written through torch
-    assert nv.fused_energy_lu(fa, fa.f) is not None
-    fa.f.mul_(1.0)
-    assert nv.fused_energy_lu(fa, fa.f) is None
-    sa(interval)
-    nv.invoke(sa)
-    assert nv.fused_energy_lu(fa, fa.f) is None
+    assert fa.i == steps
+    assert [e[0] for e in rep.out] == [e[0] for e in expect] == [e[0] for e in rep_u.out]
+    rel = 1e-12 if dtype == torch.float64 else 1e-6
+    for got, got_u, want in zip(rep.out, rep_u.out, expect):
+        assert got[2] == pytest.approx(want[1], rel=rel)
+        assert got_u[2] == pytest.approx(want[2], rel=rel)
+    # stand-alone reductions (2 launches each: reduce + fold) for both observables at step 0 and, with POST streaming,
+    # at the last step; `steps` step kernels; one fold per due report that rode on a step kernel (tiny lattice: one
+    # stage)
+    reports = steps // interval
+    fused = reports if strategy == "PRE_STREAMING" else reports - 1
+    standalone = 1 if strategy == "PRE_STREAMING" else 2
+    assert launched == 4 * standalone + steps + fused
+    if strategy == "PRE_STREAMING":
+        # the cached values are dropped as soon as the populations move on or are written through torch
+        assert nv.fused_moments(fa, fa.f) is not None
+        fa.f.mul_(1.0)
+        assert nv.fused_moments(fa, fa.f) is None
+        sa(interval)
+        nv.invoke(sa)
+    assert nv.fused_moments(fa, fa.f) is None
+
+
+@pytest.mark.parametrize("stencil,res,coll", [("D3Q27", [12, 10, 64], "kbc"), ("D3Q19", [10, 12, 96], "bgk"),
+                                              ("D2Q9", [40, 130], "trt"), ("D3Q27", [8, 12, 66], "smagorinsky"),
+                                              ("D2Q9", [36, 64], "kbc"), ("D3Q19", [8, 8, 64], "regularized")])
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
+def test_two_nodes_per_thread_kernel_is_bit_identical(stencil, res, coll, strategy):
+    """the packed float2 kernel (two neighbouring nodes per thread, FADD2 / FMUL2 / FFMA2) against the one-node
+    kernel: same bits, because every operation is an explicit round-to-nearest intrinsic in both (lbm_vec.cuh)"""
+    from lettuce_b200 import native as nv
+    from test_gpu_parity import make_collision
+    c = ctx(torch.float32)
+    flows = []
+    for lanes in (1, 2):
+        flow = lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=STENCILS[stencil]())
+        gen = torch.Generator(device=flow.f.device).manual_seed(5)
+        flow.f.mul_(1.0 + 1e-2 * (torch.rand(flow.f.shape, generator=gen, device=flow.f.device) - 0.5))
+        sim = lt.Simulation(flow, make_collision(coll, flow), [], lt.StreamingStrategy[strategy])
+        eng = nv.engine_of(sim)
+        eng.desc.variant = lanes
+        assert ("2 nodes" in eng.lib.lbm_step_variant_name(eng.desc).decode()) == (lanes == 2)
+        nv.invoke_n(sim, 7)
+        flows.append(flow)
+    assert torch.equal(flows[0].f, flows[1].f)
+
+
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
+def test_two_nodes_per_thread_kernel_with_boundaries(strategy):
+    from lettuce_b200 import native as nv
+    from test_gpu_parity import ObstacleEqOut, make_obstacle
+    c = ctx(torch.float32)
+    for stencil, res, coll in ((lt.D2Q9, [96, 32], "bgk"), (lt.D3Q27, [48, 24, 24], "trt")):
+        out = []
+        for lanes in (1, 2):
+            flow = make_obstacle(ObstacleEqOut, c, res, stencil())
+            tau = flow.units.relaxation_parameter_lu
+            sim = lt.Simulation(flow, lt.BGKCollision(tau) if coll == "bgk" else lt.TRTCollision(tau), [],
+                                lt.StreamingStrategy[strategy])
+            nv.engine_of(sim).desc.variant = lanes
+            nv.invoke_n(sim, 9)
+            out.append(flow.f)
+        assert torch.equal(out[0], out[1])
 
 
 def test_vtk_reporter_writes_engine_fields(tmp_path):
