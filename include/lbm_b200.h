@@ -253,6 +253,14 @@ int lbm_moments(const lbm_lattice *lat, const void *d_f, void *d_rho, void *d_u,
 int lbm_equilibrium(const lbm_lattice *lat, const void *d_rho, const int64_t rho_stride[3], const void *d_u,
                     const int64_t u_stride[4], void *d_f_out, void *stream);
 
+/* Initial populations with the first-order non-equilibrium part, f_q = feq_q(rho, u) - w_q Q_q : Pi1 with
+ * Pi1 = tau rho grad(u) / cs^2 from 6th-order periodic differences (initialize_f_neq, lettuce/_flow.py:341-367),
+ * written in ONE pass from the density field d_rho [nx,ny,nz] and the velocity field d_u [d,nx,ny,nz] (lattice
+ * units, e.g. from lbm_moments) without the reference's full-size temporaries.  `eye_cs2` is what the reference
+ * subtracts on the diagonal of Q: cs^2 rounded to float32 (torch.eye in torch's default dtype, _flow.py:358-360). */
+int lbm_initialize_fneq(const lbm_lattice *lat, const void *d_rho, const void *d_u, double tau, double eye_cs2,
+                        void *d_f_out, void *stream);
+
 typedef enum lbm_reduction {
     LBM_SUM_HALF_U2 = 0, /* sum over nodes of 0.5*|u|^2 in lattice units (_flow.py:200-204) */
     LBM_MAX_U = 1,       /* max over nodes of |u| in lattice units (observable_reporter.py:27-31) */

@@ -298,6 +298,9 @@ def initialize_f_neq(flow: Flow) -> torch.Tensor:
     context (_flow.py:358-360); that rounding is reproduced so that initial states are
     identical to the reference's."""
     f, st, d = flow.f, flow.torch_stencil, flow.stencil.d
+    if f.is_cuda and type(flow.equilibrium) is QuadraticEquilibrium and f.dtype in (torch.float32, torch.float64):
+        # one kernel, no full-size temporaries (row f3 of SURVEY.md section 8)
+        return native.initialize_fneq(flow.stencil, f.contiguous(), flow.units.relaxation_parameter_lu)
     rho = f.sum(dim=0, keepdim=True)
     u = torch.tensordot(st.e.t().contiguous(), f, dims=1) / rho
     grad_u = torch.stack([_gradient6(u[a]) for a in range(d)])

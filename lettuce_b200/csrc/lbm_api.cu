@@ -18,6 +18,9 @@ int launch_moments(const R *f, R *rho, R *u, int64_t N, cudaStream_t st);
 template <class S, class R>
 int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, int n2, double *partials, double *out,
                   cudaStream_t st);
+template <class S, class R>
+int launch_init_fneq(const R *rho, const R *u, double tau_over_cs2, double eye_cs2, int n0, int n1, int n2, R *f,
+                     cudaStream_t stream);
 size_t reduce_scratch_bytes();
 int launch_fold_sum(const double *partials, int n, double *stage, double *out, cudaStream_t st);
 size_t fold_pair_stage_bytes();
@@ -699,6 +702,20 @@ int lbm_equilibrium(const lbm_lattice *lat, const void *d_rho, const int64_t rho
     LBM_DISPATCH(lat->stencil, lat->dtype,
                  return cuda_fail((launch_equilibrium<S, R>((const R *)d_rho, rho_stride, (const R *)d_u, u_stride, dm.n0,
                                                             dm.n1, dm.n2, (R *)d_f_out, (cudaStream_t)stream))));
+    return LBM_ERR_BAD_ARGUMENT;
+}
+
+int lbm_initialize_fneq(const lbm_lattice *lat, const void *d_rho, const void *d_u, double tau, double eye_cs2,
+                        void *d_f_out, void *stream) {
+    Dims dm;
+    int rc = lattice_dims(lat, dm);
+    if (rc) return rc;
+    if (!d_rho || !d_u || !d_f_out) return LBM_ERR_BAD_ARGUMENT;
+    LBM_DISPATCH(lat->stencil, lat->dtype,
+                 // the reference divides by the stencil's cs^2 in the context dtype (torch_stencil.cs ** 2)
+                 return cuda_fail((launch_init_fneq<S, R>((const R *)d_rho, (const R *)d_u,
+                                                          (double)((R)tau / ((R)kCs * (R)kCs)), eye_cs2, dm.n0, dm.n1,
+                                                          dm.n2, (R *)d_f_out, (cudaStream_t)stream))));
     return LBM_ERR_BAD_ARGUMENT;
 }
 

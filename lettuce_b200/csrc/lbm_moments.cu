@@ -194,6 +194,59 @@ __global__ void enstrophy_kernel(const R *__restrict__ u, int n0, int n1, int n2
     block_fold_store<false>(acc, partials);
 }
 
+// Initial populations with the first-order non-equilibrium part (lettuce/_flow.py:341-367, Krueger et al. 2017):
+//   f_q = feq_q(rho, u) - w_q Q_q : Pi1,   Pi1_ab = tau rho d_b u_a / cs^2,   Q_q,ab = e_qa e_qb - delta_ab eye_cs2
+// with 6th-order periodic differences (torch_gradient(order=6)).  rho [N] and u [D][N] (user component order) are
+// fields; f is written in one pass, no full-size temporaries.  `eye_cs2` is the value the reference subtracts on
+// the diagonal: cs^2 rounded to float32 (torch.eye in torch's default dtype, _flow.py:358-360).
+template <class S, class R>
+__global__ void init_fneq_kernel(const R *__restrict__ rho, const R *__restrict__ u, R tau_over_cs2, R eye_cs2, int n0,
+                                 int n1, int n2, R *__restrict__ f) {
+    constexpr int D = S::D;
+    const int64_t N = (int64_t)n0 * n1 * n2;
+    const int64_t stride[3] = {(int64_t)n1 * n2, n2, 1};
+    const int extent[3] = {n0, n1, n2};
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int idx[3] = {(int)(n / stride[0]), (int)((n / n2) % n1), (int)(n % n2)};
+        const R r = rho[n];
+        R v[3] = {R(0), R(0), R(0)};      // internal axis order for the equilibrium
+        R pi[D][D];                       // user component / axis order
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            v[S::axis_of(a)] = u[a * N + n];
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+                const int ax = S::axis_of(b);
+                pi[a][b] = tau_over_cs2 * r * d6(u + a * N, n, idx[ax], extent[ax], stride[ax]);
+            }
+        }
+        Equilibrium<S, R> eq(r, v);
+        ForQ<S::Q>::run([&]<int q>() {
+            R piq = R(0);
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+#pragma unroll
+                for (int b = 0; b < D; ++b) {
+                    const R qab = R(S::e(q, S::axis_of(a)) * S::e(q, S::axis_of(b))) - (a == b ? eye_cs2 : R(0));
+                    piq += pi[a][b] * qab;
+                }
+            }
+            f[q * N + n] = eq.template get<q>() - R(S::w(q)) * piq;
+        });
+    }
+}
+
+template <class S, class R>
+int launch_init_fneq(const R *rho, const R *u, double tau_over_cs2, double eye_cs2, int n0, int n1, int n2, R *f,
+                     cudaStream_t stream) {
+    const int64_t N = (int64_t)n0 * n1 * n2;
+    int64_t b = (N + 255) / 256;
+    if (b > 148 * 32) b = 148 * 32;
+    init_fneq_kernel<S, R><<<(int)b, 256, 0, stream>>>(rho, u, (R)tau_over_cs2, (R)eye_cs2, n0, n1, n2, f);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // host-side launch helpers used by lbm_api.cu
 // ---------------------------------------------------------------------------
@@ -253,6 +306,7 @@ int launch_reduce(int what, const R *in, const uint8_t *mask, int n0, int n1, in
     template int launch_equilibrium<S, R>(const R *, const int64_t *, const R *, const int64_t *, int, int, int, R *, \
                                           cudaStream_t);                              \
     template int launch_moments<S, R>(const R *, R *, R *, int64_t, cudaStream_t);   \
+    template int launch_init_fneq<S, R>(const R *, const R *, double, double, int, int, int, R *, cudaStream_t); \
     template int launch_reduce<S, R>(int, const R *, const uint8_t *, int, int, int, double *, double *, cudaStream_t);
 LBM_INSTANTIATE(D2Q9, float)
 LBM_INSTANTIATE(D2Q9, double)

@@ -85,7 +85,8 @@ class LbmLinks(C.Structure):
 EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_step_links_n", "lbm_ipc_alloc", "lbm_ipc_open",
            "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n", "lbm_slab_step_moments",
            "lbm_step", "lbm_step_n", "lbm_step_moments", "lbm_step_moments_state", "lbm_step_moments_scratch_bytes",
-           "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_moments", "lbm_reduce_scratch_bytes",
+           "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_initialize_fneq", "lbm_moments",
+           "lbm_reduce_scratch_bytes",
            "lbm_reduce", "lbm_run_host", "lbm_run_host_release", "lbm_abi_version", "lbm_status_string",
            "lbm_last_cuda_error", "lbm_launch_count", "lbm_step_variant_name"]
 
@@ -137,6 +138,8 @@ def lib() -> C.CDLL:
     L.lbm_list_general_nodes.restype = i32
     L.lbm_equilibrium.argtypes = [C.POINTER(LbmLattice), vp, C.POINTER(i64), vp, C.POINTER(i64), vp, vp]
     L.lbm_equilibrium.restype = i32
+    L.lbm_initialize_fneq.argtypes = [C.POINTER(LbmLattice), vp, vp, C.c_double, C.c_double, vp, vp]
+    L.lbm_initialize_fneq.restype = i32
     L.lbm_moments.argtypes = [C.POINTER(LbmLattice), vp, vp, vp, vp]
     L.lbm_moments.restype = i32
     L.lbm_reduce_scratch_bytes.argtypes = [C.POINTER(LbmLattice)]
@@ -681,6 +684,22 @@ def equilibrium_field(stencil, rho: torch.Tensor, u: torch.Tensor, resolution) -
         check(lib().lbm_equilibrium(C.byref(lat), rho.data_ptr(), rs, u.data_ptr(), us, f.data_ptr(),
                                     _stream_ptr(u.device)), "lbm_equilibrium")
     return f
+
+
+def initialize_fneq(stencil, f: torch.Tensor, tau: float) -> torch.Tensor:
+    """`initialize_f_neq` (lettuce/_flow.py:341-367) on the device: moments of `f` (4 N values), then ONE kernel
+    that writes feq(rho, u) - w_q Q_q : Pi1 -- instead of the reference's chain of full-size torch temporaries
+    (gradient stacks, two einsums, feq and fneq)."""
+    _require_cuda(f, "f")
+    rho, u = moments(stencil, f)
+    lat = lattice_of(stencil, f.shape[1:], f.dtype)
+    # the reference subtracts torch.eye(d) * cs**2, a float32 tensor, on the diagonal of Q (_flow.py:358-360)
+    eye_cs2 = float(torch.tensor(stencil.cs ** 2, dtype=torch.float32))
+    out = torch.empty_like(f)
+    with torch.cuda.device(f.device):
+        check(lib().lbm_initialize_fneq(C.byref(lat), rho.data_ptr(), u.data_ptr(), float(tau), eye_cs2,
+                                        out.data_ptr(), _stream_ptr(f.device)), "lbm_initialize_fneq")
+    return out
 
 
 _scratch = {}

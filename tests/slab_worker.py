@@ -34,15 +34,19 @@ def gather_slabs(local: torch.Tensor, dec, device):
     return torch.cat(parts, dim=1)
 
 
-def gpu_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev):
+def gpu_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev, every=None):
+    """`every`: report interval (default: one report after the last step).  With every = 1 the energy / maximum
+    velocity reports ride on the slab step kernels (lbm_slab_step_moments), enstrophy is left out."""
+    every = every or steps
     ctx = lt.Context(dev, dtype=dtype)
     dec = slab.SlabDecomposition(res[0], world, rank)
     flow = slab.SlabTaylorGreenVortex(ctx, res, 1600.0, 0.05, stencil_cls(), dec)
     make = {"bgk": lambda f: lt.BGKCollision(f.units.relaxation_parameter_lu), "kbc": lambda f: lt.KBCCollision(),
             "trt": lambda f: lt.TRTCollision(f.units.relaxation_parameter_lu)}[coll]
-    energy = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=steps, out=None)
-    enst = lt.ObservableReporter(slab.SlabEnstrophy(flow), interval=steps, out=None) if min(dec.sizes) >= 3 else None
-    umax = lt.ObservableReporter(slab.GlobalMax(lt.MaximumVelocity(flow)), interval=steps, out=None)
+    energy = lt.ObservableReporter(slab.GlobalSum(lt.IncompressibleKineticEnergy(flow)), interval=every, out=None)
+    enst = (lt.ObservableReporter(slab.SlabEnstrophy(flow), interval=every, out=None)
+            if min(dec.sizes) >= 3 and every == steps else None)
+    umax = lt.ObservableReporter(slab.GlobalMax(lt.MaximumVelocity(flow)), interval=every, out=None)
     sim = slab.SlabSimulation(flow, make(flow), [r for r in (energy, enst, umax) if r is not None], strategy, dec)
     f0 = gather_slabs(flow.f, dec, dev)
     # odd and even batch lengths exercise the buffer parity logic
@@ -53,19 +57,23 @@ def gpu_case(stencil_cls, res, coll, strategy, dtype, steps, rank, world, dev):
         ref_flow = lt.TaylorGreenVortex(ctx, res, 1600.0, 0.05, stencil=stencil_cls())
         init_err = float((ref_flow.f - f0).abs().max())
         ref_flow.f = f0.clone()
-        ref_energy = lt.ObservableReporter(lt.IncompressibleKineticEnergy(ref_flow), interval=steps, out=None)
-        ref_enst = lt.ObservableReporter(lt.Enstrophy(ref_flow), interval=steps, out=None)
-        ref_umax = lt.ObservableReporter(lt.MaximumVelocity(ref_flow), interval=steps, out=None)
+        ref_energy = lt.ObservableReporter(lt.IncompressibleKineticEnergy(ref_flow), interval=every, out=None)
+        ref_enst = lt.ObservableReporter(lt.Enstrophy(ref_flow), interval=every, out=None)
+        ref_umax = lt.ObservableReporter(lt.MaximumVelocity(ref_flow), interval=every, out=None)
         ref = lt.Simulation(ref_flow, make(ref_flow), [ref_energy, ref_enst, ref_umax], strategy)
         ref(steps)
         same = torch.equal(ref_flow.f, got)
-        e_rel = abs(energy.out[-1][2] - ref_energy.out[-1][2]) / abs(ref_energy.out[-1][2])
-        if enst is not None:
-            e_rel = max(e_rel, abs(enst.out[-1][2] - ref_enst.out[-1][2]) / abs(ref_enst.out[-1][2]))
-        e_rel = max(e_rel, abs(umax.out[-1][2] - ref_umax.out[-1][2]) / abs(ref_umax.out[-1][2]))
-        print(f"[slab] {stencil_cls.__name__} {res} {coll} {strategy.name} {dtype} world={world}: "
+        e_rel = 0.0
+        pairs = [(energy, ref_energy), (umax, ref_umax)] + ([(enst, ref_enst)] if enst is not None else [])
+        for mine, theirs in pairs:
+            rows_ok = [r[0] for r in mine.out] == [r[0] for r in theirs.out]
+            same = same and rows_ok
+            for a, b in zip(mine.out, theirs.out):
+                e_rel = max(e_rel, abs(a[2] - b[2]) / abs(b[2]))
+        print(f"[slab] {stencil_cls.__name__} {res} {coll} {strategy.name} {dtype} world={world} every={every}: "
               f"bit-exact={same} init_err={init_err:.1e} observables_rel={e_rel:.1e}", flush=True)
-        ok = same and init_err < 1e-6 and e_rel < 1e-9
+        # (rank partial sums are combined in a different order than the single-GPU fold: rounding-level differences)
+        ok = same and init_err < 1e-6 and e_rel < (1e-9 if dtype == torch.float64 else 1e-6)
     sim.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
@@ -140,6 +148,8 @@ def gpu_main():
              (lt.D2Q9, [50, 32], "kbc", S.POST_STREAMING, torch.float32, 10),
              (lt.D3Q19, [world * 2, 16, 32], "bgk", S.POST_STREAMING, torch.float32, 7)]
     ok = all([gpu_case(*c, rank, world, dev) for c in cases])
+    # reports after every step: energy and maximum velocity are reduced inside the slab step kernels
+    ok = all([gpu_case(*c, rank, world, dev, every=1) for c in cases[:2] + cases[4:6]]) and ok
     ocases = [(lt.D2Q9, [64, 32], "bgk", S.POST_STREAMING, torch.float64, 12, False),
               (lt.D2Q9, [64, 32], "bgk", S.PRE_STREAMING, torch.float32, 12, False),
               (lt.D3Q27, [32, 16, 16], "trt", S.POST_STREAMING, torch.float32, 9, False),
