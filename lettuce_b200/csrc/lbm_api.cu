@@ -245,6 +245,14 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     if (x.sync) p.sync = *x.sync;
     p.energy_partials = x.partials;
     p.reduce_mode = x.partials ? x.reduce_mode : kReduceNone;
+    // consecutive steps sweep the x-planes in opposite directions (L2 reuse, StepParams::reverse_sweep); the result
+    // does not depend on the order.  LBM_B200_ALTERNATE_SWEEP=0 switches it off (A/B).
+    static std::atomic<unsigned> sweep{0};
+    static const bool alternate = [] {
+        const char *e = getenv("LBM_B200_ALTERNATE_SWEEP");
+        return !(e && e[0] == '0');
+    }();
+    p.reverse_sweep = alternate ? (int)(sweep.fetch_add(1) & 1u) : 0;
     LaunchOptions opt;
     opt.lanes = chosen_lanes(d);
     opt.chained = x.chained;
