@@ -165,6 +165,30 @@ struct Equilibrium {
             return vmul(wrho<q>(), poly);
         }
     }
+    // feq_q - g and g - feq_q with the last product fused into the subtraction.  (Spelled out because ptxas
+    // contracts a packed mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 although both carry a rounding modifier --
+    // it never does that to the scalar forms -- so the one-node and two-node kernels give the same bits only if no
+    // product is left to feed a sum: scripts/check_packed_contraction.py.)
+    template <int q>
+    LBM_HD V minus(V g) const {
+        if constexpr (q == 0) {
+            return vfma(wrho<0>(), base, vneg(g));
+        } else {
+            const V eu = e_dot<S, V, q>(u);
+            const V poly = vfma(eu, vfma(eu, vset<V>(0.5 / (kCs2 * kCs2)), vset<V>(1.0 / kCs2)), base);
+            return vfma(wrho<q>(), poly, vneg(g));
+        }
+    }
+    template <int q>
+    LBM_HD V subtracted_from(V g) const {
+        if constexpr (q == 0) {
+            return vfnma(wrho<0>(), base, g);
+        } else {
+            const V eu = e_dot<S, V, q>(u);
+            const V poly = vfma(eu, vfma(eu, vset<V>(0.5 / (kCs2 * kCs2)), vset<V>(1.0 / kCs2)), base);
+            return vfnma(wrho<q>(), poly, g);
+        }
+    }
     // even part of q and its opposite: base + (e.u)^2 / (2 cs^4); feq_q + feq_opposite = 2 w rho even
     template <int q>
     LBM_HD V even(V eu) const { return vfma(vmul(eu, eu), vset<V>(0.5 / (kCs2 * kCs2)), base); }
@@ -174,9 +198,9 @@ struct Equilibrium {
         const V eu = e_dot<S, V, q>(u);
         const V wr = wrho<q>();
         const V a = vmul(wr, even<q>(eu));
-        const V b = vmul(vmul(wr, vset<V>(1.0 / kCs2)), eu);
-        fq = vadd(a, b);
-        fo = vsub(a, b);
+        const V b = vmul(wr, vset<V>(1.0 / kCs2));
+        fq = vfma(b, eu, a);
+        fo = vfnma(b, eu, a);
     }
 };
 
@@ -206,7 +230,7 @@ struct Collide<S, V, LBM_OP_BGK> {
         density_velocity<S, V>(f, rho, u);
         Equilibrium<S, V> eq(rho, u);
         const V omega = vsplat<V>(inv_tau);
-        ForQ<S::Q>::run([&]<int q>() { f[q] = vfma(omega, vsub(eq.template get<q>(), f[q]), f[q]); });
+        ForQ<S::Q>::run([&]<int q>() { f[q] = vfma(omega, eq.template minus<q>(f[q]), f[q]); });
     }
 };
 
@@ -222,16 +246,16 @@ struct Collide<S, V, LBM_OP_TRT> {
         ForQ<S::Q>::run([&]<int q>() {
             constexpr int o = S::opp(q);
             if constexpr (q == 0) {
-                const V d = vsub(f[0], eq.template get<0>());
+                const V d = eq.template subtracted_from<0>(f[0]);
                 f[0] = vfnma(vadd(d, d), a, f[0]);
             } else if constexpr (q < o) {
                 V eq_q, eq_o;
                 eq.template pair<q>(eq_q, eq_o);
                 const V fq = f[q], fo = f[o];
-                const V even = vmul(vsub(vadd(fq, fo), vadd(eq_q, eq_o)), a);
-                const V odd = vmul(vsub(vsub(fq, fo), vsub(eq_q, eq_o)), b);
-                f[q] = vsub(fq, vadd(even, odd));
-                f[o] = vsub(fo, vsub(even, odd));
+                const V even = vsub(vadd(fq, fo), vadd(eq_q, eq_o));
+                const V odd = vsub(vsub(fq, fo), vsub(eq_q, eq_o));
+                f[q] = vfnma(b, odd, vfnma(a, even, fq));
+                f[o] = vfma(b, odd, vfnma(a, even, fo));
             }
         });
     }
@@ -368,9 +392,9 @@ struct Collide<S, V, LBM_OP_KBC> {
                 V g;
                 if constexpr (ds_index(q) >= 0) g = vfma(nwr, eq.template even<q>(eu), vmul(b, ds_of<q>(c)));
                 else g = vmul(nwr, eq.template even<q>(eu));
-                const V h = vmul(vmul(nwr, vset<V>(1.0 / kCs2)), eu);
-                f[q] = vfma(a, f[q], vadd(g, h));
-                f[o] = vfma(a, f[o], vsub(g, h));
+                const V h = vmul(nwr, vset<V>(1.0 / kCs2));
+                f[q] = vfma(a, f[q], vfma(h, eu, g));
+                f[o] = vfma(a, f[o], vfnma(h, eu, g));
             }
         });
     }
@@ -482,7 +506,7 @@ LBM_HD void collide_bgk_forced(V (&f)[S::Q], scalar_t<V> inv_tau, const ForceArg
         const V eu = e_dot<S, V, q>(u), ea = e_dot<S, V, q>(acc);
         // (e - u).a / cs^2 + (e.u)(e.a) / cs^4
         const V src = vfma(vmul(eu, ea), vset<V>(1.0 / (kCs2 * kCs2)), vmul(vsub(ea, ua), vset<V>(1.0 / kCs2)));
-        const V relaxed = vfma(omega, vsub(eq.template get<q>(), f[q]), f[q]);
+        const V relaxed = vfma(omega, eq.template minus<q>(f[q]), f[q]);
         f[q] = vfma(src_scale, vmul(vset<V>(S::w(q)), src), relaxed);
     });
 }

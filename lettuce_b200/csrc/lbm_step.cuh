@@ -382,7 +382,7 @@ LBM_D void accumulate_kinetic(const V (&f)[S::Q], const bool (&take)[2], double 
 // (block-uniform; the cut planes of a multi-GPU slab) makes the general nodes skip their stores instead: a wrong store
 // into the NEIGHBOUR's memory could land after the neighbour's sparse kernel has written the right value there
 // (nothing orders the two ranks' kernels within a step), so across a cut every slot keeps exactly one writer.
-template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES>
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES, bool EXTRAS>
 LBM_D void node_update(const StepParams<R> &p, int x, int y, int z, bool single_writer, double &e_sum, double &e_max) {
     constexpr int Q = S::Q;
     using V = typename LaneVec<R, LANES>::type;
@@ -396,9 +396,11 @@ LBM_D void node_update(const StepParams<R> &p, int x, int y, int z, bool single_
     // the labels are needed to keep the general nodes out of a fused reduction (the sparse kernel contributes
     // those) and for single_writer
     bool mine[2] = {true, true};
-    if ((p.reduce_mode != kReduceNone || single_writer) && p.labels != nullptr) {
+    if constexpr (EXTRAS) {
+        if ((p.reduce_mode != kReduceNone || single_writer) && p.labels != nullptr) {
 #pragma unroll
-        for (int l = 0; l < LANES; ++l) mine[l] = !(__ldg(p.labels + (row0 + z + l)) & kLabelGeneral);
+            for (int l = 0; l < LANES; ++l) mine[l] = !(__ldg(p.labels + (row0 + z + l)) & kLabelGeneral);
+        }
     }
 
     V f[Q];
@@ -415,11 +417,13 @@ LBM_D void node_update(const StepParams<R> &p, int x, int y, int z, bool single_
             else f[q] = make_float2(__ldg(src + (z + 1)), __ldg(src + zp));                          // from z+1, z+2
         }
     });
-    if (p.reduce_mode == kReduceInput) accumulate_kinetic<S, V>(f, mine, e_sum, e_max);
+    if constexpr (EXTRAS) {
+        if (p.reduce_mode == kReduceInput) accumulate_kinetic<S, V>(f, mine, e_sum, e_max);
+    }
 
     collide_lanes<S, V, COLL>(p, f);
 
-    if (single_writer && !(mine[0] && mine[LANES - 1])) {
+    if (EXTRAS && single_writer && !(mine[0] && mine[LANES - 1])) {
         // a general node on a cut plane: only the other lane's node (if it is plain fluid) stores, lane by lane
 #pragma unroll
         for (int l = 0; l < LANES; ++l) {
@@ -454,7 +458,9 @@ LBM_D void node_update(const StepParams<R> &p, int x, int y, int z, bool single_
             }
         });
     }
-    if (p.reduce_mode == kReduceOutput) accumulate_kinetic<S, V>(f, mine, e_sum, e_max);
+    if constexpr (EXTRAS) {
+        if (p.reduce_mode == kReduceOutput) accumulate_kinetic<S, V>(f, mine, e_sum, e_max);
+    }
 }
 
 // Slab lock step (multi-GPU): W boundary planes per side take part (2 when the step both pulls and pushes, because
@@ -503,7 +509,10 @@ LBM_D void store_cta_partials(double e_sum, double e_max, double *partials, int 
     }
 }
 
-template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES>
+// EXTRAS = false is the plain step (no slab lock step, no fused reductions: nothing but gather, collide, scatter);
+// EXTRAS = true carries both as run-time options.  Two instantiations so that the options cost the plain kernel
+// neither instructions nor registers.
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES, bool EXTRAS>
 __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_blocks_per_sm<S, R, COLL, LANES>()))
     step_kernel(const __grid_constant__ StepParams<R> p) {
     // (no-op unless THIS grid was launched programmatically behind the previous step: then the grid in front has to
@@ -513,42 +522,48 @@ __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_bloc
     // (masked runs: general_nodes_kernel; chained steps of lbm_step_n: the next step): it may become resident once
     // every CTA of this grid has got here, i.e. once the previous step is known to be complete.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const bool sync = p.sync.on != 0;
     const bool reverse = p.reverse_sweep != 0;
-    const int x = sync ? sync_plane<PULL, PUSH>(blockIdx.z, p.n0, reverse)
-                       : (reverse ? p.n0 - 1 - (int)blockIdx.z : (int)blockIdx.z);
-    constexpr int W = (PULL && PUSH) ? 2 : 1;
-    const bool lo = sync && x < W, hi = sync && x >= p.n0 - W;
-    const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
-    if (lo || hi) {
-        // boundary-plane CTAs wait for the neighbour's progress counter before they touch peer memory
-        if (leader) {
-            spin_until(p.sync.wait + (lo ? 0 : 1), p.sync.wait_value, p.sync.timeout_cycles);
-            __threadfence_system();
-        }
-        __syncthreads();
-    }
     const int z = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     double e_sum = 0.0, e_max = 0.0;
-    if (z < p.n2 && y < p.n1)
-        node_update<S, R, COLL, PULL, PUSH, LANES>(p, x, y, z, (lo || hi) && p.labels != nullptr, e_sum, e_max);
-    if (lo || hi) {
-        // ... and the last of them to finish publishes this rank's counter (unless the sparse kernel of a masked
-        // step still has to touch the boundary planes: then IT publishes, general_nodes_kernel)
-        __threadfence_system();   // this thread's loads from / stores to the neighbour are performed
-        __syncthreads();
-        if (leader && p.sync.publish) {
-            const unsigned long long old = atomicAdd(p.sync.done + (lo ? 0 : 1), 1ULL);
-            if ((old + 1) % p.sync.ctas_per_side == 0) {
+    if constexpr (!EXTRAS) {
+        const int x = reverse ? p.n0 - 1 - (int)blockIdx.z : (int)blockIdx.z;
+        if (z < p.n2 && y < p.n1) node_update<S, R, COLL, PULL, PUSH, LANES, false>(p, x, y, z, false, e_sum, e_max);
+    } else {
+        const bool sync = p.sync.on != 0;
+        const int x = sync ? sync_plane<PULL, PUSH>(blockIdx.z, p.n0, reverse)
+                           : (reverse ? p.n0 - 1 - (int)blockIdx.z : (int)blockIdx.z);
+        constexpr int W = (PULL && PUSH) ? 2 : 1;
+        const bool lo = sync && x < W, hi = sync && x >= p.n0 - W;
+        const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+        if (lo || hi) {
+            // boundary-plane CTAs wait for the neighbour's progress counter before they touch peer memory
+            if (leader) {
+                spin_until(p.sync.wait + (lo ? 0 : 1), p.sync.wait_value, p.sync.timeout_cycles);
                 __threadfence_system();
-                *(volatile unsigned long long *)(lo ? p.sync.sig_lo : p.sync.sig_hi) = p.sync.signal_value;
+            }
+            __syncthreads();
+        }
+        if (z < p.n2 && y < p.n1)
+            node_update<S, R, COLL, PULL, PUSH, LANES, true>(p, x, y, z, (lo || hi) && p.labels != nullptr, e_sum,
+                                                             e_max);
+        if (lo || hi) {
+            // ... and the last of them to finish publishes this rank's counter (unless the sparse kernel of a masked
+            // step still has to touch the boundary planes: then IT publishes, general_nodes_kernel)
+            __threadfence_system();   // this thread's loads from / stores to the neighbour are performed
+            __syncthreads();
+            if (leader && p.sync.publish) {
+                const unsigned long long old = atomicAdd(p.sync.done + (lo ? 0 : 1), 1ULL);
+                if ((old + 1) % p.sync.ctas_per_side == 0) {
+                    __threadfence_system();
+                    *(volatile unsigned long long *)(lo ? p.sync.sig_lo : p.sync.sig_hi) = p.sync.signal_value;
+                }
             }
         }
+        if (p.reduce_mode != kReduceNone)
+            store_cta_partials(e_sum, e_max, p.energy_partials,
+                               (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, p.reduce_slots);
     }
-    if (p.reduce_mode != kReduceNone)
-        store_cta_partials(e_sum, e_max, p.energy_partials,
-                           (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, p.reduce_slots);
 }
 
 // ---------------------------------------------------------------------------
