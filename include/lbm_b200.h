@@ -138,9 +138,12 @@ typedef struct lbm_step_desc {
     int32_t streaming; /* lbm_streaming */
     int32_t n_ops;     /* 1 <= n_ops <= LBM_MAX_OPS */
     int32_t collision_index; /* index of the collision entry in ops (= number of pre-boundaries) */
-    int32_t variant;   /* nodes per thread of the bulk kernel: 0 = library default, 1, or 2 (two neighbouring nodes as
-                          one float2 on the packed fp32 pipe; used where that kernel exists: fp32, even contiguous
-                          extent, PRE / POST streaming).  Both give bit-identical results (csrc/lbm_vec.cuh). */
+    int32_t variant;   /* bulk kernel: 0 = library default; 1 or 2 = LDG/STG kernel with that many nodes per thread (two
+                          neighbouring nodes as one float2 on the packed fp32 pipe; used where that kernel exists:
+                          fp32, even contiguous extent, PRE / POST streaming); 3 = TMA-staged kernel (csrc/lbm_tma.cuh:
+                          fp32, PRE / NO streaming, contiguous extent a multiple of 64, single GPU; LBM_ERR_UNSUPPORTED
+                          otherwise).  All
+                          give bit-identical results (csrc/lbm_vec.cuh). */
     lbm_op ops[LBM_MAX_OPS];
     /* Masked runs (any boundary present): per-node label byte produced by
      * lbm_pack_masks() and one frozen-slot word per node (bit q set = slot (q,node) is

@@ -4,7 +4,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
+
+#include <cudaTypedefs.h>
 
 #include "lbm_launch.cuh"
 
@@ -78,7 +82,117 @@ static int chosen_lanes(const lbm_step_desc *d) {
     return 2;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged kernel (lbm_tma.cuh): which steps take it, and the tensor maps of their buffers.
+// lbm_step_desc::variant 3 asks for it, 1 / 2 for the LDG kernel; otherwise LBM_B200_TMA=0|1 decides, else the
+// default at the end of tma_wanted.  Steps that carry the slab lock step or fused reductions always run the LDG kernel.
+// ---------------------------------------------------------------------------------------------------------
+static bool tma_wanted(const lbm_step_desc *d) {
+    const bool two_d = d->lat.stencil == LBM_D2Q9;
+    const int n2 = two_d ? d->lat.ny : d->lat.nz;
+    const int64_t nodes = (int64_t)d->lat.nx * d->lat.ny * d->lat.nz;
+    if (!tma_available(d->lat.dtype, nodes, n2) || (d->streaming & LBM_POST_STREAMING)) return false;
+    const lbm_halo &h = d->halo;
+    if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return false;      // slabs: peer planes are not in the tensor
+    if (d->variant == 3) return true;
+    if (d->variant == 1 || d->variant == 2) return false;
+    if (const char *e = getenv("LBM_B200_TMA")) return e[0] != '0';
+    // Default: where it measured faster than the LDG kernel under sustained load (profiles/r2_tma_sweep.md) -- the
+    // entropic operator on D3Q27, whose LDG kernel is bound by its issue rate and by the power cap, not by HBM
+    // (512^3: 0.95 of the copy bandwidth instead of 0.86).  The bandwidth-bound operators are equal on D3Q27 and a
+    // few percent slower on the smaller velocity sets (shorter tiles, same per-tile overheads).
+    return d->lat.stencil == LBM_D3Q27 && d->ops[d->collision_index].kind == LBM_OP_KBC;
+}
+
+namespace {
+struct TmaMapSlot {
+    const void *ptr = nullptr;
+    int n0 = 0, n1 = 0, n2 = 0, q = 0, b0 = 0, b1 = 0, b2 = 0, device = -1;
+    CUtensorMap map;
+    uint64_t used = 0;
+};
+std::mutex g_tma_mutex;
+TmaMapSlot g_tma_slots[32];
+uint64_t g_tma_clock = 0;
+
+PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (PFN_cuTensorMapEncodeTiled)p;
+    }();
+    return fn;
+}
+
+// tensor map of one population buffer: fp32 [q][n0][n1][n2], box = (b0, b1, b2, 1) along (z, y, x, q); small LRU
+// cache (a simulation alternates between two buffers)
+int tensor_map_of(const void *ptr, int n0, int n1, int n2, int q, int b0, int b1, int b2, CUtensorMap *out) {
+    int device = -1;
+    if (cudaGetDevice(&device)) return LBM_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_tma_mutex);
+    TmaMapSlot *victim = &g_tma_slots[0];
+    for (TmaMapSlot &s : g_tma_slots) {
+        if (s.ptr == ptr && s.n0 == n0 && s.n1 == n1 && s.n2 == n2 && s.q == q && s.b0 == b0 && s.b1 == b1 &&
+            s.b2 == b2 && s.device == device) {
+            s.used = ++g_tma_clock;
+            *out = s.map;
+            return LBM_OK;
+        }
+        if (s.used < victim->used) victim = &s;
+    }
+    PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
+    if (!encode) return LBM_ERR_UNSUPPORTED;
+    const cuuint64_t dims[4] = {(cuuint64_t)n2, (cuuint64_t)n1, (cuuint64_t)n0, (cuuint64_t)q};
+    const cuuint64_t strides[3] = {(cuuint64_t)n2 * 4, (cuuint64_t)n1 * n2 * 4, (cuuint64_t)n0 * n1 * n2 * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return LBM_ERR_UNSUPPORTED;
+    victim->ptr = ptr; victim->n0 = n0; victim->n1 = n1; victim->n2 = n2; victim->q = q;
+    victim->b0 = b0; victim->b1 = b1; victim->b2 = b2;
+    victim->device = device; victim->map = m; victim->used = ++g_tma_clock;
+    *out = m;
+    return LBM_OK;
+}
+
+// tile counters of the TMA-staged kernel: two words per (device, stream), zero between launches (the kernel rearms
+// them itself), never freed
+unsigned *tma_counters_of(cudaStream_t stream) {
+    static std::mutex mutex;
+    static std::map<std::pair<int, cudaStream_t>, unsigned *> slots;
+    int device = -1;
+    if (cudaGetDevice(&device)) return nullptr;
+    std::lock_guard<std::mutex> lock(mutex);
+    auto it = slots.find({device, stream});
+    if (it != slots.end()) return it->second;
+    unsigned *p = nullptr;
+    if (cudaMalloc(&p, 2 * sizeof(unsigned)) || cudaMemset(p, 0, 2 * sizeof(unsigned))) return nullptr;
+    slots[{device, stream}] = p;
+    return p;
+}
+
+int device_sm_count() {
+    static int cached[64] = {};
+    int device = 0;
+    if (cudaGetDevice(&device) || device < 0 || device >= 64) return 148;
+    if (!cached[device]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) || n <= 0) n = 148;
+        cached[device] = n;
+    }
+    return cached[device];
+}
+}  // namespace
+
 static const char *step_variant_name(const lbm_step_desc *d, bool masked) {
+    if (tma_wanted(d)) return masked ? "step_tma_kernel<TMA-staged, 2 nodes/thread, packed fp32> + general_nodes" :
+                                       "step_tma_kernel<TMA-staged, 2 nodes/thread, packed fp32>";
     if (chosen_lanes(d) == 2) return masked ? "step_kernel<2 nodes/thread, packed fp32> + general_nodes" :
                                               "step_kernel<2 nodes/thread, packed fp32>";
     return masked ? "step_kernel<1 node/thread> + general_nodes" : "step_kernel<1 node/thread>";
@@ -256,6 +370,34 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     LaunchOptions opt;
     opt.lanes = chosen_lanes(d);
     opt.chained = x.chained;
+    TmaMaps maps;
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &capturing);      // (graph replays may run concurrently: they keep the LDG kernel)
+    if (!x.sync && !x.partials && tma_wanted(d) && capturing == cudaStreamCaptureStatusNone) {
+        const int tz = tma_row_extent(dm.n2), rows = tma_tile_rows(dm.n2);
+        const bool boxable = tma_rows_boxable(dm.n0, dm.n1, dm.n2);
+        const int by = dm.n1 > 1 ? rows : 1, bx = dm.n1 > 1 ? 1 : rows;      // rows run along y (3-D) or x (2-D)
+        int rc = tensor_map_of(f_in, dm.n0, dm.n1, dm.n2, dm.q, tz, 1, 1, &maps.in_row);
+        if (!rc) rc = tensor_map_of(f_out, dm.n0, dm.n1, dm.n2, dm.q, tz, 1, 1, &maps.out_row);
+        if (boxable) {
+            if (!rc) rc = tensor_map_of(f_in, dm.n0, dm.n1, dm.n2, dm.q, tz, by, bx, &maps.in_box);
+            if (!rc) rc = tensor_map_of(f_in, dm.n0, dm.n1, dm.n2, dm.q, 4, by, bx, &maps.in_halo);
+            if (!rc) rc = tensor_map_of(f_out, dm.n0, dm.n1, dm.n2, dm.q, tz, by, bx, &maps.out_box);
+        } else {
+            maps.in_box = maps.in_halo = maps.in_row;                         // never used
+            maps.out_box = maps.out_row;
+        }
+        if (!rc && !(opt.tma_counters = tma_counters_of(st))) rc = LBM_ERR_CUDA;
+        if (!rc) {
+            opt.tma = &maps;
+            opt.tma_boxable = boxable ? 1 : 0;
+            opt.sm_count = device_sm_count();
+        } else if (d->variant == 3) {
+            return rc;                      // asked for explicitly: no silent change of kernel
+        }
+    } else if (d->variant == 3 && (x.sync || x.partials || !tma_wanted(d))) {
+        if (!x.sync && !x.partials) return LBM_ERR_UNSUPPORTED;
+    }
     return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, opt, st));
 }
 

@@ -5,6 +5,7 @@
 #include <atomic>
 
 #include "lbm_step.cuh"
+#include "lbm_tma.cuh"
 
 namespace lbm {
 
@@ -37,10 +38,33 @@ inline int reduce_slots_for(int n0, int n1, int n2, int lanes, int64_t n_general
 }
 
 struct LaunchOptions {
+    const TmaMaps *tma = nullptr;   // tensor maps of (f_in, f_out): run the TMA-staged kernel (lbm_tma.cuh) when the
+                                    // step carries neither the slab lock step nor fused reductions
+    int tma_boxable = 0;            // the box / halo maps are valid (tma_rows_boxable)
+    unsigned *tma_counters = nullptr;   // two zeroed words in device memory: the kernel's tile counter (lbm_tma.cuh)
+    int sm_count = 148;
     int lanes;        // 1, or 2 (fp32, even n2, PRE / POST streaming): nodes per thread of the bulk kernel
     bool chained;     // the previous launch on the stream is a step kernel of this library: launch behind it with
                       // programmatic stream serialization (it released its dependents, see step_kernel)
 };
+
+// true when the TMA-staged kernel can run this lattice: fp32, contiguous extent a multiple of 64 (the tile rows are
+// power-of-two boxes that divide it; 16-byte global strides), and enough nodes to fill the persistent grid
+inline bool tma_available(int dtype, int64_t nodes, int n2) {
+    return dtype == LBM_F32 && n2 % 64 == 0 && nodes >= (int64_t)kTmaTileNodes * 148;
+}
+inline int tma_row_extent(int n2) {                 // largest power of two <= 256 that divides n2
+    int tz = 64;
+    while (tz < 256 && n2 % (2 * tz) == 0) tz *= 2;
+    return tz;
+}
+
+inline int tma_tile_rows(int n2) { return kTmaTileNodes / tma_row_extent(n2); }
+// the rows of a full tile are consecutive along ONE axis (y in 3-D, x in 2-D) and never straddle it
+inline bool tma_rows_boxable(int n0, int n1, int n2) {
+    const int rows = tma_tile_rows(n2);
+    return n1 > 1 ? n1 % rows == 0 : n0 % rows == 0;
+}
 
 // true when the two-nodes-per-thread kernel exists for this request (instantiated for float, PRE and POST streaming)
 inline bool lanes2_available(int dtype, int streaming, int n2) {

@@ -141,8 +141,8 @@ LBM_D const uint8_t *label_plane(const StepParams<R> &p, int x) {
 LBM_D int wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
 
 // the collision entry of the transformer list applied to the node (V = R) or the two nodes (V = float2) held in f
-template <class S, class V, int COLL>
-LBM_D void collide_lanes(const StepParams<scalar_t<V>> &p, V (&f)[S::Q]) {
+template <class S, class V, int COLL, class P>
+LBM_D void collide_lanes(const P &p, V (&f)[S::Q]) {
     if constexpr (COLL == LBM_OP_BGK_FORCED) collide_bgk_forced<S, V>(f, p.ca, p.force);
     else Collide<S, V, COLL>::apply(f, p.ca, p.cb);
 }

@@ -77,6 +77,7 @@ def report(name, flow, sim, steps=50, warmup=5, **extra):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c2", "c3", "c4", "c5"]
     small = "--small" in sys.argv
+    pre_only = "--pre-only" in sys.argv
     S = lt.StreamingStrategy
     f32, f64 = torch.float32, torch.float64
     for case in args:
@@ -89,7 +90,7 @@ def main():
             print(json.dumps(dict(case="C1 via Simulation.__call__(1000)", mlups=m, wall_s=dt)), flush=True)
         elif case == "c2":
             for n in ((256,) if small else (256, 512)):
-                for strat in (S.PRE_STREAMING, S.POST_STREAMING):
+                for strat in ((S.PRE_STREAMING,) if pre_only else (S.PRE_STREAMING, S.POST_STREAMING)):
                     ctx = lt.Context("cuda", dtype=f32)
                     flow = lt.TaylorGreenVortex(ctx, [n] * 3, 1600.0, 0.05, stencil=lt.D3Q19())
                     sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], strat)
@@ -98,7 +99,7 @@ def main():
                     gc.collect(); torch.cuda.empty_cache()
         elif case == "c3":
             for n in ((256,) if small else (256, 512)):
-                for strat in (S.PRE_STREAMING, S.POST_STREAMING):
+                for strat in ((S.PRE_STREAMING,) if pre_only else (S.PRE_STREAMING, S.POST_STREAMING)):
                     ctx = lt.Context("cuda", dtype=f32)
                     flow = lt.TaylorGreenVortex(ctx, [n] * 3, 1600.0, 0.05, stencil=lt.D3Q27())
                     sim = lt.Simulation(flow, lt.KBCCollision(), [], strat)
@@ -106,8 +107,8 @@ def main():
                     del flow, sim
                     gc.collect(); torch.cuda.empty_cache()
         elif case == "c4":
-            for dt_ in (f32, f64):
-                for strat in (S.POST_STREAMING, S.PRE_STREAMING):
+            for dt_ in ((f32,) if pre_only else (f32, f64)):
+                for strat in ((S.PRE_STREAMING,) if pre_only else (S.POST_STREAMING, S.PRE_STREAMING)):
                     ctx = lt.Context("cuda", dtype=dt_)
                     flow = make_obstacle(ctx, [4096, 1024], lt.D2Q9())
                     sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], strat)
@@ -117,7 +118,7 @@ def main():
                     del flow, sim, eng
         elif case == "c5":
             res = [512, 256, 256] if small else [1024, 512, 512]
-            for strat in (S.POST_STREAMING, S.PRE_STREAMING):
+            for strat in ((S.PRE_STREAMING,) if pre_only else (S.POST_STREAMING, S.PRE_STREAMING)):
                 ctx = lt.Context("cuda", dtype=f32)
                 flow = make_obstacle(ctx, res, lt.D3Q27())
                 torch.cuda.empty_cache()
@@ -157,6 +158,8 @@ def main():
         elif case == "extra":
             for st, coll, dt_ in ((lt.D3Q27, "bgk", f32), (lt.D3Q27, "trt", f32), (lt.D3Q19, "bgk", f64),
                                   (lt.D3Q19, "trt", f32), (lt.D3Q27, "kbc", f64)):
+                if pre_only and dt_ == f64:
+                    continue
                 ctx = lt.Context("cuda", dtype=dt_)
                 flow = lt.TaylorGreenVortex(ctx, [256] * 3, 1600.0, 0.05, stencil=st())
                 tau = flow.units.relaxation_parameter_lu

@@ -259,5 +259,5 @@ def test_boundary_call_contract():
         assert res_t is flow.f
         got = flow.f.cpu().numpy()
         want = f0.copy()
-        want[:, -1] = lo.equilibrium(st, np.full_like(rho_f[:, -2], 1.02), u_f[:, -2])
+        want[:, -1] = lo.equilibrium(st, np.full_like(rho_f[-2], 1.02), u_f[:, -2])
         assert max_rel(got, want) < 1e-13

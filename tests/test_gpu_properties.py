@@ -392,6 +392,69 @@ def test_two_nodes_per_thread_kernel_is_bit_identical(stencil, res, coll, strate
     assert torch.equal(flows[0].f, flows[1].f)
 
 
+@pytest.mark.parametrize("stencil,res,coll", [("D3Q27", [12, 10, 640], "kbc"), ("D3Q19", [37, 9, 256], "bgk"),
+                                              ("D2Q9", [300, 320], "trt"), ("D3Q27", [24, 24, 192], "trt"),
+                                              ("D2Q9", [2048, 64], "kbc"), ("D3Q19", [5, 70, 512], "regularized"),
+                                              ("D3Q27", [16, 16, 320], "kbc"), ("D3Q19", [12, 32, 256], "bgk")])
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING"])
+def test_tma_staged_kernel_is_bit_identical(stencil, res, coll, strategy):
+    """the TMA-staged persistent kernel (csrc/lbm_tma.cuh: bulk tensor loads of rows shifted in x and y, halo quads
+    for the shift along z, partial last tile, several z chunks per row) against the one-node LDG kernel: same bits,
+    it only moves data differently"""
+    from lettuce_b200 import native as nv
+    from test_gpu_parity import make_collision
+    c = ctx(torch.float32)
+    flows = []
+    for variant in (1, 3):
+        flow = lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=STENCILS[stencil]())
+        gen = torch.Generator(device=flow.f.device).manual_seed(11)
+        flow.f.mul_(1.0 + 1e-2 * (torch.rand(flow.f.shape, generator=gen, device=flow.f.device) - 0.5))
+        sim = lt.Simulation(flow, make_collision(coll, flow), [], lt.StreamingStrategy[strategy])
+        eng = nv.engine_of(sim)
+        eng.desc.variant = variant
+        assert ("TMA" in eng.lib.lbm_step_variant_name(eng.desc).decode()) == (variant == 3)
+        nv.invoke_n(sim, 5)
+        flows.append(flow)
+    assert torch.equal(flows[0].f, flows[1].f)
+
+
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING"])
+def test_tma_staged_kernel_with_boundaries(strategy):
+    from lettuce_b200 import native as nv
+    from test_gpu_parity import ObstacleEqOut, make_obstacle
+    c = ctx(torch.float32)
+    for stencil, res, coll in ((lt.D2Q9, [1200, 64], "bgk"), (lt.D3Q27, [48, 32, 64], "trt")):
+        out = []
+        for variant in (1, 3):
+            flow = make_obstacle(ObstacleEqOut, c, res, stencil())
+            tau = flow.units.relaxation_parameter_lu
+            sim = lt.Simulation(flow, lt.BGKCollision(tau) if coll == "bgk" else lt.TRTCollision(tau), [],
+                                lt.StreamingStrategy[strategy])
+            eng = nv.engine_of(sim)
+            eng.desc.variant = variant
+            assert ("TMA" in eng.lib.lbm_step_variant_name(eng.desc).decode()) == (variant == 3)
+            nv.invoke_n(sim, 9)
+            out.append(flow.f)
+        assert torch.equal(out[0], out[1])
+
+
+def test_tma_staged_kernel_refuses_what_it_cannot_run():
+    """variant 3 is an explicit request: a lattice it cannot stage (contiguous extent not a multiple of 32) or a
+    pushing step is an error, never a silent change of kernel"""
+    from lettuce_b200 import native as nv
+    c = ctx(torch.float32)
+    for res, strategy in (([64, 48, 100], "PRE_STREAMING"), ([64, 48, 128], "POST_STREAMING")):
+        flow = lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=lt.D3Q19())
+        sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [],
+                            lt.StreamingStrategy[strategy])
+        eng = nv.engine_of(sim)
+        eng.desc.variant = 3
+        with pytest.raises(RuntimeError):
+            nv.invoke_n(sim, 1)
+        eng.desc.variant = 0
+        nv.invoke_n(sim, 1)
+
+
 @pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
 def test_two_nodes_per_thread_kernel_with_boundaries(strategy):
     from lettuce_b200 import native as nv
