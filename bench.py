@@ -71,8 +71,13 @@ def ncu_traffic(config: str, size: int, strategy: str):
         return None, None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_dram_{config}_{size}_{tag}.csv")), reverse=True):
         try:
+            rows = {}
             with open(path) as fh:
-                rows = {r["metric"]: float(r["value"]) for r in csv.DictReader(fh)}
+                for r in csv.DictReader(fh):
+                    try:
+                        rows[r["metric"]] = float(r["value"])
+                    except ValueError:
+                        pass                                   # the kernel-name rows
             return rows["dram__bytes_read.sum"] + rows["dram__bytes_write.sum"], os.path.relpath(path, ROOT)
         except Exception:
             continue

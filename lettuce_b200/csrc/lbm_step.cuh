@@ -382,7 +382,7 @@ LBM_D void accumulate_kinetic(const V (&f)[S::Q], const bool (&take)[2], double 
 // (block-uniform; the cut planes of a multi-GPU slab) makes the general nodes skip their stores instead: a wrong store
 // into the NEIGHBOUR's memory could land after the neighbour's sparse kernel has written the right value there
 // (nothing orders the two ranks' kernels within a step), so across a cut every slot keeps exactly one writer.
-template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES, bool EXTRAS>
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES, bool EXTRAS>   // EXTRAS: labels / reductions
 LBM_D void node_update(const StepParams<R> &p, int x, int y, int z, bool single_writer, double &e_sum, double &e_max) {
     constexpr int Q = S::Q;
     using V = typename LaneVec<R, LANES>::type;
@@ -509,10 +509,13 @@ LBM_D void store_cta_partials(double e_sum, double e_max, double *partials, int 
     }
 }
 
-// EXTRAS = false is the plain step (no slab lock step, no fused reductions: nothing but gather, collide, scatter);
-// EXTRAS = true carries both as run-time options.  Two instantiations so that the options cost the plain kernel
-// neither instructions nor registers.
-template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES, bool EXTRAS>
+// Three instantiations, so that the run-time options cost the plain kernel neither instructions nor registers:
+//   kStepPlain   nothing but gather, collide, scatter
+//   kStepSync    + the slab lock step (multi-GPU, unmasked lattices, no reductions): what a slab step normally is
+//   kStepFull    + fused reductions and, on masked slabs, single-writer cut planes
+enum : int { kStepPlain = 0, kStepSync = 1, kStepFull = 2 };
+
+template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES, int MODE>
 __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_blocks_per_sm<S, R, COLL, LANES>()))
     step_kernel(const __grid_constant__ StepParams<R> p) {
     // (no-op unless THIS grid was launched programmatically behind the previous step: then the grid in front has to
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_bloc
     const int z = (blockIdx.x * blockDim.x + threadIdx.x) * LANES;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     double e_sum = 0.0, e_max = 0.0;
-    if constexpr (!EXTRAS) {
+    if constexpr (MODE == kStepPlain) {
         const int x = reverse ? p.n0 - 1 - (int)blockIdx.z : (int)blockIdx.z;
         if (z < p.n2 && y < p.n1) node_update<S, R, COLL, PULL, PUSH, LANES, false>(p, x, y, z, false, e_sum, e_max);
     } else {
@@ -544,9 +547,13 @@ __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_bloc
             }
             __syncthreads();
         }
-        if (z < p.n2 && y < p.n1)
-            node_update<S, R, COLL, PULL, PUSH, LANES, true>(p, x, y, z, (lo || hi) && p.labels != nullptr, e_sum,
-                                                             e_max);
+        if (z < p.n2 && y < p.n1) {
+            if constexpr (MODE == kStepFull)
+                node_update<S, R, COLL, PULL, PUSH, LANES, true>(p, x, y, z, (lo || hi) && p.labels != nullptr, e_sum,
+                                                                 e_max);
+            else
+                node_update<S, R, COLL, PULL, PUSH, LANES, false>(p, x, y, z, false, e_sum, e_max);
+        }
         if (lo || hi) {
             // ... and the last of them to finish publishes this rank's counter (unless the sparse kernel of a masked
             // step still has to touch the boundary planes: then IT publishes, general_nodes_kernel)
@@ -560,9 +567,11 @@ __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_bloc
                 }
             }
         }
-        if (p.reduce_mode != kReduceNone)
-            store_cta_partials(e_sum, e_max, p.energy_partials,
-                               (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, p.reduce_slots);
+        if constexpr (MODE == kStepFull) {
+            if (p.reduce_mode != kReduceNone)
+                store_cta_partials(e_sum, e_max, p.energy_partials,
+                                   (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, p.reduce_slots);
+        }
     }
 }
 

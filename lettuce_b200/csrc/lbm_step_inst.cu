@@ -59,10 +59,13 @@ int launch_lanes(const StepParams<R> &p_in, const LaunchOptions &opt, cudaStream
         p.sync.ctas_per_side = grid.x * grid.y * ((PULL && PUSH) ? 2 : 1);
         p.sync.publish = sparse ? 0 : 1;
     }
-    // the plain kernel unless the step carries the slab lock step or fused reductions
-    void (*bulk)(const StepParams<R>) = (p.sync.on || p.reduce_mode != kReduceNone)
-                                            ? step_kernel<S, R, COLL, PULL, PUSH, LANES, true>
-                                            : step_kernel<S, R, COLL, PULL, PUSH, LANES, false>;
+    // the plain kernel unless the step carries the slab lock step (kStepSync) or fused reductions / a masked slab's
+    // single-writer cut planes (kStepFull)
+    void (*bulk)(const StepParams<R>) =
+        (p.reduce_mode != kReduceNone || (p.sync.on && p.labels != nullptr))
+            ? step_kernel<S, R, COLL, PULL, PUSH, LANES, kStepFull>
+            : (p.sync.on ? step_kernel<S, R, COLL, PULL, PUSH, LANES, kStepSync>
+                         : step_kernel<S, R, COLL, PULL, PUSH, LANES, kStepPlain>);
     int e;
     if (opt.chained) {
         e = launch_dependent<R>(bulk, grid, block, p, stream);

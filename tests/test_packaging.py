@@ -50,3 +50,14 @@ def test_shipped_library_was_built_from_the_current_sources():
     assert os.path.exists(build.STAMP), "liblbm_b200.so has no source stamp"
     with open(build.STAMP) as fh:
         assert fh.read().strip() == build.source_digest(), "liblbm_b200.so is older than csrc/ or include/"
+
+
+def test_packed_fp32_operators_are_free_of_ptxas_contractions():
+    """ptxas fuses `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 (never the scalar forms): the two-nodes-per-thread
+    kernels equal the one-node kernels bit for bit only while every fusable multiply-add in csrc/lbm_core.cuh is
+    spelled vfma.  The checker compiles every operator for float2 and compares PTX with SASS (no GPU needed)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_packed_contraction.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
