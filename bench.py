@@ -297,6 +297,9 @@ def gpu_main(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries the JSON line only: NCCL's version / debug output (NCCL_DEBUG is set on the GPU boxes) goes
+        # to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     c = CONFIGS[args.config]
     bytes_per_node = 2 * c["q"] * 4          # every population read once and written once

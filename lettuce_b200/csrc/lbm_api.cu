@@ -87,13 +87,19 @@ static int chosen_lanes(const lbm_step_desc *d) {
 // lbm_step_desc::variant 3 asks for it, 1 / 2 for the LDG kernel; otherwise LBM_B200_TMA=0|1 decides, else the
 // default at the end of tma_wanted.  Steps that carry the slab lock step or fused reductions always run the LDG kernel.
 // ---------------------------------------------------------------------------------------------------------
-static bool tma_wanted(const lbm_step_desc *d) {
+static bool tma_wanted(const lbm_step_desc *d, bool slab = false) {
     const bool two_d = d->lat.stencil == LBM_D2Q9;
     const int n2 = two_d ? d->lat.ny : d->lat.nz;
     const int64_t nodes = (int64_t)d->lat.nx * d->lat.ny * d->lat.nz;
     if (!tma_available(d->lat.dtype, nodes, n2) || (d->streaming & LBM_POST_STREAMING)) return false;
     const lbm_halo &h = d->halo;
-    if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) return false;      // slabs: peer planes are not in the tensor
+    // slabs: the neighbours' planes are not in the tensor -- the staged kernel takes the interior planes only, of
+    // unmasked pulling steps (lbm_step_inst.cu); otherwise the peer planes rule it out
+    if (slab) {
+        if (d->labels || d->streaming != LBM_PRE_STREAMING || d->lat.nx < 4) return false;
+    } else if (h.in_lo || h.in_hi || h.out_lo || h.out_hi) {
+        return false;
+    }
     if (d->variant == 3) return true;
     if (d->variant == 1 || d->variant == 2) return false;
     if (const char *e = getenv("LBM_B200_TMA")) return e[0] != '0';
@@ -373,7 +379,8 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     TmaMaps maps;
     cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &capturing);      // (graph replays may run concurrently: they keep the LDG kernel)
-    if (!x.sync && !x.partials && tma_wanted(d) && capturing == cudaStreamCaptureStatusNone) {
+    const bool slab_step = x.sync != nullptr && x.sync->on;
+    if (!x.partials && tma_wanted(d, slab_step) && capturing == cudaStreamCaptureStatusNone) {
         const int tz = tma_row_extent(dm.n2), rows = tma_tile_rows(dm.n2);
         const bool boxable = tma_rows_boxable(dm.n0, dm.n1, dm.n2);
         const int by = dm.n1 > 1 ? rows : 1, bx = dm.n1 > 1 ? 1 : rows;      // rows run along y (3-D) or x (2-D)
@@ -390,13 +397,14 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
         if (!rc && !(opt.tma_counters = tma_counters_of(st))) rc = LBM_ERR_CUDA;
         if (!rc) {
             opt.tma = &maps;
+            opt.tma_interior = slab_step;
             opt.tma_boxable = boxable ? 1 : 0;
             opt.sm_count = device_sm_count();
         } else if (d->variant == 3) {
             return rc;                      // asked for explicitly: no silent change of kernel
         }
-    } else if (d->variant == 3 && (x.sync || x.partials || !tma_wanted(d))) {
-        if (!x.sync && !x.partials) return LBM_ERR_UNSUPPORTED;
+    } else if (d->variant == 3 && !x.sync && !x.partials) {
+        return LBM_ERR_UNSUPPORTED;
     }
     return cuda_fail(launch_step<S, R>(p, d->ops[d->collision_index].kind, d->streaming, opt, st));
 }

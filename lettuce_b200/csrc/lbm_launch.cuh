@@ -41,6 +41,7 @@ struct LaunchOptions {
     const TmaMaps *tma = nullptr;   // tensor maps of (f_in, f_out): run the TMA-staged kernel (lbm_tma.cuh) when the
                                     // step carries neither the slab lock step nor fused reductions
     int tma_boxable = 0;            // the box / halo maps are valid (tma_rows_boxable)
+    bool tma_interior = false;      // multi-GPU slab: cut planes by the LDG lock-step kernel, interior planes staged
     unsigned *tma_counters = nullptr;   // two zeroed words in device memory: the kernel's tile counter (lbm_tma.cuh)
     int sm_count = 148;
     int lanes;        // 1, or 2 (fp32, even n2, PRE / POST streaming): nodes per thread of the bulk kernel

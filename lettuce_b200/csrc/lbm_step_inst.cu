@@ -44,10 +44,12 @@ int launch_dependent(void (*kernel)(const StepParams<R>), dim3 grid, dim3 block,
 // two nodes were computed with scalar arithmetic (4096x1024 fp32: 65.8 GLUPS vs 64.6); LANES = 2 here means the
 // packed float2 arithmetic of lbm_vec.cuh, which halves the fp32 issue slots.
 template <class S, class R, int COLL, bool PULL, bool PUSH, int LANES>
-int launch_lanes(const StepParams<R> &p_in, const LaunchOptions &opt, cudaStream_t stream) {
+int launch_lanes(const StepParams<R> &p_in, const LaunchOptions &opt, cudaStream_t stream, bool cut_planes_only = false) {
     StepParams<R> p = p_in;
     dim3 grid, block;
     bulk_geometry(p.n0, p.n1, p.n2, LANES, bulk_threads<S, R, COLL, LANES>(), grid, block);
+    // (slab lock step: the first 2 W grid layers are the cut planes, sync_plane)
+    if (cut_planes_only) grid.z = (PULL && PUSH) ? 4 : 2;
     const bool sparse = p.labels != nullptr && p.n_general > 0;
     const int bulk_ctas = (int)(grid.x * grid.y * grid.z);
     if (p.reduce_mode != kReduceNone) {
@@ -112,8 +114,11 @@ int launch_tma(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_
     while ((1 << t.tz_log2) < t.tz) ++t.tz_log2;
     t.rows = kTmaTileNodes / t.tz;
     t.zchunks = p.n2 / t.tz;
-    t.n_rows = p.n0 * p.n1;
-    t.n_tiles = ((t.n_rows + t.rows - 1) / t.rows) * t.zchunks;
+    // a slab's cut planes (x = 0 and x = n0 - 1) are left to the lock-step kernel
+    t.row_begin = opt.tma_interior ? p.n1 : 0;
+    t.n_rows = p.n0 * p.n1 - t.row_begin;
+    t.n_tiles = ((t.n_rows - t.row_begin + t.rows - 1) / t.rows) * t.zchunks;
+    t.skip_wait = opt.tma_interior ? 1 : 0;
     t.stages = stages;
     t.boxable = opt.tma_boxable;
     t.reverse = p.reverse_sweep;
@@ -127,7 +132,7 @@ int launch_tma(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
-    cfg.numAttrs = opt.chained ? 1 : 0;
+    cfg.numAttrs = (opt.chained || opt.tma_interior) ? 1 : 0;
     const int e = (int)cudaLaunchKernelEx(&cfg, kernel, *opt.tma, t);
     ++g_launch_count;
     return e;
@@ -136,6 +141,19 @@ int launch_tma(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_
 template <class S, class R, int COLL, bool PULL, bool PUSH>
 int by_lanes(const StepParams<R> &p, const LaunchOptions &opt, cudaStream_t stream) {
     if constexpr (sizeof(R) == 4 && !PUSH) {
+        if (opt.tma && opt.tma_interior && p.sync.on && p.reduce_mode == kReduceNone && p.labels == nullptr) {
+            // Multi-GPU slab: the two cut planes by the lock-step LDG kernel (it waits for the neighbours' progress
+            // counters, reads their planes over NVLink and publishes this rank's counter), the interior planes by the
+            // staged kernel, launched programmatically behind it: it becomes resident as soon as every cut-plane CTA
+            // has started (i.e. the previous step is complete) and runs next to them.
+            LaunchOptions o = opt;
+            o.chained = false;
+            int e;
+            if (o.lanes == 2 && p.n2 % 2 == 0) e = launch_lanes<S, R, COLL, PULL, PUSH, 2>(p, o, stream, true);
+            else e = launch_lanes<S, R, COLL, PULL, PUSH, 1>(p, o, stream, true);
+            if (e) return e;
+            return launch_tma<S, COLL, PULL>(p, opt, stream);
+        }
         if (opt.tma && !p.sync.on && p.reduce_mode == kReduceNone) {
             int e = launch_tma<S, COLL, PULL>(p, opt, stream);
             if (e || !(p.labels != nullptr && p.n_general > 0)) return e;

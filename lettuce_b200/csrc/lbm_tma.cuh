@@ -54,8 +54,11 @@ struct TmaParams {
     int tz, tz_log2;          // z extent of a tile row (box width), a power of two dividing n2
     int rows;                 // tile rows: kTmaTileNodes / tz consecutive (x, y) rows
     int zchunks;              // n2 / tz
-    int n_rows;               // n0 * n1
+    int row_begin, n_rows;    // rows (x * n1 + y) this launch covers: [row_begin, n_rows); the whole lattice, or
+                              // the interior planes of a multi-GPU slab (its cut planes need the neighbours)
     int n_tiles;
+    int skip_wait;            // launched behind a kernel of the SAME step (slab: the cut-plane kernel): do not wait
+                              // for that grid to complete, its start already implies that the previous step is done
     int stages;
     int boxable;              // a full tile never straddles two planes (3-D) / rows divide n0 (2-D): box maps usable
     int reverse;              // sweep the tiles backwards (L2 reuse between consecutive steps)
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
     if (threadIdx.x == 0 && (tma::smem_addr(stage0) & 127u)) __trap();
 
     // (see step_kernel: complete the step in front, then let the kernel behind become resident)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!p.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int NS = p.stages;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
                 const int t = p.reverse ? p.n_tiles - 1 - (int)k : (int)k;
                 const int zc = t % p.zchunks;
                 info.z0 = zc << p.tz_log2;
-                info.r0 = (t / p.zchunks) * p.rows;
+                info.r0 = p.row_begin + (t / p.zchunks) * p.rows;
                 info.x0 = info.r0 / p.n1;
                 info.y0 = info.r0 - info.x0 * p.n1;
             }

@@ -146,10 +146,13 @@ def gpu_main():
              (lt.D3Q27, [19, 16, 24], "trt", S.DOUBLE_STREAMING, torch.float32, 8),
              (lt.D2Q9, [48, 40], "bgk", S.PRE_STREAMING, torch.float64, 10),
              (lt.D2Q9, [50, 32], "kbc", S.POST_STREAMING, torch.float32, 10),
-             (lt.D3Q19, [world * 2, 16, 32], "bgk", S.POST_STREAMING, torch.float32, 7)]
+             (lt.D3Q19, [world * 2, 16, 32], "bgk", S.POST_STREAMING, torch.float32, 7),
+             # large enough for the TMA-staged kernel: interior planes staged, cut planes by the lock-step kernel
+             (lt.D3Q27, [world * 8, 32, 320], "kbc", S.PRE_STREAMING, torch.float32, 7),
+             (lt.D3Q27, [world * 8 + 1, 40, 256], "kbc", S.PRE_STREAMING, torch.float32, 6)]
     ok = all([gpu_case(*c, rank, world, dev) for c in cases])
     # reports after every step: energy and maximum velocity are reduced inside the slab step kernels
-    ok = all([gpu_case(*c, rank, world, dev, every=1) for c in cases[:2] + cases[4:6]]) and ok
+    ok = all([gpu_case(*c, rank, world, dev, every=1) for c in cases[:2] + cases[4:6] + cases[7:8]]) and ok
     ocases = [(lt.D2Q9, [64, 32], "bgk", S.POST_STREAMING, torch.float64, 12, False),
               (lt.D2Q9, [64, 32], "bgk", S.PRE_STREAMING, torch.float32, 12, False),
               (lt.D3Q27, [32, 16, 16], "trt", S.POST_STREAMING, torch.float32, 9, False),
