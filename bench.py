@@ -297,10 +297,19 @@ def gpu_main(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        # stdout carries the JSON line only: NCCL's version / debug output (NCCL_DEBUG is set on the GPU boxes) goes
-        # to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the JSON line only: whatever NCCL prints while the communicator comes up (its version line,
+        # debug output when NCCL_DEBUG is set on the box) is sent to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     c = CONFIGS[args.config]
     bytes_per_node = 2 * c["q"] * 4          # every population read once and written once
     strategy = lt.StreamingStrategy[args.strategy]
