@@ -181,6 +181,14 @@ int lbm_step_moments_state(const lbm_step_desc *desc);
 size_t lbm_step_moments_scratch_bytes(const lbm_step_desc *desc);
 int lbm_step_moments(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, void *d_scratch,
                      size_t scratch_bytes, double *d_result, void *stream);
+/* n consecutive steps (populations alternate between d_f_a and d_f_b like lbm_step_n), every one with the fused
+ * reductions: d_results[2 k], d_results[2 k + 1] = (sum 0.5|u|^2, max |u|^2) of the state AFTER step k + 1, for
+ * k < n when the steps describe the state they write (LBM_MOMENTS_OF_OUTPUT) and for k < n - 1 when they describe the
+ * state they read (LBM_MOMENTS_OF_INPUT: the last state's moments would need a step n + 1; the caller reduces it with
+ * lbm_reduce or lets the next batch deliver it).  A reporter with interval 1
+ * (lettuce/ext/_reporter/observable_reporter.py:185-200) costs one library call per batch instead of one per step. */
+int lbm_step_moments_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *d_scratch,
+                       size_t scratch_bytes, double *d_results, void *stream);
 
 /* Link-wise bounce-back boundaries applied AFTER streaming -- the "efficient bounce-back" boundaries of the
  * reference's example project examples/advanced_projects/efficient_bounce_back_obstacle: its EbbSimulation runs

@@ -140,6 +140,16 @@ class Simulation:
             k = min(k, interval - self.flow.i % interval)
         return max(k, 1)
 
+    def _reports_ride_on_every_step(self) -> bool:
+        """all reporters have interval 1 and accept the step kernels' own reductions for whole batches"""
+        if self._collide_and_stream is not native.invoke or not self.reporter or not self.flow.f.is_cuda:
+            return False
+        if not all(callable(getattr(r, "accepts_fused_batches", None)) and r.accepts_fused_batches(self)
+                   for r in self.reporter):
+            return False
+        engine = native.engine_of(self)
+        return type(engine) is native.Engine and engine.moments_state() != native.MOMENTS_UNAVAILABLE
+
     def _fused_reporters_due(self, k: int):
         """(any, all): `k` steps from now, does ANY due reporter evaluate an observable that the step kernels can
         reduce on the fly (`fused_with_step`: IncompressibleKineticEnergy / MaximumVelocity of this flow), and are
@@ -168,6 +178,17 @@ class Simulation:
             self._report()
         remaining = int(num_steps)
         ahead = 0                       # 1 when flow.f is already one step ahead of flow.i (see above)
+        if remaining >= 2 and self._reports_ride_on_every_step():
+            # every reporter wants every step and nothing but moments the step kernels reduce themselves: the whole
+            # run is ONE library call (lbm_step_moments_n), the reporters take their rows from its result
+            engine = native.engine_of(self)
+            moments = engine.steps_with_moments(remaining)
+            for reporter in self.reporter:
+                reporter.ingest_fused_batch(self, self.flow.i + 1, moments)
+            self.flow.i += remaining
+            if len(moments) < remaining:            # POST streaming: the last state is reduced on its own
+                self._report()
+            remaining = 0
         while remaining > 0:
             k = self._batch_length(remaining)
             todo = k - ahead

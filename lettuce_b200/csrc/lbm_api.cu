@@ -598,6 +598,28 @@ int lbm_step_moments(const lbm_step_desc *desc, const void *d_f_in, void *d_f_ou
     return step_moments_general(desc, d_f_in, d_f_out, nullptr, d_scratch, scratch_bytes, d_result, false, stream);
 }
 
+int lbm_step_moments_n(const lbm_step_desc *desc, void *d_f_a, void *d_f_b, int64_t n, void *d_scratch,
+                       size_t scratch_bytes, double *d_results, void *stream) {
+    if (n < 0 || !desc || !d_results) return LBM_ERR_BAD_ARGUMENT;
+    const int state = lbm_step_moments_state(desc);
+    if (state == LBM_MOMENTS_UNAVAILABLE) return LBM_ERR_UNSUPPORTED;
+    void *a = d_f_a, *b = d_f_b;
+    for (int64_t k = 0; k < n; ++k) {
+        int rc;
+        if (state == LBM_MOMENTS_OF_OUTPUT) {
+            rc = step_moments_general(desc, a, b, nullptr, d_scratch, scratch_bytes, d_results + 2 * k, k > 0, stream);
+        } else if (k == 0) {
+            rc = lbm_step(desc, a, b, stream);       // describes the caller's state: nothing to report
+        } else {
+            rc = step_moments_general(desc, a, b, nullptr, d_scratch, scratch_bytes, d_results + 2 * (k - 1), true,
+                                      stream);
+        }
+        if (rc) return rc;
+        void *t = a; a = b; b = t;
+    }
+    return LBM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // CUDA-graph replay of step batches on small lattices.  Below a few hundred thousand nodes one step takes a few
 // microseconds and the loop is bound by launch latency; kGraphSteps consecutive steps (a -> b -> a ...) are

@@ -39,6 +39,10 @@ class MaximumVelocity(Observable):
         u_max = torch.sqrt(fused[1]) if fused is not None else native.reduce(self.flow.stencil, native.MAX_U, f)
         return self.flow.units.convert_velocity_to_pu(u_max)
 
+    def from_fused_moments(self, moments):
+        """values of a whole batch of steps from the rows (sum 0.5|u|^2, max |u|^2) the step kernels reduced"""
+        return self.flow.units.convert_velocity_to_pu(torch.sqrt(moments[:, 1]))
+
 
 class IncompressibleKineticEnergy(Observable):
     """sum 0.5 |u|^2 dx^d in physical units (observable_reporter.py:34-42).  `fused_with_step`: when a reporter
@@ -53,6 +57,11 @@ class IncompressibleKineticEnergy(Observable):
         fused = native.fused_moments(self.flow, f)            # reduced inside a step kernel?
         e_lu = fused[0] if fused is not None else native.reduce(self.flow.stencil, native.SUM_HALF_U2, f)
         return units.convert_incompressible_energy_to_pu(e_lu) * units.convert_length_to_pu(1.0) ** self.flow.stencil.d
+
+    def from_fused_moments(self, moments):
+        units = self.flow.units
+        return (units.convert_incompressible_energy_to_pu(moments[:, 0])
+                * units.convert_length_to_pu(1.0) ** self.flow.stencil.d)
 
 
 class Enstrophy(Observable):
@@ -164,12 +173,33 @@ class ObservableReporter(Reporter):
         if not self._pending:
             return
         pending, self._pending = self._pending, []
-        flat = torch.cat([v.reshape(-1).to(torch.float64) for _, v in pending]).cpu().tolist()
+        flat = torch.cat([v.reshape(-1).to(torch.float64) for _, v, _ in pending]).cpu().tolist()
         pos = 0
-        for index, v in pending:
+        for index, v, per_row in pending:
             n = v.numel()
-            self._rows[index] = self._rows[index][:2] + flat[pos:pos + n]
+            if per_row:                       # a batch: one value for each of n consecutive rows
+                for k in range(n):
+                    self._rows[index + k] = self._rows[index + k][:2] + [flat[pos + k]]
+            else:
+                self._rows[index] = self._rows[index][:2] + flat[pos:pos + n]
             pos += n
+
+    def accepts_fused_batches(self, simulation) -> bool:
+        """can `Simulation.__call__` hand this reporter the values of a whole batch of steps at once
+        (`ingest_fused_batch`)?  Every step is reported, the observable is one the step kernels reduce themselves, and
+        the rows are collected in a list with their values left on the device until they are read."""
+        obs = self.observable
+        return (int(self.interval) == 1 and isinstance(self._rows, list) and self._defer is not False
+                and getattr(obs, "fused_with_step", False) and getattr(obs, "flow", None) is simulation.flow
+                and hasattr(obs, "from_fused_moments") and simulation.flow.f.is_cuda)
+
+    def ingest_fused_batch(self, simulation, first_step: int, moments):
+        """rows for steps first_step .. first_step + len(moments) - 1 from the moments the step kernels reduced"""
+        values = self.observable.from_fused_moments(moments).detach()
+        units = simulation.units
+        start = len(self._rows)
+        self._rows.extend([i, units.convert_time_to_pu(i)] for i in range(first_step, first_step + len(moments)))
+        self._pending.append((start, values, True))
 
     def __call__(self, simulation):
         if simulation.flow.i % self.interval != 0:
@@ -180,7 +210,7 @@ class ObservableReporter(Reporter):
         if defer and isinstance(self._rows, list) and torch.is_tensor(value):
             assert value.dim() < 2
             self._rows.append(head)
-            self._pending.append((len(self._rows) - 1, value.detach().clone()))
+            self._pending.append((len(self._rows) - 1, value.detach().clone(), False))
             return
         observed = self.observable.context.convert_to_ndarray(value)
         assert len(observed.shape) < 2

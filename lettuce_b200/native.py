@@ -28,13 +28,18 @@ F32, F64 = 0, 1
 OP_NO_COLLISION, OP_BGK, OP_TRT, OP_KBC, OP_REGULARIZED, OP_SMAGORINSKY, OP_BGK_FORCED = 0, 1, 2, 3, 4, 5, 6
 OP_BOUNCE_BACK, OP_EQUILIBRIUM, OP_OUTLET_P, OP_ANTI_BOUNCE_BACK, OP_IDENTITY = 16, 17, 18, 19, 20
 NO_STREAMING, POST_STREAMING, PRE_STREAMING, DOUBLE_STREAMING = 0, 1, 2, 3
-# Opt-in (0 = off, the default): batches of at least this many POST_STREAMING steps run as collide-only +
-# (n-1) pull steps + stream-only.  Measured on B200: it pays only where the push kernel is well behind the pull
-# kernel and the batch is long (sphere D3Q27 TRT: +5 % at n = 20; D3Q19 BGK: break-even at n ~ 40).  The result
-# was bit-identical to n push steps in every tested case, but that rests on nvcc contracting the collide code
-# identically in three kernel variants, which nothing guarantees; off by default so that sim(n) == n x sim(1)
-# holds by construction.
-LAZY_POST_MIN_STEPS = int(os.environ.get("LBM_B200_LAZY_POST_MIN", "0"))
+# Batches of at least this many POST_STREAMING steps run as (S C)^n = S (C S)^(n-1) C: one collide-only pass, n - 1
+# pull steps, one stream-only pass.  The result is bit-identical to n push steps: streaming only moves values, and
+# every kernel variant evaluates the collide phase with the same explicitly rounded operations (csrc/lbm_vec.cuh;
+# scripts/check_packed_contraction.py, tests/test_gpu_parity.py::test_lazy_post_batches_match_push_steps).
+# LBM_B200_LAZY_POST_MIN=n forces the threshold (0 = never).  Unset: automatic -- from 16 steps on, and only where the
+# pull step runs the TMA-staged kernel while the push step cannot (D3Q27 KBC: push 0.83, pull 0.95 of the roofline;
+# n + 1 passes instead of n).  Elsewhere push and pull are within a few percent and the extra pass does not pay
+# (sphere D3Q27 TRT: +5 % at n = 20; D3Q19 BGK: break-even at n ~ 40).
+_LAZY_ENV = os.environ.get("LBM_B200_LAZY_POST_MIN")
+LAZY_POST_MIN_STEPS = int(_LAZY_ENV) if _LAZY_ENV is not None else 0
+LAZY_POST_AUTO = _LAZY_ENV is None
+LAZY_POST_AUTO_MIN_STEPS = 16
 SUM_HALF_U2, MAX_U, SUM_F, SUM_F_INNER, SUM_F_MASKED, ENSTROPHY = range(6)
 # lbm_step_moments_state: which state the reductions fused into a step describe
 MOMENTS_UNAVAILABLE, MOMENTS_OF_OUTPUT, MOMENTS_OF_INPUT = 0, 1, 2
@@ -84,7 +89,8 @@ class LbmLinks(C.Structure):
 
 EXPORTS = ["lbm_apply_links", "lbm_links_scratch_doubles", "lbm_step_links_n", "lbm_ipc_alloc", "lbm_ipc_open",
            "lbm_ipc_close", "lbm_ipc_free", "lbm_slab_step_n", "lbm_slab_step_moments",
-           "lbm_step", "lbm_step_n", "lbm_step_moments", "lbm_step_moments_state", "lbm_step_moments_scratch_bytes",
+           "lbm_step", "lbm_step_n", "lbm_step_moments", "lbm_step_moments_n", "lbm_step_moments_state",
+           "lbm_step_moments_scratch_bytes",
            "lbm_pack_masks", "lbm_list_general_nodes", "lbm_equilibrium", "lbm_initialize_fneq", "lbm_moments",
            "lbm_reduce_scratch_bytes",
            "lbm_reduce", "lbm_run_host", "lbm_run_host_release", "lbm_abi_version", "lbm_status_string",
@@ -109,6 +115,8 @@ def lib() -> C.CDLL:
     L.lbm_step_n.restype = i32
     L.lbm_step_moments_state.argtypes = [C.POINTER(LbmStepDesc)]
     L.lbm_step_moments_state.restype = i32
+    L.lbm_step_moments_n.argtypes = [C.POINTER(LbmStepDesc), vp, vp, i64, vp, C.c_size_t, vp, vp]
+    L.lbm_step_moments_n.restype = C.c_int
     L.lbm_step_moments_scratch_bytes.argtypes = [C.POINTER(LbmStepDesc)]
     L.lbm_step_moments_scratch_bytes.restype = C.c_size_t
     L.lbm_step_moments.argtypes = [C.POINTER(LbmStepDesc), vp, vp, vp, C.c_size_t, vp, vp]
@@ -289,6 +297,7 @@ class Engine:
         self.refresh_parameters()
         self.labels: Optional[torch.Tensor] = None
         self.frozen: Optional[torch.Tensor] = None
+        self._pull_is_staged: Optional[bool] = None     # would a PRE_STREAMING step run the TMA-staged kernel?
         if dry:
             self.variant_name = "dry"
             return
@@ -477,6 +486,31 @@ class Engine:
     def _after_moments_step(self, f, g):
         self.flow.f, self.flow.f_next = g, f
 
+    def steps_with_moments(self, n: int) -> torch.Tensor:
+        """`n` time steps in ONE library call, every one with the fused reductions (`lbm_step_moments_n`): returns a
+        float64 CUDA tensor `[m, 2]` whose row k holds (sum 0.5|u|^2, max |u|^2) of the state after step k + 1, with
+        m = n when the steps describe the state they write (NO / PRE streaming) and m = n - 1 when they describe the
+        state they read (POST streaming)."""
+        state = self.moments_state()
+        if state == MOMENTS_UNAVAILABLE or n <= 0:
+            raise RuntimeError("steps_with_moments needs NO / PRE / POST streaming and n > 0")
+        self.refresh_parameters()
+        f, g = self._buffers()
+        scratch = self._moments_scratch()
+        m = n if state == MOMENTS_OF_OUTPUT else n - 1
+        out = torch.empty((max(m, 1), 2), dtype=torch.float64, device=self.device)
+        self.flow._b200_moments = None
+        with torch.cuda.device(self.device):
+            check(self.lib.lbm_step_moments_n(C.byref(self.desc), f.data_ptr(), g.data_ptr(), n, scratch.data_ptr(),
+                                              scratch.numel(), out.data_ptr(), _stream_ptr(self.device)),
+                  "lbm_step_moments_n")
+        if n & 1:
+            self.flow.f, self.flow.f_next = g, f
+        if state == MOMENTS_OF_OUTPUT:
+            new = self.flow.f
+            self.flow._b200_moments = (new.data_ptr(), new._version, out[n - 1])
+        return out[:m]
+
     def apply_links(self, boundary):
         """One post-streaming link boundary (ext/bounce_back.py) on the populations the last `step(1)` produced:
         `lbm_apply_links` with the step's input (now `flow.f_next`, left intact by the two-buffer scheme) and its
@@ -517,12 +551,22 @@ class Engine:
                 d.ops[i].kind = OP_NO_COLLISION if i == d.collision_index else OP_IDENTITY
         return d
 
+    def _lazy_post(self, n: int) -> bool:
+        """run a batch of n POST_STREAMING steps as collide-only + (n - 1) pull steps + stream-only?"""
+        if LAZY_POST_MIN_STEPS > 0:
+            return n >= LAZY_POST_MIN_STEPS
+        if not LAZY_POST_AUTO or n < LAZY_POST_AUTO_MIN_STEPS:
+            return False
+        if self._pull_is_staged is None:
+            name = self.lib.lbm_step_variant_name(C.byref(self._variant_of(PRE_STREAMING))).decode()
+            self._pull_is_staged = "TMA" in name
+        return self._pull_is_staged
+
     def step(self, n: int = 1):
         """Advance `n` time steps; afterwards flow.f holds the new populations.
 
-        With LAZY_POST_MIN_STEPS > 0 (opt-in), long POST_STREAMING batches use the identity
-        (S C)^n = S (C S)^(n-1) C: one collide-only pass, n-1 steps of the pull kernel (aligned stores) and one
-        stream-only pass; observed bit-identical to n push steps (tests/test_gpu_parity.py)."""
+        Long POST_STREAMING batches may use the identity (S C)^n = S (C S)^(n-1) C (see LAZY_POST_MIN_STEPS): one
+        collide-only pass, n-1 steps of the pull kernel and one stream-only pass; bit-identical to n push steps."""
         if n <= 0:
             return
         self.refresh_parameters()
@@ -532,7 +576,7 @@ class Engine:
         bufs, cur = [f, g], 0
         with torch.cuda.device(self.device):
             stream = _stream_ptr(self.device)
-            if self.desc.streaming == POST_STREAMING and 0 < LAZY_POST_MIN_STEPS <= n:
+            if self.desc.streaming == POST_STREAMING and self._lazy_post(n):
                 first = self._variant_of(NO_STREAMING)
                 middle = self._variant_of(PRE_STREAMING)
                 last = self._variant_of(PRE_STREAMING, stream_only=True)

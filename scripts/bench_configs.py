@@ -155,6 +155,13 @@ def main():
                                           finite=bool(torch.isfinite(flow.f).all()))), flush=True)
                     del flow, sim
             os.environ.pop("LBM_B200_EBB_BATCH", None)
+        elif case == "kbc2d":     # D2Q9 KBC: LDG vs staged kernel (LBM_B200_TMA=0|1)
+            for strat in (S.PRE_STREAMING,):
+                ctx = lt.Context("cuda", dtype=f32)
+                flow = lt.TaylorGreenVortex(ctx, [4096, 4096], 1600.0, 0.05, stencil=lt.D2Q9())
+                sim = lt.Simulation(flow, lt.KBCCollision(), [], strat)
+                report("TGV2D D2Q9 KBC 4096^2 fp32", flow, sim, steps=100)
+                del flow, sim
         elif case == "extra":
             for st, coll, dt_ in ((lt.D3Q27, "bgk", f32), (lt.D3Q27, "trt", f32), (lt.D3Q19, "bgk", f64),
                                   (lt.D3Q19, "trt", f32), (lt.D3Q27, "kbc", f64)):

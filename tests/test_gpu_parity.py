@@ -412,6 +412,33 @@ def test_lazy_post_batches_match_push_steps(case, monkeypatch):
     assert torch.equal(flow_a.f, flow_b.f)
 
 
+def test_long_post_batches_of_the_entropic_operator_run_on_the_staged_kernel():
+    """D3Q27 KBC, POST_STREAMING (the Simulation default): the push step cannot be staged through TMA, the pull step
+    can, so batches of >= 16 steps automatically run as collide-only + pull steps + stream-only -- with the same bits
+    as step-by-step push launches, and short batches stay on the push kernel."""
+    from lettuce_b200 import native as nv
+    ctx = cuda_ctx(torch.float32)
+    assert nv.LAZY_POST_AUTO and nv.LAZY_POST_MIN_STEPS == 0
+
+    def build():
+        flow = lt.TaylorGreenVortex(ctx, [16, 16, 320], 1600.0, 0.05, stencil=lt.D3Q27())
+        return flow, lt.Simulation(flow, lt.KBCCollision(), [])
+
+    flow_a, sim_a = build()
+    for _ in range(5 + 20 + 17):
+        nv.invoke(sim_a)
+    flow_b, sim_b = build()
+    eng = nv.engine_of(sim_b)
+    launches = nv.launch_count()
+    nv.invoke_n(sim_b, 5)                      # short: 5 push launches
+    assert nv.launch_count() - launches == 5
+    launches = nv.launch_count()
+    nv.invoke_n(sim_b, 20)                     # long: 1 + 19 + 1 passes
+    assert nv.launch_count() - launches == 21 and eng._pull_is_staged
+    nv.invoke_n(sim_b, 17)
+    assert torch.equal(flow_a.f, flow_b.f)
+
+
 # ------------------------------------------------------------------ further flows on the same kernels
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_doubly_periodic_shear_matches_reference_golden(dtype):
