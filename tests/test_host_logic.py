@@ -431,6 +431,51 @@ def test_observable_reporter_defers_device_values_until_read():
     assert stream.getvalue().split() == ["3", "1.5", "4.0"] and printed.out is stream
 
 
+def test_observable_reporter_takes_whole_batches_of_fused_moments():
+    """`Simulation.__call__` hands reporters with interval 1 the step kernels' own reductions for a whole run at once
+    (`lbm_step_moments_n`): same rows as step-by-step reports, mixed freely with single deferred values"""
+    class FakeUnits:
+        @staticmethod
+        def convert_time_to_pu(i):
+            return 0.25 * i
+
+    class FakeFlow:
+        i = 0
+        f = torch.zeros(1)                       # a CPU tensor: batches are refused, see below
+
+    class FakeSim:
+        flow = FakeFlow()
+        units = FakeUnits()
+
+    class Energy:
+        context = cpu(torch.float64)
+        fused_with_step = True
+        flow = FakeSim.flow
+
+        def __call__(self, f=None):
+            return torch.tensor(10.0 * FakeSim.flow.i, dtype=torch.float64)
+
+        def from_fused_moments(self, moments):
+            return 10.0 * moments[:, 0]
+
+    sim = FakeSim()
+    rep = lt.ObservableReporter(Energy(), interval=1, out=None, defer=True)
+    assert not rep.accepts_fused_batches(sim)                # CPU populations: no engine, no batches
+    sim.flow.i = 0
+    rep(sim)                                                 # step 0, single deferred value
+    moments = torch.tensor([[1.0, 0.5], [2.0, 0.5], [3.0, 0.5]], dtype=torch.float64)
+    rep.ingest_fused_batch(sim, 1, moments)                  # steps 1..3 in one go
+    sim.flow.i = 4
+    rep(sim)                                                 # step 4, single again
+    assert len(rep._pending) == 3 and [len(r) for r in rep._rows] == [2] * 5
+    assert rep.out == [[0, 0.0, 0.0], [1, 0.25, 10.0], [2, 0.5, 20.0], [3, 0.75, 30.0], [4, 1.0, 40.0]]
+    assert not rep._pending
+    # reporters that print, report less often, or evaluate anything else keep the step-by-step path
+    import io
+    assert not lt.ObservableReporter(Energy(), interval=1, out=io.StringIO()).accepts_fused_batches(sim)
+    assert not lt.ObservableReporter(Energy(), interval=2, out=None).accepts_fused_batches(sim)
+
+
 def test_engine_rejects_other_equilibria():
     """the kernels evaluate the quadratic equilibrium; a flow built with another one must not run silently"""
     class Other(lt.Equilibrium):
