@@ -266,18 +266,14 @@ static int validate_desc(const lbm_step_desc *d, Dims &dm) {
                 return LBM_ERR_BAD_ARGUMENT;
             const int n = op.axis == 0 ? d->lat.nx : (op.axis == 1 ? d->lat.ny : d->lat.nz);
             if (n < 2) return LBM_ERR_BAD_ARGUMENT;
-            // The neighbour of an outlet node is evaluated with node-local operators only; an earlier
-            // outlet acting on that neighbour (two outlets on different axes, or on both ends of a
-            // 3-plane axis) would need a second level of look-up.
-            for (int k = 0; k < i; ++k) {
-                if (!is_outlet(d->ops[k].kind) || d->ops[k].side == 0 || op.side == 0) continue;
-                if (d->ops[k].axis != op.axis) return LBM_ERR_UNSUPPORTED;
-                const int here_k = d->ops[k].side > 0 ? n - 1 : 0;
-                const int nb_i = op.side > 0 ? n - 2 : 1;
-                if (here_k == nb_i) return LBM_ERR_UNSUPPORTED;
-            }
+            // (an outlet's neighbour may lie on the plane of an earlier outlet -- planes of different axes meet, or
+            // both ends of a three-plane axis: the sparse kernel evaluates that neighbour's own outlet first,
+            // pipeline_prefix; the nesting is bounded by the number of active outlets)
         }
     }
+    int active_outlets = 0;
+    for (int i = 0; i < d->n_ops; ++i) active_outlets += is_outlet(d->ops[i].kind) && d->ops[i].side != 0;
+    if (active_outlets > kMaxOutletDepth + 1) return LBM_ERR_UNSUPPORTED;
     if (d->n_ops > 1 && (!d->labels || !d->frozen)) return LBM_ERR_BAD_ARGUMENT;
     if ((d->labels == nullptr) != (d->frozen == nullptr)) return LBM_ERR_BAD_ARGUMENT;
     if (d->n_general < 0 || (d->n_general > 0 && !d->general_nodes)) return LBM_ERR_BAD_ARGUMENT;
@@ -331,6 +327,9 @@ static void fill_params(const lbm_step_desc *d, const Dims &dm, const void *f_in
     p.n_general = (int)d->n_general;
     p.n_ops = d->n_ops;
     p.collision_index = d->collision_index;
+    int active_outlets = 0;
+    for (int i = 0; i < d->n_ops; ++i) active_outlets += is_outlet(d->ops[i].kind) && d->ops[i].side != 0;
+    p.nested_outlets = active_outlets >= 2 ? 1 : 0;
     const lbm_op &c = d->ops[d->collision_index];
     collision_scalars<R>(c.kind, c.p0, c.p1, p.ca, p.cb);
     for (int a = 0; a < 3; ++a) p.force.a[a] = R(0);

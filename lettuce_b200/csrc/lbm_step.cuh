@@ -89,6 +89,7 @@ struct StepParams {
     const int32_t *general_nodes;  // flat indices of the nodes with label bit 7 set
     int n_general;
     int n_ops, collision_index;
+    int nested_outlets;  // two or more active outlets: an outlet's neighbour may lie on another outlet's plane
     R ca, cb;  // scalars of the collision entry
     ForceArgs<R> force;  // LBM_OP_BGK_FORCED only
     SlabSync sync;
@@ -199,12 +200,19 @@ LBM_D void equilibrium_boundary(const OpDev<R> &op, int x, int y, int z, R (&f)[
 
 // applies transformer entry `i` to node-local populations if the node carries label i.
 // Outlet kinds are handled by the caller (they need a neighbour).
+// (one out-of-line copy of the collision per translation unit for the nested pipelines of multi-outlet lattices)
 template <class S, class R, int COLL>
+__device__ __noinline__ void collide_node_out_of_line(const StepParams<R> &p, R (&f)[S::Q]) {
+    collide_node<S, R, COLL>(p, f);
+}
+
+template <class S, class R, int COLL, bool OUT_OF_LINE = false>
 LBM_D void apply_local_op(const StepParams<R> &p, int i, int label, int x, int y, int z, R (&f)[S::Q]) {
     if (label != i) return;
     const OpDev<R> &op = p.ops[i];
     if (i == p.collision_index) {
-        collide_node<S, R, COLL>(p, f);
+        if constexpr (OUT_OF_LINE) collide_node_out_of_line<S, R, COLL>(p, f);
+        else collide_node<S, R, COLL>(p, f);
     } else if (op.kind == LBM_OP_BOUNCE_BACK) {
         bounce_back<S, R>(f);
     } else if (op.kind == LBM_OP_EQUILIBRIUM) {
@@ -219,35 +227,54 @@ LBM_D bool in_plane_of(int axis, int side, int x, int y, int z, int n0, int n1, 
     return c == (side > 0 ? n - 1 : 0);
 }
 
-// velocity of the neighbour node one step inside the domain from an outlet node, as
-// the reference sees it when boundary `i` runs: populations after entries < i.
-template <class S, class R, int COLL, bool PULL>
-__device__ void neighbour_state(const StepParams<R> &p, int i, int x, int y, int z, R &rho, R (&u)[3]) {
-    R g[S::Q];
-    gather_node<S, R, PULL>(p, x, y, z, g);
-    const int label = label_plane(p, x)[(int64_t)y * p.n2 + z] & 0x7f;
-    for (int k = 0; k < i; ++k) apply_local_op<S, R, COLL>(p, k, label, x, y, z, g);
-    R j[3];
-    moments<S, R>(g, rho, j);
-    const R inv = R(1) / rho;
-    u[0] = j[0] * inv; u[1] = j[1] * inv; u[2] = j[2] * inv;
-}
+// Populations of node (x,y,z) as the reference's collide phase sees them when transformer entry `n_end` is about to
+// run: gathered (pre-streaming), then entries 0 .. n_end-1 applied in order.  An outlet entry rewrites its plane from
+// the velocity of the neighbour node one step inside the domain, taken from the populations after the entries BEFORE
+// that outlet -- itself such a prefix, one level down.  An outlet's neighbour lies on the plane of an EARLIER outlet
+// only where outlet planes of different axes meet (or on a three-plane axis with outlets at both ends), so the
+// nesting never exceeds the number of outlets minus one (kMaxOutletDepth, checked on the host).  Lattices with at most
+// one active outlet take the inline two-level form (NESTED = false, DEPTH = 1).
+constexpr int kMaxOutletDepth = 2;
 
-// populations of node (x,y,z) after the collide phase (all transformer entries), before any post-streaming
-template <class S, class R, int COLL, bool PULL>
-__device__ void node_pipeline(const StepParams<R> &p, int x, int y, int z, int label, R (&f)[S::Q]) {
+template <class R>
+struct NodeState {
+    R rho, u[3];
+};
+// (out of line: one copy per translation unit instead of one per nesting level and kernel -- inlined, the four levels
+// multiplied the build time by seven; only nodes on outlet planes ever get here)
+template <class S, class R, int COLL, bool PULL, int DEPTH>
+__device__ __noinline__ NodeState<R> neighbour_prefix(const StepParams<R> &p, int n_end, int x, int y, int z);
+
+template <class S, class R, int COLL, bool PULL, int DEPTH, bool NESTED>
+__device__ void pipeline_prefix(const StepParams<R> &p, int n_end, int x, int y, int z, int label, R (&f)[S::Q]) {
     constexpr int Q = S::Q;
     gather_node<S, R, PULL>(p, x, y, z, f);
 
-    for (int i = 0; i < p.n_ops; ++i) {
+    for (int i = 0; i < n_end; ++i) {
         const OpDev<R> &op = p.ops[i];
         if (op.kind == LBM_OP_OUTLET_P || op.kind == LBM_OP_ANTI_BOUNCE_BACK) {
             if (!in_plane_of(op.axis, op.side, x, y, z, p.n0, p.n1, p.n2)) continue;
-            const int xn = x - (op.axis == 0 ? op.side : 0);
-            const int yn = y - (op.axis == 1 ? op.side : 0);
-            const int zn = z - (op.axis == 2 ? op.side : 0);
-            R rho_n, u_n[3];
-            neighbour_state<S, R, COLL, PULL>(p, i, xn, yn, zn, rho_n, u_n);
+            if constexpr (DEPTH == 0) continue;      // (unreachable: the host picks NESTED whenever planes can meet
+                                                     // and bounds the number of outlets)
+            R rho_n = R(1), u_n[3] = {R(0), R(0), R(0)};
+            if constexpr (DEPTH > 0) {
+                // velocity of the neighbour as the reference sees it when boundary i runs
+                const int xn = x - (op.axis == 0 ? op.side : 0);
+                const int yn = y - (op.axis == 1 ? op.side : 0);
+                const int zn = z - (op.axis == 2 ? op.side : 0);
+                if constexpr (NESTED) {
+                    const NodeState<R> nb = neighbour_prefix<S, R, COLL, PULL, DEPTH - 1>(p, i, xn, yn, zn);
+                    rho_n = nb.rho;
+                    u_n[0] = nb.u[0]; u_n[1] = nb.u[1]; u_n[2] = nb.u[2];
+                } else {
+                    R g[Q], j[3];
+                    const int label_n = label_plane(p, xn)[(int64_t)yn * p.n2 + zn] & 0x7f;
+                    pipeline_prefix<S, R, COLL, PULL, DEPTH - 1, false>(p, i, xn, yn, zn, label_n, g);
+                    moments<S, R>(g, rho_n, j);
+                    const R inv = R(1) / rho_n;
+                    u_n[0] = j[0] * inv; u_n[1] = j[1] * inv; u_n[2] = j[2] * inv;
+                }
+            }
             if (op.kind == LBM_OP_OUTLET_P) {
                 // equilibrium_outlet_p.py:63-73: whole plane <- feq(rho_outlet, u[neighbour]),
                 // irrespective of the label
@@ -283,9 +310,38 @@ __device__ void node_pipeline(const StepParams<R> &p, int x, int y, int z, int l
                 ForQ<Q>::run([&]<int q>() { f[q] = fnew[q]; });
             }
         } else {
-            apply_local_op<S, R, COLL>(p, i, label, x, y, z, f);
+            apply_local_op<S, R, COLL, NESTED>(p, i, label, x, y, z, f);
         }
     }
+}
+
+// (one instantiation per nesting level: the stack each needs is known at compile time)
+template <class S, class R, int COLL, bool PULL, int DEPTH>
+__device__ __noinline__ NodeState<R> neighbour_prefix(const StepParams<R> &p, int n_end, int x, int y, int z) {
+    R g[S::Q];
+    const int label = label_plane(p, x)[(int64_t)y * p.n2 + z] & 0x7f;
+    pipeline_prefix<S, R, COLL, PULL, DEPTH, true>(p, n_end, x, y, z, label, g);
+    NodeState<R> out;
+    R j[3];
+    moments<S, R>(g, out.rho, j);
+    const R inv = R(1) / out.rho;
+    out.u[0] = j[0] * inv; out.u[1] = j[1] * inv; out.u[2] = j[2] * inv;
+    return out;
+}
+
+template <class S, class R, int COLL, bool PULL>
+__device__ __noinline__ void nested_node_pipeline(const StepParams<R> &p, int x, int y, int z, int label,
+                                                  R (&f)[S::Q]) {
+    pipeline_prefix<S, R, COLL, PULL, kMaxOutletDepth + 1, true>(p, p.n_ops, x, y, z, label, f);
+}
+
+// populations of node (x,y,z) after the collide phase (all transformer entries), before any post-streaming.
+// NESTED = false (at most one active outlet: no outlet's neighbour lies on an outlet plane): node and neighbour
+// inline, as fast as it gets; NESTED = true: every level out of line.
+template <class S, class R, int COLL, bool PULL, bool NESTED>
+__device__ void node_pipeline(const StepParams<R> &p, int x, int y, int z, int label, R (&f)[S::Q]) {
+    if constexpr (NESTED) nested_node_pipeline<S, R, COLL, PULL>(p, x, y, z, label, f);
+    else pipeline_prefix<S, R, COLL, PULL, 1, false>(p, p.n_ops, x, y, z, label, f);
 }
 
 // scatter of a general node's populations with the destination-side frozen-slot rule (_simulation.py:252-255):
@@ -579,7 +635,7 @@ __global__ void __launch_bounds__((bulk_threads<S, R, COLL, LANES>()), (min_bloc
 // sparse kernel: one thread per node of the precomputed list of general nodes
 // (boundaries, frozen slots), launched behind step_kernel on the same stream.
 // ---------------------------------------------------------------------------
-template <class S, class R, int COLL, bool PULL, bool PUSH>
+template <class S, class R, int COLL, bool PULL, bool PUSH, bool NESTED>
 __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constant__ StepParams<R> p) {
     // Launched programmatically behind the bulk kernel, which released this grid only after the previous step
     // had completed: the input populations are final.  The next step's bulk kernel may become resident right away
@@ -611,7 +667,7 @@ __global__ void __launch_bounds__(128) general_nodes_kernel(const __grid_constan
             gather_node<S, R, false>(p, x, y, z, f);
             accumulate_kinetic<S, R>(f, take, e_sum, e_max);
         }
-        node_pipeline<S, R, COLL, PULL>(p, x, y, z, p.labels[n] & 0x7f, f);
+        node_pipeline<S, R, COLL, PULL, NESTED>(p, x, y, z, p.labels[n] & 0x7f, f);
     }
     // the bulk kernel updated every node as if it were plain fluid: wait for it to finish before overwriting the
     // slots that belong to the general nodes (every thread passes the wait, so that completion of this grid
@@ -662,7 +718,7 @@ struct LinkArgs {
 
 constexpr int kLinkThreads = 128;
 
-template <class S, class R, int COLL>
+template <class S, class R, int COLL, bool NESTED>
 __global__ void __launch_bounds__(kLinkThreads) link_gather_kernel(const __grid_constant__ StepParams<R> p,
                                                                      const LinkArgs<R> a) {
     constexpr int Q = S::Q;
@@ -682,7 +738,7 @@ __global__ void __launch_bounds__(kLinkThreads) link_gather_kernel(const __grid_
             const int x = n / (p.n1 * p.n2);
             R f[Q];
             const int label = p.labels ? (p.labels[n] & 0x7f) : p.collision_index;
-            node_pipeline<S, R, COLL, false>(p, x, y, z, label, f);
+            node_pipeline<S, R, COLL, false, NESTED>(p, x, y, z, label, f);
             R fcq = R(0), fco = R(0);                               // fc[q], fc[opposite(q)] of this node
             ForQ<Q>::run([&]<int k>() {
                 if (k == q) {

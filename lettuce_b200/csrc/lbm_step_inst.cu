@@ -77,8 +77,9 @@ int launch_lanes(const StepParams<R> &p_in, const LaunchOptions &opt, cudaStream
         e = (int)cudaGetLastError();
     }
     if (e || !sparse) return e;
-    return launch_dependent<R>(general_nodes_kernel<S, R, COLL, PULL, PUSH>, dim3(sparse_blocks(p.n_general)),
-                               dim3(kSparseThreads), p, stream);
+    return launch_dependent<R>(p.nested_outlets ? general_nodes_kernel<S, R, COLL, PULL, PUSH, true>
+                                                : general_nodes_kernel<S, R, COLL, PULL, PUSH, false>,
+                               dim3(sparse_blocks(p.n_general)), dim3(kSparseThreads), p, stream);
 }
 
 // the TMA-staged persistent kernel (lbm_tma.cuh): one CTA per SM, tiles of kTmaTileNodes nodes dealt round-robin
@@ -158,7 +159,8 @@ int by_lanes(const StepParams<R> &p, const LaunchOptions &opt, cudaStream_t stre
             int e = launch_tma<S, COLL, PULL>(p, opt, stream);
             if (e || !(p.labels != nullptr && p.n_general > 0)) return e;
             // masked runs: the sparse kernel behind it, as after the LDG bulk kernel (launch_lanes)
-            return launch_dependent<R>(general_nodes_kernel<S, R, COLL, PULL, PUSH>,
+            return launch_dependent<R>(p.nested_outlets ? general_nodes_kernel<S, R, COLL, PULL, PUSH, true>
+                                                        : general_nodes_kernel<S, R, COLL, PULL, PUSH, false>,
                                        dim3(sparse_blocks(p.n_general)), dim3(kSparseThreads), p, stream);
         }
     }
@@ -185,7 +187,8 @@ template <class S, class R, int COLL>
 int launch_links_coll(const StepParams<R> &p, const LinkArgs<R> &a, cudaStream_t stream) {
     if (a.n <= 0) return 0;
     const int blocks = link_blocks(a.n);
-    link_gather_kernel<S, R, COLL><<<blocks, kLinkThreads, 0, stream>>>(p, a);
+    if (p.nested_outlets) link_gather_kernel<S, R, COLL, true><<<blocks, kLinkThreads, 0, stream>>>(p, a);
+    else link_gather_kernel<S, R, COLL, false><<<blocks, kLinkThreads, 0, stream>>>(p, a);
     ++g_launch_count;
     int e = (int)cudaGetLastError();
     if (e) return e;

@@ -135,8 +135,28 @@ def _reference_case(ref, case, device, dtype):
                     ref.EquilibriumOutletP(direction=self._unit_vector().tolist(), flow=self, rho_outlet=1.0),
                     ref.BounceBackBoundary(self.mask)]
 
+    class ObstacleCornerOutlets(ref.Obstacle):
+        """outlets on DIFFERENT axes (their planes meet along an edge / in a corner): the pressure outlet's neighbour
+        on the edge lies on the anti-bounce-back outlet's plane and vice versa"""
+        @property
+        def post_boundaries(self):
+            x = self.grid[0]
+            d = self.stencil.d
+            unit = lambda a, s=1: [s if k == a else 0 for k in range(d)]
+            out = [ref.EquilibriumBoundaryPU(flow=self, context=self.context, mask=torch.abs(x) < 1e-6,
+                                             velocity=self.units.characteristic_velocity_pu * self._unit_vector()),
+                   ref.AntiBounceBackOutlet(unit(1), self),
+                   ref.EquilibriumOutletP(direction=unit(0), flow=self, rho_outlet=1.0)]
+            if d == 3:
+                out.append(ref.EquilibriumOutletP(direction=unit(2, -1), flow=self, rho_outlet=1.01))
+            return out + [ref.BounceBackBoundary(self.mask)]
+
     if case == "sphere_d3q27_trt_post":
         cls, res, stencil = ObstacleEqOut, [32, 16, 16], ref.D3Q27()
+    elif case == "corner_outlets_d2q9_bgk_post":
+        cls, res, stencil = ObstacleCornerOutlets, [40, 24], ref.D2Q9()
+    elif case == "corner_outlets_d3q19_trt_post":
+        cls, res, stencil = ObstacleCornerOutlets, [24, 16, 12], ref.D3Q19()
     elif case == "cylinder_d2q9_bgk_post":
         cls, res, stencil = ObstacleEqOut, [64, 16], ref.D2Q9()
     else:                                               # stock lt.Obstacle: anti-bounce-back outlet
@@ -157,7 +177,8 @@ def _reference_case(ref, case, device, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("case", ["tgv3d_d3q19_bgk_pre", "tgv3d_d3q27_kbc_post", "sphere_d3q27_trt_post",
-                                  "cylinder_d2q9_bgk_post", "stock_obstacle_d2q9_bgk_post"])
+                                  "cylinder_d2q9_bgk_post", "stock_obstacle_d2q9_bgk_post",
+                                  "corner_outlets_d2q9_bgk_post", "corner_outlets_d3q19_trt_post"])
 def test_reference_simulation_steps_on_the_engine(ref, case, dtype):
     """INTEGRATION.md section 2, executed: the reference's Simulation / Flow / Collision / Boundary objects, unmodified,
     with `native.invoke` assigned where the reference installs its generated kernel (lettuce/_simulation.py:229)."""

@@ -272,11 +272,13 @@ def test_descriptor_validation_without_gpu():
     d.lat = native.LbmLattice(native.D3Q27, native.F32, 2048, 2048, 1024, 0)
     assert L.lbm_step(ctypes.byref(d), 1 << 20, 1 << 50, None) == -5          # >= 2^31 nodes
     d.lat = native.LbmLattice(native.D3Q27, native.F32, 8, 8, 8, 0)
-    d.n_ops = 3
-    d.ops[1].kind, d.ops[1].axis, d.ops[1].side = native.OP_OUTLET_P, 0, 1
-    d.ops[2].kind, d.ops[2].axis, d.ops[2].side = native.OP_OUTLET_P, 1, 1
+    # outlets on up to three different axes are evaluated (nested neighbour look-ups in the sparse kernel); a fourth
+    # active outlet is refused
+    d.n_ops = 5
+    for i, (axis, side) in enumerate([(0, 1), (1, 1), (2, -1), (0, -1)], start=1):
+        d.ops[i].kind, d.ops[i].axis, d.ops[i].side = native.OP_OUTLET_P, axis, side
     d.labels, d.frozen = 1 << 20, 1 << 21
-    assert L.lbm_step(ctypes.byref(d), 1 << 22, 1 << 30, None) == -2          # outlets on two axes
+    assert L.lbm_step(ctypes.byref(d), 1 << 22, 1 << 30, None) == -2
 
 
 def test_equilibrium_boundary_parameters_are_re_read_when_modified():
