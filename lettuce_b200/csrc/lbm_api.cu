@@ -379,7 +379,11 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &capturing);      // (graph replays may run concurrently: they keep the LDG kernel)
     const bool slab_step = x.sync != nullptr && x.sync->on;
-    if (!x.partials && tma_wanted(d, slab_step) && capturing == cudaStreamCaptureStatusNone) {
+    // (fused reductions: the staged kernel has them for unmasked pulling steps on one GPU)
+    const bool reduce_ok = !x.partials || (!slab_step && x.reduce_mode == kReduceOutput && !d->labels &&
+                                           d->streaming == LBM_PRE_STREAMING);
+    opt.slots_used = x.slots_used;
+    if (reduce_ok && tma_wanted(d, slab_step) && capturing == cudaStreamCaptureStatusNone) {
         const int tz = tma_row_extent(dm.n2), rows = tma_tile_rows(dm.n2);
         const bool boxable = tma_rows_boxable(dm.n0, dm.n1, dm.n2);
         const int by = dm.n1 > 1 ? rows : 1, bx = dm.n1 > 1 ? 1 : rows;      // rows run along y (3-D) or x (2-D)
@@ -546,7 +550,8 @@ int step_general(const lbm_step_desc *desc, const void *d_f_in, void *d_f_out, c
 static int max_reduce_slots(const lbm_step_desc *desc, const Dims &dm) {
     const int a = reduce_slots_for(dm.n0, dm.n1, dm.n2, 1, desc->n_general);
     const int b = reduce_slots_for(dm.n0, dm.n1, dm.n2, 2, desc->n_general);
-    return a > b ? a : b;
+    const int c = 1024;                       // the staged kernel: one pair per persistent CTA
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 // one step with fused reductions into (partials, stage) -> d_result[2]; shared by lbm_step_moments and the slab entry
@@ -565,9 +570,11 @@ int step_moments_general(const lbm_step_desc *desc, const void *d_f_in, void *d_
     x.partials = (double *)d_scratch;
     x.reduce_mode = state == LBM_MOMENTS_OF_OUTPUT ? kReduceOutput : kReduceInput;
     x.chained = chained;
+    int used = 0;
+    x.slots_used = &used;
     rc = step_general(desc, d_f_in, d_f_out, x, stream);
     if (rc) return rc;
-    const int slots = reduce_slots_for(dm.n0, dm.n1, dm.n2, chosen_lanes(desc), desc->n_general);
+    const int slots = used > 0 ? used : reduce_slots_for(dm.n0, dm.n1, dm.n2, chosen_lanes(desc), desc->n_general);
     return cuda_fail(launch_fold_pair((const double *)d_scratch, slots, (double *)d_scratch + 2 * (size_t)max_reduce_slots(desc, dm),
                                       d_result, (cudaStream_t)stream));
 }

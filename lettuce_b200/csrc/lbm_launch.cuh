@@ -43,6 +43,8 @@ struct LaunchOptions {
     int tma_boxable = 0;            // the box / halo maps are valid (tma_rows_boxable)
     bool tma_interior = false;      // multi-GPU slab: cut planes by the LDG lock-step kernel, interior planes staged
     unsigned *tma_counters = nullptr;   // two zeroed words in device memory: the kernel's tile counter (lbm_tma.cuh)
+    int *slots_used = nullptr;          // out: partial pairs a step with fused reductions wrote, when that is not
+                                        // reduce_slots_for (the staged kernel: one pair per persistent CTA)
     int sm_count = 148;
     int lanes;        // 1, or 2 (fp32, even n2, PRE / POST streaming): nodes per thread of the bulk kernel
     bool chained;     // the previous launch on the stream is a step kernel of this library: launch behind it with
@@ -78,6 +80,7 @@ struct StepExtras {
     double *partials = nullptr;         // fused reductions: 2 * reduce_slots doubles ...
     int reduce_mode = kReduceNone;      // ... of the written (kReduceOutput) or the read (kReduceInput) state
     bool chained = false;               // launch behind the previous step kernel with programmatic serialization
+    int *slots_used = nullptr;          // out, see LaunchOptions
 };
 // lbm_step plus the optional in-kernel slab lock step (lbm_slab_step_n), fused reductions (lbm_step_moments) and
 // programmatic chaining behind the previous step (lbm_step_n); returns an lbm_status

@@ -83,9 +83,9 @@ int launch_lanes(const StepParams<R> &p_in, const LaunchOptions &opt, cudaStream
 }
 
 // the TMA-staged persistent kernel (lbm_tma.cuh): one CTA per SM, tiles of kTmaTileNodes nodes dealt round-robin
-template <class S, int COLL, bool PULL>
+template <class S, int COLL, bool PULL, bool REDUCE = false>
 int launch_tma(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_t stream) {
-    auto kernel = step_tma_kernel<S, COLL, PULL>;
+    auto kernel = step_tma_kernel<S, COLL, PULL, REDUCE>;
     // CTAs per SM and stages per CTA: as many stages as fit next to each other in the SM's 227 KB (1 KB per CTA is
     // reserved by the system); LBM_B200_TMA_CTAS / LBM_B200_TMA_STAGES override (measurements)
     static const int env_ctas = [] { const char *e = getenv("LBM_B200_TMA_CTAS"); return e ? atoi(e) : 0; }();
@@ -126,6 +126,11 @@ int launch_tma(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_
     t.ca = p.ca; t.cb = p.cb; t.force = p.force;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(t.n_tiles < opt.sm_count * ctas ? t.n_tiles : opt.sm_count * ctas);
+    if constexpr (REDUCE) {
+        t.partials = p.energy_partials;
+        t.reduce_slots = (int)cfg.gridDim.x;
+        if (opt.slots_used) *opt.slots_used = t.reduce_slots;
+    }
     cfg.blockDim = dim3(kTmaThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -154,6 +159,11 @@ int by_lanes(const StepParams<R> &p, const LaunchOptions &opt, cudaStream_t stre
             else e = launch_lanes<S, R, COLL, PULL, PUSH, 1>(p, o, stream, true);
             if (e) return e;
             return launch_tma<S, COLL, PULL>(p, opt, stream);
+        }
+        if constexpr (PULL) {
+            // fused reductions of the state a pulling step writes (unmasked lattices): the staged kernel's consumers
+            if (opt.tma && !p.sync.on && p.reduce_mode == kReduceOutput && p.labels == nullptr)
+                return launch_tma<S, COLL, PULL, true>(p, opt, stream);
         }
         if (opt.tma && !p.sync.on && p.reduce_mode == kReduceNone) {
             int e = launch_tma<S, COLL, PULL>(p, opt, stream);

@@ -59,6 +59,8 @@ struct TmaParams {
     int n_tiles;
     int skip_wait;            // launched behind a kernel of the SAME step (slab: the cut-plane kernel): do not wait
                               // for that grid to complete, its start already implies that the previous step is done
+    double *partials;         // REDUCE instantiation: one (sum 0.5|u|^2, max |u|^2) pair per CTA of the state the step
+    int reduce_slots;         // writes -- sums in [0, reduce_slots), maxima in [reduce_slots, 2 reduce_slots)
     int stages;
     int boxable;              // a full tile never straddles two planes (3-D) / rows divide n0 (2-D): box maps usable
     int reverse;              // sweep the tiles backwards (L2 reuse between consecutive steps)
@@ -181,7 +183,7 @@ struct TileInfo {
 template <class S>
 constexpr int tma_ctas_per_sm() { return S::Q <= 19 ? 2 : 1; }
 
-template <class S, int COLL, bool PULL>
+template <class S, int COLL, bool PULL, bool REDUCE>
 __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
     step_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaParams p) {
     constexpr int Q = S::Q;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
     extern __shared__ __align__(128) float stage0[];
     __shared__ __align__(8) unsigned long long full_bar[kTmaMaxStages], done_bar[kTmaMaxStages], ring_bar[kTmaRing];
     __shared__ TileInfo ring[kTmaRing];
+    __shared__ double reduce_part[2][kTmaConsumers / 32];
     if (threadIdx.x == 0 && (tma::smem_addr(stage0) & 127u)) __trap();
 
     // (see step_kernel: complete the step in front, then let the kernel behind become resident)
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
     // are its neighbours in the row, except at the row's ends, where they come from the halo quad.
     const int i0 = 2 * t;
     const bool first = zl == 0, last = zl == p.tz - 2;
+    double e_sum = 0.0, e_max = 0.0;                 // REDUCE: moments of the nodes this thread has written
     for (int i = 0;; ++i) {
         const int s = i % NS;
         const TileInfo ti = tile(i);
@@ -390,9 +394,36 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
             collide_lanes<S, float2, COLL>(p, f);
             float2 *out = reinterpret_cast<float2 *>(st + i0);
             ForQ<Q>::run([&]<int q>() { out[q * (T / 2)] = f[q]; });
+            if constexpr (REDUCE) {
+                const bool take[2] = {true, true};
+                accumulate_kinetic<S, float2>(f, take, e_sum, e_max);
+            }
         }
         tma::fence_async_shared();
         tma::mbar_arrive(tma::smem_addr(&done_bar[s]));
+    }
+    if constexpr (REDUCE) {
+        // one (sum, max) pair per CTA, folded in a fixed order among the consumer warps (the producers are elsewhere:
+        // a named barrier for the 256 consumers)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            e_sum += __shfl_down_sync(0xffffffffu, e_sum, o);
+            e_max = fmax(e_max, __shfl_down_sync(0xffffffffu, e_max, o));
+        }
+        if ((t & 31) == 0) {
+            reduce_part[0][t >> 5] = e_sum;
+            reduce_part[1][t >> 5] = e_max;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kTmaConsumers) : "memory");
+        if (t == 0) {
+            double sum = 0.0, mx = 0.0;
+            for (int w = 0; w < kTmaConsumers / 32; ++w) {
+                sum += reduce_part[0][w];
+                mx = fmax(mx, reduce_part[1][w]);
+            }
+            p.partials[blockIdx.x] = sum;
+            p.partials[p.reduce_slots + blockIdx.x] = mx;
+        }
     }
 }
 

@@ -260,7 +260,9 @@ def test_convergence_orders():
                                                     ("D3Q27", [12, 16, 20], "kbc", torch.float32),
                                                     ("D2Q9", [40, 33], "trt", torch.float64),
                                                     # 4200 CTAs: the partials take the two-stage fold
-                                                    ("D2Q9", [4200, 40], "bgk", torch.float64)])
+                                                    ("D2Q9", [4200, 40], "bgk", torch.float64),
+                                                    # large enough for the TMA-staged kernel (its consumers reduce)
+                                                    ("D3Q27", [16, 16, 320], "kbc", torch.float32)])
 @pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING", "POST_STREAMING"])
 def test_fused_step_moments_equal_the_reductions(stencil, res, coll, dtype, strategy):
     """lbm_step_moments: same populations as lbm_step, and (sum 0.5|u|^2, max |u|^2) equal the stand-alone
