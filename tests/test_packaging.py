@@ -61,3 +61,16 @@ def test_packed_fp32_operators_are_free_of_ptxas_contractions():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_packed_contraction.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_gpu_evidence_was_recorded_on_the_shipped_sources():
+    """profiles/r2_gpu_tests_tail.txt (the round's full GPU test run + smoke) names the source digest of the library
+    that ran on the B200; it must be the digest of the sources in this tree."""
+    import re
+    from lettuce_b200 import build
+    with open(os.path.join(ROOT, "profiles", "r2_gpu_tests_tail.txt")) as fh:
+        text = fh.read()
+    m = re.search(r"source digest ([0-9a-f]{64})", text)
+    assert m, "no source digest in profiles/r2_gpu_tests_tail.txt"
+    assert m.group(1) == build.source_digest(), "the GPU evidence under profiles/ is older than csrc/ or include/"
+    assert re.search(r"\b\d+ passed", text) and " failed" not in text
