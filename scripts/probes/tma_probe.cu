@@ -4,7 +4,7 @@
 //   2  descriptor in global memory, box 32                           3  shifted coordinate (-1) with box 32
 //   6 / 7 / 8 / 9  coordinate +1 / -4 / n2-4 / +3        10 / 11  shared-memory box 16 / 64 bytes off a 128-byte boundary
 //   4  1-D bulk copy of 16 bytes                                      5  lane-parallel issue (27 lanes), box 32
-// nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a scripts/probes/tma_probe.cu -o gpurun_out/tma_probe
+// nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a scripts/probes/tma_probe.cu -o variants/tma_probe   (variants/ is git-ignored and travels with gpurun)
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
