@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--checkpoint", default=None, help="write the global lattice here at the end (rank 0)")
     args = ap.parse_args()
+    if "RANK" not in os.environ:
+        sys.exit("one process per GPU: launch with `torchrun --nproc-per-node N --master-addr 127.0.0.1 " + sys.argv[0] + "`")
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
