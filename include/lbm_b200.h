@@ -141,8 +141,8 @@ typedef struct lbm_step_desc {
     int32_t variant;   /* bulk kernel: 0 = library default; 1 or 2 = LDG/STG kernel with that many nodes per thread (two
                           neighbouring nodes as one float2 on the packed fp32 pipe; used where that kernel exists:
                           fp32, even contiguous extent, PRE / POST streaming); 3 = TMA-staged kernel (csrc/lbm_tma.cuh:
-                          fp32, PRE / NO streaming, contiguous extent a multiple of 64, single GPU; LBM_ERR_UNSUPPORTED
-                          otherwise).  All
+                          fp32, every streaming mode but DOUBLE, contiguous extent a multiple of 64;
+                          LBM_ERR_UNSUPPORTED otherwise).  All
                           give bit-identical results (csrc/lbm_vec.cuh). */
     lbm_op ops[LBM_MAX_OPS];
     /* Masked runs (any boundary present): per-node label byte produced by

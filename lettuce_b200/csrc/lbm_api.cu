@@ -91,7 +91,7 @@ static bool tma_wanted(const lbm_step_desc *d, bool slab = false) {
     const bool two_d = d->lat.stencil == LBM_D2Q9;
     const int n2 = two_d ? d->lat.ny : d->lat.nz;
     const int64_t nodes = (int64_t)d->lat.nx * d->lat.ny * d->lat.nz;
-    if (!tma_available(d->lat.dtype, nodes, n2) || (d->streaming & LBM_POST_STREAMING)) return false;
+    if (!tma_available(d->lat.dtype, nodes, n2) || d->streaming == LBM_DOUBLE_STREAMING) return false;
     const lbm_halo &h = d->halo;
     // slabs: the neighbours' planes are not in the tensor -- the staged kernel takes the interior planes only, of
     // unmasked pulling steps (lbm_step_inst.cu); otherwise the peer planes rule it out
@@ -381,7 +381,7 @@ static int step_typed(const lbm_step_desc *d, const Dims &dm, const void *f_in, 
     const bool slab_step = x.sync != nullptr && x.sync->on;
     // (fused reductions: the staged kernel has them for unmasked pulling steps on one GPU)
     const bool reduce_ok = !x.partials || (!slab_step && x.reduce_mode == kReduceOutput && !d->labels &&
-                                           d->streaming == LBM_PRE_STREAMING);
+                                           d->streaming == LBM_PRE_STREAMING);      // (the pushing kernel has none)
     opt.slots_used = x.slots_used;
     if (reduce_ok && tma_wanted(d, slab_step) && capturing == cudaStreamCaptureStatusNone) {
         const int tz = tma_row_extent(dm.n2), rows = tma_tile_rows(dm.n2);

@@ -144,8 +144,69 @@ int launch_tma(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_
     return e;
 }
 
+// the pushing step on the staged machinery (step_tma_push_kernel)
+template <class S, int COLL>
+int launch_tma_push(const StepParams<float> &p, const LaunchOptions &opt, cudaStream_t stream) {
+    auto kernel = step_tma_push_kernel<S, COLL>;
+    static const int env_ctas = [] { const char *e = getenv("LBM_B200_TMA_CTAS"); return e ? atoi(e) : 0; }();
+    static const int env_stages = [] { const char *e = getenv("LBM_B200_TMA_STAGES"); return e ? atoi(e) : 0; }();
+    int ctas = S::Q == 9 ? 2 : 1;
+    if (env_ctas >= 1 && env_ctas <= tma_ctas_per_sm<S>()) ctas = env_ctas;
+    const size_t per_cta = (227 * 1024) / ctas - (ctas > 1 ? 1024 : 0) - 1024;
+    int max_stages = (int)(per_cta / (tma_push_stage_floats<S>() * sizeof(float)));
+    if (max_stages > kTmaMaxStages) max_stages = kTmaMaxStages;
+    int stages = max_stages < 5 ? max_stages : 5;
+    if (env_stages >= 2 && env_stages <= max_stages) stages = env_stages;
+    if (stages < 2) return LBM_ERR_UNSUPPORTED;
+    const size_t smem = tma_push_smem_bytes<S>(stages);
+    static size_t configured = 0;
+    if (smem > configured) {
+        const int e = (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return e;
+        configured = smem;
+    }
+    TmaParams t = {};
+    t.in = p.in; t.out = p.out; t.N = p.N;
+    t.counters = opt.tma_counters;
+    t.n0 = p.n0; t.n1 = p.n1; t.n2 = p.n2;
+    t.tz = tma_row_extent(p.n2);
+    t.tz_log2 = 0;
+    while ((1 << t.tz_log2) < t.tz) ++t.tz_log2;
+    t.rows = kTmaTileNodes / t.tz;
+    t.zchunks = p.n2 / t.tz;
+    t.row_begin = 0;
+    t.n_rows = p.n0 * p.n1;
+    t.n_tiles = ((t.n_rows + t.rows - 1) / t.rows) * t.zchunks;
+    t.stages = stages;
+    t.boxable = opt.tma_boxable;
+    t.reverse = p.reverse_sweep;
+    t.ca = p.ca; t.cb = p.cb; t.force = p.force;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(t.n_tiles < opt.sm_count * ctas ? t.n_tiles : opt.sm_count * ctas);
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = opt.chained ? 1 : 0;
+    const int e = (int)cudaLaunchKernelEx(&cfg, kernel, *opt.tma, t);
+    ++g_launch_count;
+    return e;
+}
+
 template <class S, class R, int COLL, bool PULL, bool PUSH>
 int by_lanes(const StepParams<R> &p, const LaunchOptions &opt, cudaStream_t stream) {
+    if constexpr (sizeof(R) == 4 && !PULL && PUSH) {
+        if (opt.tma && !p.sync.on && p.reduce_mode == kReduceNone) {
+            int e = launch_tma_push<S, COLL>(p, opt, stream);
+            if (e || !(p.labels != nullptr && p.n_general > 0)) return e;
+            return launch_dependent<R>(p.nested_outlets ? general_nodes_kernel<S, R, COLL, PULL, PUSH, true>
+                                                        : general_nodes_kernel<S, R, COLL, PULL, PUSH, false>,
+                                       dim3(sparse_blocks(p.n_general)), dim3(kSparseThreads), p, stream);
+        }
+    }
     if constexpr (sizeof(R) == 4 && !PUSH) {
         if (opt.tma && opt.tma_interior && p.sync.on && p.reduce_mode == kReduceNone && p.labels == nullptr) {
             // Multi-GPU slab: the two cut planes by the lock-step LDG kernel (it waits for the neighbours' progress

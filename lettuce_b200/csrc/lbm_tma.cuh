@@ -427,4 +427,243 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The pushing step (POST_STREAMING, the default of lettuce's Simulation) on the same machinery.
+//
+// A bulk tensor store cannot write a row shifted by one element along z either (16-byte box starts), and the element
+// that would arrive at the row's first / last position comes from a node of the NEIGHBOURING tile.  So every tile
+// also loads the quads next to its rows' ends -- for ALL populations -- and a ninth consumer warp ("halo warp")
+// collides those 2 x rows neighbour nodes itself, one node per lane, next to the eight warps that do the tile's own
+// nodes two per thread: overlapped tiling, ~1 % redundant arithmetic and bytes.  The consumers then write their results
+// into the rows shifted by e_z in shared memory (position k of a row = what arrives at z0 + k), and the producers store
+// every row with one aligned box at its destination (x + e_x, y + e_y, z0): no scalar stores, no second pass.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTmaPushProducers = 3;                       // producer warps of the pushing kernel (384 threads in all)
+constexpr int kTmaPushConsumers = kTmaConsumers + 32;      // + the halo warp
+template <class S>
+constexpr int tma_push_stage_floats() { return S::Q * (kTmaTileNodes + 2 * kTmaHaloSlot); }
+template <class S>
+constexpr size_t tma_push_smem_bytes(int stages) { return (size_t)stages * tma_push_stage_floats<S>() * sizeof(float); }
+
+template <class S, int COLL>
+__global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm<S>())
+    step_tma_push_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaParams p) {
+    constexpr int Q = S::Q;
+    constexpr int T = kTmaTileNodes;
+    constexpr int kStageFloats = tma_push_stage_floats<S>();
+    static_assert(kTmaPushConsumers + 32 * kTmaPushProducers == kTmaThreads, "thread roles");
+    extern __shared__ __align__(128) float stage0[];
+    __shared__ __align__(8) unsigned long long full_bar[kTmaMaxStages], done_bar[kTmaMaxStages], ring_bar[kTmaRing];
+    __shared__ TileInfo ring[kTmaRing];
+    if (threadIdx.x == 0 && (tma::smem_addr(stage0) & 127u)) __trap();
+
+    if (!p.skip_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const int NS = p.stages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            tma::mbar_init(tma::smem_addr(&full_bar[s]), Q);
+            tma::mbar_init(tma::smem_addr(&done_bar[s]), kTmaPushConsumers);
+        }
+        for (int s = 0; s < kTmaRing; ++s) tma::mbar_init(tma::smem_addr(&ring_bar[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma::fence_async_shared();
+    }
+    __syncthreads();
+
+    auto tile = [&](int i) {
+        tma::mbar_wait(tma::smem_addr(&ring_bar[i % kTmaRing]), (uint32_t)(i / kTmaRing) & 1u);
+        return ring[i % kTmaRing];
+    };
+    // halo quads of a stage: per population a slot for the quads in front of the rows (lo: z0 - 4 .. z0 - 1) and one
+    // for the quads behind them (hi: z0 + tz .. z0 + tz + 3), a quad per tile row each
+    auto halo_of = [&](float *st, int q, int side) { return st + Q * T + (q * 2 + side) * kTmaHaloSlot; };
+
+    if (threadIdx.x >= kTmaPushConsumers) {
+        // ------------------------------------------------------------------ producers: one thread per population
+        const int pt = threadIdx.x - kTmaPushConsumers;
+        const int q = (pt >> 5) + kTmaPushProducers * (pt & 31);
+        if (q >= Q) return;
+        const int e0 = velocity_component<S>(q, 0), e1 = velocity_component<S>(q, 1);
+        const uint32_t row_bytes = (uint32_t)p.tz * sizeof(float);
+        const bool rows_along_y = p.n1 > 1;
+        const bool claimer = q == 0;
+        int claimed = 0;
+        bool exhausted = false;
+        auto publish = [&](unsigned k) {
+            TileInfo info;
+            if (k >= (unsigned)p.n_tiles) {
+                info.z0 = info.x0 = info.y0 = 0;
+                info.r0 = -1;
+                if (!exhausted) {
+                    exhausted = true;
+                    if (atomicAdd(p.counters + 1, 1u) == gridDim.x - 1) {
+                        p.counters[0] = 0;
+                        p.counters[1] = 0;
+                    }
+                }
+            } else {
+                const int t = p.reverse ? p.n_tiles - 1 - (int)k : (int)k;
+                const int zc = t % p.zchunks;
+                info.z0 = zc << p.tz_log2;
+                info.r0 = p.row_begin + (t / p.zchunks) * p.rows;
+                info.x0 = info.r0 / p.n1;
+                info.y0 = info.r0 - info.x0 * p.n1;
+            }
+            ring[claimed % kTmaRing] = info;
+            tma::mbar_arrive(tma::smem_addr(&ring_bar[claimed % kTmaRing]));
+            ++claimed;
+        };
+        if (claimer) {
+            const unsigned k0 = atomicAdd(p.counters, (unsigned)NS);
+            for (int i = 0; i < NS; ++i) publish(exhausted ? 0xffffffffu : k0 + i);
+        }
+        auto issue_loads = [&](int i, const TileInfo &ti) {
+            const int s = i % NS;
+            const int rows = min(p.rows, p.n_rows - ti.r0);
+            const uint32_t bar = tma::smem_addr(&full_bar[s]);
+            float *st = stage0 + (size_t)s * kStageFloats;
+            float *pop = st + q * T;
+            tma::mbar_arrive_expect_tx(bar, (uint32_t)rows * (row_bytes + 32u));
+            int zlo = ti.z0 - 4, zhi = ti.z0 + p.tz;             // the neighbours across the rows' ends, periodic
+            if (zlo < 0) zlo += p.n2;
+            if (zhi >= p.n2) zhi -= p.n2;
+            if (p.boxable && rows == p.rows) {                   // (the rows at their own place: never a wrap)
+                tma::load_4d(tma::smem_addr(pop), &maps.in_box, ti.z0, ti.y0, ti.x0, q, bar);
+                tma::load_4d(tma::smem_addr(halo_of(st, q, 0)), &maps.in_halo, zlo, ti.y0, ti.x0, q, bar);
+                tma::load_4d(tma::smem_addr(halo_of(st, q, 1)), &maps.in_halo, zhi, ti.y0, ti.x0, q, bar);
+            } else {
+                for (int j = 0; j < rows; ++j) {
+                    const int r = ti.r0 + j;
+                    const int x = r / p.n1, y = r - x * p.n1;
+                    const float *src = p.in + q * p.N + ((int64_t)x * p.n1 + y) * p.n2;
+                    tma::load_4d(tma::smem_addr(pop + (j << p.tz_log2)), &maps.in_row, ti.z0, y, x, q, bar);
+                    tma::load_16(tma::smem_addr(halo_of(st, q, 0) + j * 4), src + zlo, bar);
+                    tma::load_16(tma::smem_addr(halo_of(st, q, 1) + j * 4), src + zhi, bar);
+                }
+            }
+        };
+        auto issue_stores = [&](int i, const TileInfo &ti) {
+            const int s = i % NS;
+            const int rows = min(p.rows, p.n_rows - ti.r0);
+            float *pop = stage0 + (size_t)s * kStageFloats + q * T;
+            // the rows arrive at (x + e_x, y + e_y), still consecutive unless they wrap around the lattice
+            const int xd0 = ti.x0 + e0, yd0 = ti.y0 + e1;
+            const bool box = p.boxable && rows == p.rows &&
+                             (rows_along_y ? (yd0 >= 0 && yd0 + rows <= p.n1) : (xd0 >= 0 && xd0 + rows <= p.n0));
+            if (box) {
+                tma::store_4d(&maps.out_box, ti.z0, yd0, rows_along_y ? wrap(xd0, p.n0) : xd0, q, tma::smem_addr(pop));
+            } else {
+                for (int j = 0; j < rows; ++j) {
+                    const int r = ti.r0 + j;
+                    const int x = r / p.n1, y = r - x * p.n1;
+                    tma::store_4d(&maps.out_row, ti.z0, wrap(y + e1, p.n1), wrap(x + e0, p.n0), q,
+                                  tma::smem_addr(pop + (j << p.tz_log2)));
+                }
+            }
+            tma::store_commit();
+        };
+        int loaded = 0;
+        bool more = true;
+        for (int i = 0; i < NS - 1 && more; ++i) {
+            const TileInfo ti = tile(i);
+            if (ti.r0 < 0) more = false;
+            else { issue_loads(i, ti); ++loaded; }
+        }
+        for (int i = 0; i < loaded; ++i) {
+            const int s = i % NS;
+            const TileInfo ti = ring[i % kTmaRing];
+            tma::mbar_wait(tma::smem_addr(&done_bar[s]), (uint32_t)(i / NS) & 1u);
+            issue_stores(i, ti);
+            if (more) {
+                const int n = i + NS - 1;
+                const TileInfo tn = tile(n);
+                if (tn.r0 < 0) {
+                    more = false;
+                } else {
+                    tma::store_wait_read_1();
+                    issue_loads(n, tn);
+                    ++loaded;
+                    if (claimer) publish(exhausted ? 0xffffffffu : atomicAdd(p.counters, 1u));
+                }
+            }
+        }
+        tma::store_wait_all();
+        return;
+    }
+
+    const int t = threadIdx.x;
+    if (t < kTmaConsumers) {
+        // -------------------------------------------------------------- the tile's own nodes, two per thread
+        const int j = (2 * t) >> p.tz_log2;
+        const int zl = (2 * t) & (p.tz - 1);
+        const int i0 = 2 * t;
+        const bool first = zl == 0, last = zl == p.tz - 2;
+        for (int i = 0;; ++i) {
+            const int s = i % NS;
+            const TileInfo ti = tile(i);
+            if (ti.r0 < 0) break;
+            float *st = stage0 + (size_t)s * kStageFloats;
+            tma::mbar_wait(tma::smem_addr(&full_bar[s]), (uint32_t)(i / NS) & 1u);
+            float2 f[Q];
+            const bool valid = ti.r0 + j < p.n_rows;
+            if (valid) {
+                ForQ<Q>::run([&]<int q>() { f[q] = *reinterpret_cast<const float2 *>(st + q * T + i0); });
+            }
+            // (results are written into the rows the inputs came from, shifted: nobody stores before everybody has loaded)
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmaPushConsumers) : "memory");
+            if (valid) {
+                collide_lanes<S, float2, COLL>(p, f);
+                ForQ<Q>::run([&]<int q>() {
+                    constexpr int e2 = S::e(q, 2);
+                    float *pop = st + q * T + i0;
+                    if constexpr (e2 == 0) {
+                        *reinterpret_cast<float2 *>(pop) = f[q];
+                    } else if constexpr (e2 == 1) {            // arrives at z + 1, z + 2
+                        pop[1] = f[q].x;
+                        if (!last) pop[2] = f[q].y;            // (the row's last node feeds the next tile: its halo warp)
+                    } else {                                   // arrives at z - 1, z
+                        if (!first) pop[-1] = f[q].x;
+                        pop[0] = f[q].y;
+                    }
+                });
+            }
+            tma::fence_async_shared();
+            tma::mbar_arrive(tma::smem_addr(&done_bar[s]));
+        }
+    } else {
+        // -------------------------------------------------------------- halo warp: the nodes beyond the rows' ends
+        const int lane = t - kTmaConsumers;
+        const int j = lane >> 1, side = lane & 1;      // row; 0: node z0 - 1 (feeds position 0), 1: node z0 + tz
+        for (int i = 0;; ++i) {
+            const int s = i % NS;
+            const TileInfo ti = tile(i);
+            if (ti.r0 < 0) break;
+            float *st = stage0 + (size_t)s * kStageFloats;
+            tma::mbar_wait(tma::smem_addr(&full_bar[s]), (uint32_t)(i / NS) & 1u);
+            float g[Q];
+            const bool valid = j < p.rows && ti.r0 + j < p.n_rows;
+            if (valid) {
+                ForQ<Q>::run([&]<int q>() { g[q] = halo_of(st, q, side)[j * 4 + (side ? 0 : 3)]; });
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmaPushConsumers) : "memory");
+            if (valid) {
+                collide_lanes<S, float, COLL>(p, g);
+                float *row = st + (j << p.tz_log2);
+                ForQ<Q>::run([&]<int q>() {
+                    constexpr int e2 = S::e(q, 2);
+                    if constexpr (e2 == 1) {
+                        if (side == 0) row[q * T] = g[q];                    // node z0 - 1 arrives at z0
+                    } else if constexpr (e2 == -1) {
+                        if (side == 1) row[q * T + p.tz - 1] = g[q];         // node z0 + tz arrives at z0 + tz - 1
+                    }
+                });
+            }
+            tma::fence_async_shared();
+            tma::mbar_arrive(tma::smem_addr(&done_bar[s]));
+        }
+    }
+}
+
 }  // namespace lbm

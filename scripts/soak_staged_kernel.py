@@ -49,12 +49,22 @@ def main():
         flow = lt.TaylorGreenVortex(ctx, [2048, 1024], 1600.0, 0.05, stencil=lt.D2Q9())
         return flow, lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], S.PRE_STREAMING)
 
+    def tgv_kbc_post():
+        flow = lt.TaylorGreenVortex(ctx, [256] * 3, 1600.0, 0.05, stencil=lt.D3Q27())
+        return flow, lt.Simulation(flow, lt.KBCCollision(), [], S.POST_STREAMING)
+
+    def sphere_trt_post():
+        flow = make_obstacle(ctx, [256, 128, 128], lt.D3Q27())
+        return flow, lt.Simulation(flow, lt.TRTCollision(flow.units.relaxation_parameter_lu), [], S.POST_STREAMING)
+
     ok = True
     for name, make, n in (("TGV3D D3Q27 KBC 256^3", tgv_kbc, steps), ("sphere D3Q27 TRT 256x128x128", sphere_trt, steps),
-                          ("TGV2D D2Q9 BGK 2048x1024", tgv2d_bgk, steps)):
+                          ("TGV2D D2Q9 BGK 2048x1024", tgv2d_bgk, steps),
+                          ("TGV3D D3Q27 KBC 256^3 POST (pushing kernel)", tgv_kbc_post, steps),
+                          ("sphere D3Q27 TRT 256x128x128 POST (pushing kernel)", sphere_trt_post, steps)):
         t0 = time.perf_counter()
-        ref, ref_name = run(make, 2, n, 97)
-        got, got_name = run(make, 3, n, 61)              # different batch lengths: different launch chaining
+        ref, ref_name = run(make, 2, n, 13)
+        got, got_name = run(make, 3, n, 11)              # different batch lengths: different launch chaining
         same = bool(torch.equal(ref, got))
         finite = bool(torch.isfinite(got).all())
         ok = ok and same and finite

@@ -398,7 +398,7 @@ def test_two_nodes_per_thread_kernel_is_bit_identical(stencil, res, coll, strate
                                               ("D2Q9", [300, 320], "trt"), ("D3Q27", [24, 24, 192], "trt"),
                                               ("D2Q9", [2048, 64], "kbc"), ("D3Q19", [5, 70, 512], "regularized"),
                                               ("D3Q27", [16, 16, 320], "kbc"), ("D3Q19", [12, 32, 256], "bgk")])
-@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING"])
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "NO_STREAMING", "POST_STREAMING"])
 def test_tma_staged_kernel_is_bit_identical(stencil, res, coll, strategy):
     """the TMA-staged persistent kernel (csrc/lbm_tma.cuh: bulk tensor loads of rows shifted in x and y, halo quads
     for the shift along z, partial last tile, several z chunks per row) against the one-node LDG kernel: same bits,
@@ -420,7 +420,7 @@ def test_tma_staged_kernel_is_bit_identical(stencil, res, coll, strategy):
     assert torch.equal(flows[0].f, flows[1].f)
 
 
-@pytest.mark.parametrize("strategy", ["PRE_STREAMING"])
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
 def test_tma_staged_kernel_with_boundaries(strategy):
     from lettuce_b200 import native as nv
     from test_gpu_parity import ObstacleEqOut, make_obstacle
@@ -441,11 +441,11 @@ def test_tma_staged_kernel_with_boundaries(strategy):
 
 
 def test_tma_staged_kernel_refuses_what_it_cannot_run():
-    """variant 3 is an explicit request: a lattice it cannot stage (contiguous extent not a multiple of 32) or a
-    pushing step is an error, never a silent change of kernel"""
+    """variant 3 is an explicit request: a lattice it cannot stage (contiguous extent not a multiple of 64) or a step
+    that both pulls and pushes is an error, never a silent change of kernel"""
     from lettuce_b200 import native as nv
     c = ctx(torch.float32)
-    for res, strategy in (([64, 48, 100], "PRE_STREAMING"), ([64, 48, 128], "POST_STREAMING")):
+    for res, strategy in (([64, 48, 100], "PRE_STREAMING"), ([64, 48, 128], "DOUBLE_STREAMING")):
         flow = lt.TaylorGreenVortex(c, res, 1600.0, 0.05, stencil=lt.D3Q19())
         sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [],
                             lt.StreamingStrategy[strategy])
