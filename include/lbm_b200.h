@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LBM_ABI_VERSION 4
+#define LBM_ABI_VERSION 5
 #define LBM_MAX_OPS 8 /* transformer list length: pre_boundaries + collision + post_boundaries */
 
 typedef enum lbm_status {

@@ -21,9 +21,10 @@
 // over a ring of NS shared-memory stages (full[] barriers: TMA bytes landed; done[] barriers: consumers' results are
 // in shared memory).  The halo quad's address wraps around the contiguous axis like torch.roll does.
 //
-// Used for steps that do not push (PRE_STREAMING, NO_STREAMING) on fp32 lattices whose contiguous extent is a
-// multiple of 64, single GPU, no fused reductions; everything else runs the LDG kernel (a pushing step would have
-// to write rows shifted by one element, which a bulk store cannot do either).  Results are bit-identical to it (same collide code, data movement only).
+// step_tma_kernel takes the steps that do not push (PRE_STREAMING, NO_STREAMING), step_tma_push_kernel at the end of
+// this file the pushing step (POST_STREAMING); fp32 lattices whose contiguous extent is a multiple of 64, the whole
+// lattice on one GPU or the interior planes of a multi-GPU slab (pulling steps).  Everything else runs the LDG kernel.
+// Results are bit-identical to it (same collide code, data movement only).
 #pragma once
 #include <cuda.h>
 

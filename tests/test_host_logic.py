@@ -213,7 +213,7 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(L, sym), f"{sym} declared in include/lbm_b200.h but not exported"
     assert set(native.EXPORTS) == declared
-    assert L.lbm_abi_version() == 4
+    assert L.lbm_abi_version() == 5
     assert b"unsupported" in L.lbm_status_string(-2)
 
 
