@@ -22,6 +22,8 @@ Prints ONE JSON line:
   cpu_baseline        the UNMODIFIED reference (baseline/_ref, lettuce.Simulation on Context('cpu',
                       use_native=False)) timed on this box's host cores on a bounded sample of the workload
   torch_gpu_reference the same unmodified reference on Context('cuda', use_native=False), device-synchronised
+  native_gpu_reference the same unmodified reference on its own generated CUDA kernel (use_native=True), prebuilt
+                      for sm_100a by baseline/build_native.py
 
 `--impl reference` times only the reference's own CPU implementation (stock lettuce.Simulation, all host threads)
 and prints the same line shape; under torchrun only rank 0 works.
@@ -264,6 +266,60 @@ def reference_torch_gpu(config, strategy, n, steps, dev):
     return {"unavailable": "out of memory at every size"}
 
 
+def reference_native_gpu(config, strategy, n, steps, dev):
+    """The unmodified reference on ITS OWN generated CUDA kernel (Context('cuda', use_native=True),
+    lettuce/_simulation.py:172-229, lettuce/cuda_native/_template.py:64-81), prebuilt for sm_100a by
+    baseline/build_native.py.  The generated kernel exists for BGK only and indexes with 32-bit ints, so the cube
+    is the largest of (n, 384, 256) with q * nodes < 2^31; it synchronises the device after every launch itself."""
+    import torch
+    from baseline import reference
+    c = CONFIGS[config]
+    if not reference.available():
+        return {"unavailable": "baseline/_ref is missing"}
+    if c["collision"] != "BGK":
+        return {"unavailable": f"the reference generates no native kernel for {c['collision']} "
+                               "(lettuce/cuda_native/ext/_collision: BGK and NoCollision only)"}
+    lt = reference.load()
+    size = max(s for s in (n, 384, 256, 128) if s <= n and c["q"] * s ** 3 < 2 ** 31)
+    ctx = lt.Context(device=dev, dtype=torch.float32, use_native=True)
+    flow = lt.TaylorGreenVortex(ctx, [size] * 3, RE, MA, stencil=getattr(lt, c["stencil"])())
+    sim = reference.native_simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [],
+                                      lt.StreamingStrategy[strategy])
+    if sim is None:
+        return {"unavailable": "generated module not prebuilt (python baseline/build_native.py)"}
+    sim(3)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    sim(steps)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(flow.f).all()
+    v = steps * size ** 3 / 1e6 / dt
+    return {"value": v, "unit": "MLUPS", "kind": "reference", "steps": steps, "lattice": [size] * 3,
+            "same_config": size == n, "roofline_frac": v * 1e6 * 2 * c["q"] * 4 / 1e9 / measured_hbm_peak()[0],
+            "what": "unmodified lettuce.Simulation (baseline/_ref) on Context('cuda', use_native=True): the "
+                    "reference's generated CUDA kernel (8x8x8 threads, one node per thread, --use_fast_math), "
+                    "compiled for sm_100a from the reference's own generator and setup.py, fp32, this GPU; "
+                    "32-bit indices limit it to q * nodes < 2^31"}
+
+
+def native_leg_in_subprocess(args, n):
+    """reference_native_gpu in a process of its own: a fault inside the reference's kernel (sticky CUDA error) or a
+    module that does not load must not cost the contract line."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", "native_gpu_reference", "--config", args.config,
+           "--strategy", args.strategy, "--size", str(n)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        if out.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"unavailable": f"leg exited {out.returncode}: {out.stderr.strip()[-300:]}"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
 def reference_main(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -400,6 +456,7 @@ def gpu_main(args):
             gc.collect()
             torch.cuda.empty_cache()
         extra["torch_gpu_reference"] = reference_torch_gpu(args.config, args.strategy, n, 5, dev)
+        extra["native_gpu_reference"] = native_leg_in_subprocess(args, n)
     if rank != 0:
         return
     peak, peak_src = measured_hbm_peak()
@@ -492,9 +549,14 @@ def main():
     ap.add_argument("--slab", action="store_true",
                     help="with --gpus 1: run the multi-GPU slab kernel (in-kernel lock step) with the rank as its own "
                          "neighbour, e.g. to profile it under ncu")
+    ap.add_argument("--leg", default=None, choices=["native_gpu_reference"],
+                    help="run one comparison leg alone and print its JSON object (used by the main run)")
     args = ap.parse_args()
     if args.size is None:
         args.size = CONFIGS[args.config]["default_size"]
+    if args.leg == "native_gpu_reference":
+        print(json.dumps(reference_native_gpu(args.config, args.strategy, args.size, 20, "cuda:0")))
+        return
     if args.impl == "reference":
         reference_main(args)
     else:

@@ -201,6 +201,37 @@ def test_reference_simulation_steps_on_the_engine(ref, case, dtype):
     assert err < tol, (case, dtype, err)
 
 
+@pytest.mark.parametrize("strategy", ["PRE_STREAMING", "POST_STREAMING"])
+def test_engine_against_the_references_generated_kernel(ref, strategy):
+    """The kernel this engine replaces (lettuce/cuda_native/_template.py:64-81), generated and compiled by the
+    reference's own tools (baseline/build_native.py), and `native.invoke` installed in the same slot
+    (lettuce/_simulation.py:229) of a second, identical reference Simulation: same populations after 10 steps.
+    (The generated kernel is compiled with --use_fast_math: approximate division, fp32 only here.)"""
+    from baseline import reference
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    strat = ref.StreamingStrategy[strategy]
+    sims = []
+    for use_native in (True, False):
+        ctx = ref.Context(device="cuda", dtype=torch.float32, use_native=use_native)
+        flow = ref.TaylorGreenVortex(ctx, [40, 24, 64], 1600.0, 0.05, stencil=ref.D3Q19())
+        collision = ref.BGKCollision(flow.units.relaxation_parameter_lu)
+        sim = (reference.native_simulation(flow, collision, [], strat) if use_native
+               else ref.Simulation(flow, collision, [], strat))
+        if sim is None:
+            pytest.skip("the reference's generated module is not prebuilt (python baseline/build_native.py)")
+        sims.append((flow, sim))
+    (flow_ref, sim_ref), (flow_eng, sim_eng) = sims
+    assert sim_ref._collide_and_stream.__module__.startswith("lettuce_")        # the generated package's invoke
+    flow_eng.f = flow_ref.f.clone()
+    sim_eng._collide_and_stream = native.invoke
+    sim_ref(10)
+    sim_eng(10)
+    torch.cuda.synchronize()
+    err = max_rel(flow_eng.f.cpu().numpy(), flow_ref.f.cpu().numpy())
+    assert err < 2e-5, (strategy, err)
+
+
 # ------------------------------------------------------------------ operators are callable
 class RandomFlow(lt.ExtFlow):
     def make_resolution(self, resolution, stencil=None):
