@@ -24,6 +24,8 @@ Prints ONE JSON line:
   torch_gpu_reference the same unmodified reference on Context('cuda', use_native=False), device-synchronised
   native_gpu_reference the same unmodified reference on its own generated CUDA kernel (use_native=True), prebuilt
                       for sm_100a by baseline/build_native.py
+  c3_512              (default configuration only) value / roofline / clocks of `bench.py --config c3` (D3Q27 KBC
+                      512^3, BASELINE.json configs[2]) run in a process of its own
 
 `--impl reference` times only the reference's own CPU implementation (stock lettuce.Simulation, all host threads)
 and prints the same line shape; under torchrun only rank 0 works.
@@ -56,12 +58,30 @@ CONFIGS = {
 
 
 def measured_hbm_peak():
+    """HBM copy bandwidth in GB/s from the driver-written MEASURED_PEAKS.json (the sustained figure where the file
+    distinguishes one: the step kernel is timed inside a long run of back-to-back launches), else the fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy bandwidth)"
+            data = json.load(fh)
+        found = []
+
+        def walk(node, trail):
+            if isinstance(node, dict):
+                for k, v in node.items():
+                    walk(v, trail + [str(k).lower()])
+            elif isinstance(node, (int, float)) and not isinstance(node, bool):
+                name = ".".join(trail)
+                if "hbm" in name and 1000.0 <= float(node) <= 9000.0:
+                    found.append((name, float(node)))
+        walk(data, [])
+        for want in ("sustain", "hbm_gbs", "burst", ""):
+            for name, value in found:
+                if want in name:
+                    return value, f"measured (MEASURED_PEAKS.json: {name})"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def ncu_traffic(config: str, size: int, strategy: str):
@@ -303,21 +323,37 @@ def reference_native_gpu(config, strategy, n, steps, dev):
                     "32-bit indices limit it to q * nodes < 2^31"}
 
 
-def native_leg_in_subprocess(args, n):
-    """reference_native_gpu in a process of its own: a fault inside the reference's kernel (sticky CUDA error) or a
-    module that does not load must not cost the contract line."""
-    import subprocess
-    cmd = [sys.executable, os.path.abspath(__file__), "--leg", "native_gpu_reference", "--config", args.config,
-           "--strategy", args.strategy, "--size", str(n)]
+def leg_in_subprocess(cmd_args, timeout=240):
+    """One comparison leg in a process of its own (its memory is returned before the next leg; a fault inside the
+    reference's generated kernel -- a sticky CUDA error -- or a module that does not load cannot cost the contract
+    line).  Returns the last JSON object the child printed."""
+    cmd = [sys.executable, os.path.abspath(__file__)] + [str(a) for a in cmd_args]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
         if out.returncode == 0 and lines:
             return json.loads(lines[-1])
         return {"unavailable": f"leg exited {out.returncode}: {out.stderr.strip()[-300:]}"}
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def native_leg_in_subprocess(args, n):
+    return leg_in_subprocess(["--leg", "native_gpu_reference", "--config", args.config, "--strategy", args.strategy,
+                              "--size", n])
+
+
+def second_config_leg(args):
+    """The D3Q27 KBC configuration (BASELINE.json configs[2], `bench.py --config c3`) as a secondary key of the
+    default line: device-resident value and roofline of its own run, in its own process."""
+    line = leg_in_subprocess(["--config", "c3", "--steps", args.steps, "--warmup", args.warmup, "--quick", "--no-cpu",
+                              "--no-e2e"], timeout=300)
+    if "unavailable" in line:
+        return line
+    return {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"],
+            "lattice": line["config"]["global_lattice"], "roofline": line["roofline"], "clocks": line["clocks"],
+            "gpu_launches": line["gpu_launches"], "note": "python bench.py --config c3 (device-resident leg only)"}
 
 
 def reference_main(args):
@@ -456,7 +492,11 @@ def gpu_main(args):
             gc.collect()
             torch.cuda.empty_cache()
         extra["torch_gpu_reference"] = reference_torch_gpu(args.config, args.strategy, n, 5, dev)
+        gc.collect()
+        torch.cuda.empty_cache()                      # the legs below run in processes of their own
         extra["native_gpu_reference"] = native_leg_in_subprocess(args, n)
+        if args.config == "c2":
+            extra["c3_512"] = second_config_leg(args)
     if rank != 0:
         return
     peak, peak_src = measured_hbm_peak()
@@ -545,7 +585,8 @@ def main():
                     choices=["NO_STREAMING", "PRE_STREAMING", "POST_STREAMING", "DOUBLE_STREAMING"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
-    ap.add_argument("--quick", action="store_true", help="skip the at_256 and torch_gpu_reference legs")
+    ap.add_argument("--quick", action="store_true",
+                    help="skip the at_256, torch_gpu_reference, native_gpu_reference and c3_512 legs")
     ap.add_argument("--slab", action="store_true",
                     help="with --gpus 1: run the multi-GPU slab kernel (in-kernel lock step) with the rank as its own "
                          "neighbour, e.g. to profile it under ncu")
