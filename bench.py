@@ -192,6 +192,10 @@ def reference_cpu(config: str, strategy: str, steps: int, warmup: int, budget_s:
     if not reference.available():
         return _oracle_port_cpu(config, strategy, steps, warmup, budget_s)
     lt = reference.load()
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the reference's torch CPU
+    # path on ONE thread (measured: 1.7 instead of 12 MLUPS) -- the environment variable only sets the default
+    if torch.get_num_threads() < cores:
+        torch.set_num_threads(cores)
     threads = torch.get_num_threads()
 
     def run(n, k, w):
