@@ -426,9 +426,40 @@ def kbc_fp32_floor_case():
     save("kbc_fp32_floor", **out)
 
 
+def pre_boundary_case():
+    """A boundary BEFORE the collision (`Flow.pre_boundaries`): `collision_index` is 1, and because the reference
+    fills the no-streaming mask with `collision_index` (lettuce/_simulation.py:104-107) every
+    slot of every node is frozen -- nothing streams, every node is a "general" node of the engine's sparse kernel."""
+    ctx = lt.Context(device="cpu", dtype=torch.float64, use_native=False)
+    out = {}
+    for stencil, res in (("D2Q9", [24, 16]), ("D3Q19", [12, 8, 16])):
+        solid = np.zeros(res, dtype=bool)
+        solid[3:6, 2:5] = True
+
+        class PreFlow(lt.TaylorGreenVortex):
+            @property
+            def pre_boundaries(self):
+                return [lt.BounceBackBoundary(torch.tensor(solid))]
+
+        flow = PreFlow(ctx, list(res), 100.0, 0.05, stencil=STENCILS[stencil]())
+        f0 = npy(flow.f).copy()
+        out[f"{stencil}_f0"], out[f"{stencil}_solid"] = f0, solid
+        out[f"{stencil}_tau"] = np.float64(flow.units.relaxation_parameter_lu)
+        for sname in ("POST_STREAMING", "PRE_STREAMING"):
+            flow.f = ctx.convert_to_tensor(f0.copy())
+            sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [], STRATS[sname])
+            assert sim.collision_index == 1 and bool((sim.no_streaming_mask == 1).all())
+            sim(6)
+            out[f"{stencil}_{sname}"] = npy(flow.f)
+    save("pre_boundary", **out)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["kbc_floor"]:
         kbc_fp32_floor_case()
+        sys.exit(0)
+    if sys.argv[1:] == ["pre_boundary"]:
+        pre_boundary_case()
         sys.exit(0)
     if sys.argv[1:] == ["ebb"]:
         ebb_cases()
@@ -473,3 +504,4 @@ if __name__ == "__main__":
     more_flows_case()
     ebb_random_links_case()
     kbc_fp32_floor_case()
+    pre_boundary_case()

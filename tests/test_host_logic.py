@@ -630,3 +630,23 @@ def test_hdf5_reporter_with_a_stand_in_h5py(tmp_path, monkeypatch):
     assert rec["attrs"]["data"] == "3" and rec["attrs"]["steps"] == "4" and rec["attrs"]["note"] == "x"
     import pickle
     assert pickle.loads(bytes(rec["attrs"]["_collision"]))["cls"] == "BGKCollision"
+
+
+def test_pre_boundary_masks_follow_the_reference_quirk():
+    """`Flow.pre_boundaries`: collision_index = 1 and BOTH masks start from collision_index
+    (lettuce/_simulation.py:104-107) -- the no-streaming mask is 1 everywhere."""
+    g = load_golden("pre_boundary")
+    solid = g["D2Q9_solid"]
+    mask = torch.tensor(solid)
+
+    class PreFlow(lt.TaylorGreenVortex):
+        @property
+        def pre_boundaries(self):
+            return [lt.BounceBackBoundary(mask)]
+
+    flow = PreFlow(cpu(), list(solid.shape), 100.0, 0.05, stencil=lt.D2Q9())
+    assert max_rel(flow.f.numpy(), g["D2Q9_f0"]) < 1e-14
+    sim = lt.Simulation(flow, lt.BGKCollision(flow.units.relaxation_parameter_lu), [])
+    assert sim.collision_index == 1 and len(sim.transformer) == 2
+    assert bool((sim.no_streaming_mask == 1).all())
+    assert np.array_equal(sim.no_collision_mask.numpy(), np.where(solid, 0, 1).astype(np.uint8))
